@@ -1,0 +1,227 @@
+"""Thin Python binding of the C-ABI (include/okvis_b200.h) -- the same calls a C++ host (the OKVIS
+Estimator/Frontend shims) makes.  No numerics live here."""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = abi.load_library()
+    return _lib
+
+
+class OkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("okb error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """okb_ctx: device memory for `max_windows` resident keyframe windows + the frontend buffers."""
+
+    def __init__(self, device=0, max_windows=1):
+        self._h = C.c_void_p()
+        rc = lib().okb_ctx_create(int(device), int(max_windows), C.byref(self._h))
+        if rc != 0:
+            raise OkbError(rc, lib().okb_last_error(None).decode())
+        self.max_windows = max_windows
+        self._windows = {}
+
+    def close(self):
+        if self._h:
+            lib().okb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise OkbError(rc, lib().okb_last_error(self._h).decode())
+
+    @property
+    def kernel_launches(self):
+        return int(lib().okb_kernel_launches(self._h))
+
+    @property
+    def stream(self):
+        return lib().okb_stream(self._h)
+
+    # ---------------------------------------------------------------- estimator path
+    def upload(self, win, window):
+        d = window.desc()
+        self._check(lib().okb_window_upload(self._h, int(win), C.byref(d)))
+        self._windows[win] = window
+
+    def reset(self, first=0, count=1):
+        self._check(lib().okb_window_reset(self._h, int(first), int(count)))
+
+    @staticmethod
+    def _options(max_iterations, min_iterations, time_limit_s, use_cauchy_loss):
+        o = abi.SolveOptions()
+        o.max_iterations, o.min_iterations, o.time_limit_s, o.use_cauchy_loss = (max_iterations, min_iterations,
+                                                                                time_limit_s, use_cauchy_loss)
+        return o
+
+    def optimize(self, first=0, count=1, max_iterations=10, min_iterations=0, time_limit_s=-1.0, use_cauchy_loss=1):
+        o = self._options(max_iterations, min_iterations, time_limit_s, use_cauchy_loss)
+        out = (abi.Summary * count)()
+        self._check(lib().okb_optimize(self._h, int(first), int(count), C.byref(o), out))
+        return [s.as_dict() for s in out]
+
+    def optimize_async(self, first=0, count=1, max_iterations=10, min_iterations=0, time_limit_s=-1.0,
+                       use_cauchy_loss=1):
+        o = self._options(max_iterations, min_iterations, time_limit_s, use_cauchy_loss)
+        self._check(lib().okb_optimize_async(self._h, int(first), int(count), C.byref(o)))
+
+    def optimize_finish(self, first=0, count=1):
+        out = (abi.Summary * count)()
+        self._check(lib().okb_optimize_finish(self._h, int(first), int(count), out))
+        return [s.as_dict() for s in out]
+
+    def download(self, win, with_quality=True):
+        w = self._windows[win]
+        poses, sb, lms = np.zeros_like(w.poses), np.zeros_like(w.speed_bias), np.zeros_like(w.landmarks)
+        q = np.zeros(len(w.landmarks)) if with_quality else None
+        self._check(lib().okb_window_download(self._h, int(win), _p(poses), _p(sb), _p(lms), _p(q)))
+        return dict(poses=poses, speed_bias=sb, landmarks=lms, quality=q)
+
+    # ---------------------------------------------------------------- single-block hooks
+    def eval_reprojection(self, cam, pose, lm, ext, z, sqrt_info):
+        pose, lm, ext, z, sqrt_info = map(_f64, (pose, lm, ext, z, sqrt_info))
+        n = len(pose)
+        cam_arr = np.array([cam], dtype=abi.camera_dtype)
+        r, J0, J1, J2 = np.zeros((n, 2)), np.zeros((n, 2, 6)), np.zeros((n, 2, 3)), np.zeros((n, 2, 6))
+        self._check(lib().okb_eval_reprojection(self._h, n, _p(cam_arr), _p(pose), _p(lm), _p(ext), _p(z),
+                                                _p(sqrt_info), _p(r), _p(J0), _p(J1), _p(J2)))
+        return r, J0, J1, J2
+
+    def eval_imu(self, params, samples, t0_ns, t1_ns, pose0, sb0, pose1, sb1, sb_ref=None):
+        a = [_f64(x) for x in (pose0, sb0, pose1, sb1)]
+        ref = _f64(sb_ref) if sb_ref is not None else None
+        samples = np.ascontiguousarray(samples)
+        r = np.zeros(15)
+        J = [np.zeros((15, 6)), np.zeros((15, 9)), np.zeros((15, 6)), np.zeros((15, 9))]
+        sq = np.zeros((15, 15))
+        rc = lib().okb_eval_imu(self._h, C.byref(params), _p(samples), len(samples), C.c_int64(int(t0_ns)),
+                                C.c_int64(int(t1_ns)), *[_p(x) for x in a], _p(ref), _p(r), *[_p(j) for j in J], _p(sq))
+        if rc < 0:
+            self._check(rc)
+        return r, J, sq, rc
+
+    def imu_propagate(self, params, samples, t0_ns, t1_ns, pose, sb, want_cov=True):
+        pose, sb = np.array(pose, dtype=np.float64), np.array(sb, dtype=np.float64)
+        samples = np.ascontiguousarray(samples)
+        P, F = np.zeros((15, 15)), np.zeros((15, 15))
+        n = C.c_int(0)
+        self._check(lib().okb_imu_propagate(self._h, C.byref(params), _p(samples), len(samples), C.c_int64(int(t0_ns)),
+                                            C.c_int64(int(t1_ns)), _p(pose), _p(sb), _p(P) if want_cov else None, _p(F),
+                                            C.byref(n)))
+        return n.value, pose, sb, P, F
+
+    def eval_pose_error(self, meas, sqrt_info, pose):
+        r, J = np.zeros(6), np.zeros((6, 6))
+        self._check(lib().okb_eval_pose_error(self._h, _p(_f64(meas)), _p(_f64(sqrt_info)), _p(_f64(pose)), _p(r), _p(J)))
+        return r, J
+
+    def eval_speed_bias_error(self, meas, sqrt_info, sb):
+        r, J = np.zeros(9), np.zeros((9, 9))
+        self._check(lib().okb_eval_speed_bias_error(self._h, _p(_f64(meas)), _p(_f64(sqrt_info)), _p(_f64(sb)), _p(r),
+                                                    _p(J)))
+        return r, J
+
+    def eval_relative_pose(self, sqrt_info, pose0, pose1):
+        r, J0, J1 = np.zeros(6), np.zeros((6, 6)), np.zeros((6, 6))
+        self._check(lib().okb_eval_relative_pose(self._h, _p(_f64(sqrt_info)), _p(_f64(pose0)), _p(_f64(pose1)), _p(r),
+                                                 _p(J0), _p(J1)))
+        return r, J0, J1
+
+    def eval_marginalization(self, marg, x):
+        m = abi.MargPrior()
+        m.n, m.n_blocks = int(marg["J"].shape[0]), len(marg["block_kind"])
+        m.block_kind = marg["block_kind"].ctypes.data_as(C.POINTER(C.c_int32))
+        m.block_idx = marg["block_idx"].ctypes.data_as(C.POINTER(C.c_uint32))
+        m.x0, m.J, m.e0 = abi.dptr(marg["x0"]), abi.dptr(marg["J"]), abi.dptr(marg["e0"])
+        r, J = np.zeros(m.n), np.zeros((m.n, m.n))
+        self._check(lib().okb_eval_marginalization(self._h, C.byref(m), _p(_f64(x)), _p(r), _p(J)))
+        return r, J
+
+    # ---------------------------------------------------------------- frontend path
+    def hamming_match(self, A, B, skipA=None, skipB=None, threshold=60.0, num_best=4, use_ratio=False,
+                      ratio_threshold=3.0):
+        A = np.ascontiguousarray(A, dtype=np.uint8)
+        B = np.ascontiguousarray(B, dtype=np.uint8)
+        nA, nB, nbytes = A.shape[0], B.shape[0], A.shape[1]
+        topk = np.zeros((nA, num_best), abi.pair_dtype)
+        pairs = np.zeros(nB, abi.pair_dtype)
+        sa = np.ascontiguousarray(skipA, dtype=np.uint8) if skipA is not None else None
+        sb = np.ascontiguousarray(skipB, dtype=np.uint8) if skipB is not None else None
+        self._check(lib().okb_hamming_match(self._h, _p(A), nA, _p(B), nB, nbytes, _p(sa), _p(sb), C.c_float(threshold),
+                                            num_best, int(use_ratio), C.c_float(ratio_threshold), _p(topk), _p(pairs)))
+        return dict(topk=topk, pairs=pairs)
+
+    def hamming_candidates(self, A, B, threshold=60.0, cap=None):
+        A = np.ascontiguousarray(A, dtype=np.uint8)
+        B = np.ascontiguousarray(B, dtype=np.uint8)
+        nA, nB, nbytes = A.shape[0], B.shape[0], A.shape[1]
+        cap = cap or nA * nB
+        row_ptr = np.zeros(nA + 1, np.uint32)
+        col = np.zeros(cap, np.uint32)
+        dist = np.zeros(cap, np.uint16)
+        rc = lib().okb_hamming_candidates(self._h, _p(A), nA, _p(B), nB, nbytes, C.c_float(threshold), _p(row_ptr),
+                                          _p(col), _p(dist), cap)
+        self._check(rc)
+        n = int(row_ptr[-1])
+        return row_ptr, col[:n].copy(), dist[:n].copy()
+
+    def detect_describe(self, img, cam, R_CW, uniformity_radius=40.0, absolute_threshold=800.0, max_keypoints=400,
+                        desc_bytes=48, rotation_invariance=True, cam_slot=0):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        prm = abi.DetectParams()
+        prm.uniformity_radius, prm.absolute_threshold = uniformity_radius, absolute_threshold
+        prm.max_keypoints, prm.desc_bytes, prm.rotation_invariance = max_keypoints, desc_bytes, int(rotation_invariance)
+        cam_arr = np.array([cam], dtype=abi.camera_dtype)
+        R = _f64(np.asarray(R_CW).reshape(9))
+        kps = np.zeros(max_keypoints, abi.keypoint_dtype)
+        desc = np.zeros((max_keypoints, desc_bytes), np.uint8)
+        n = C.c_int(0)
+        self._check(lib().okb_detect_describe(self._h, int(cam_slot), _p(img), w, h, img.strides[0], _p(cam_arr), _p(R),
+                                              C.byref(prm), _p(kps), _p(desc), max_keypoints, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+
+def matches_from_pairs(pairs, topk, threshold, use_ratio=False, ratio_threshold=3.0):
+    """The serial epilogue of DenseMatcher::matchBody (DenseMatcher.hpp(impl):97-122): turns the per-B
+    winners into the ordered (A, B, distance) callback list.  Pure bookkeeping on the host side of the
+    boundary, exactly where the reference runs setBestMatch."""
+    out = []
+    for b in range(len(pairs)):
+        a, dist = int(pairs[b]["index_a"]), float(pairs[b]["distance"])
+        if not dist < threshold:
+            continue
+        if use_ratio:
+            bl = topk[a]
+            if bl[1]["index_a"] != -1:
+                d0, d1 = float(bl[0]["distance"]), float(bl[1]["distance"])
+                if not (d0 == 0 or d1 / d0 > ratio_threshold):
+                    continue
+        out.append((a, b, dist))
+    return out

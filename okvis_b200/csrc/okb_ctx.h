@@ -1,0 +1,42 @@
+// Opaque context behind the C-ABI handle (host side).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "okb_estimator.cuh"
+
+struct WinStore {
+  unsigned char* arena = nullptr;     // device
+  size_t arena_bytes = 0;
+  unsigned char* staging = nullptr;   // pinned host mirror of the arena's input region
+  size_t staging_bytes = 0;
+  size_t h2d_bytes = 0;
+  bool uploaded = false;
+};
+
+struct okb_frontend_state;
+
+struct okb_ctx {
+  int device = 0;
+  int max_windows = 0;
+  int sm_count = 148;
+  int smem_optin = 0;
+  int chunk_cap = 1;
+  cudaStream_t stream = nullptr;
+  std::vector<WinStore> wins;
+  std::vector<okb::WinDev> host;      // host mirror of d_wins
+  okb::WinDev* d_wins = nullptr;
+  okb::SolverState* d_states = nullptr;
+  okb::SolverState* h_states = nullptr;  // pinned
+  okb_solve_options last_opt{};
+  void* hook_buf = nullptr;
+  size_t hook_bytes = 0;
+  okb_frontend_state* frontend = nullptr;
+  int64_t launches = 0;
+  std::string error;
+  void set_error(const std::string& e) { error = e; }
+};
+
+void okb_frontend_release(okb_ctx* c);

@@ -1,0 +1,733 @@
+// Host side of the estimator path of libokvis_b200.so: context, window packing/upload, the solver
+// launch sequence, download, and the single-residual-block test hooks.  C-ABI: include/okvis_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "okb_ctx.h"
+#include "okb_kernels.cuh"
+
+using namespace okb;
+
+static std::string g_create_error;
+
+#define OKB_CUDA(ctx, call)                                                                             \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      (ctx)->set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                             \
+      return OKB_ERR_CUDA;                                                                              \
+    }                                                                                                   \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
+  if (!out || max_windows < 1) return OKB_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return OKB_ERR_NO_DEVICE;
+  }
+  if (device_id < 0 || device_id >= n) { g_create_error = "bad device id"; return OKB_ERR_INVALID_ARG; }
+  okb_ctx* c = new okb_ctx();
+  c->device = device_id;
+  c->max_windows = max_windows;
+  if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cudaSetDevice / cudaStreamCreate failed";
+    delete c;
+    return OKB_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device_id);
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  c->wins.resize(max_windows);
+  c->host.assign(max_windows, WinDev());
+  std::memset(c->host.data(), 0, sizeof(WinDev) * max_windows);
+  c->chunk_cap = std::max(1, std::min(kMaxChunks, (2 * c->sm_count) / max_windows));
+  if (cudaMalloc(&c->d_wins, sizeof(WinDev) * max_windows) != cudaSuccess ||
+      cudaMalloc(&c->d_states, sizeof(SolverState) * max_windows) != cudaSuccess ||
+      cudaMallocHost(&c->h_states, sizeof(SolverState) * max_windows) != cudaSuccess) {
+    g_create_error = "cudaMalloc failed";
+    delete c;
+    return OKB_ERR_CUDA;
+  }
+  cudaMemset(c->d_states, 0, sizeof(SolverState) * max_windows);
+  cudaFuncSetAttribute(k_landmarks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_landmarks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_quality, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  *out = c;
+  return OKB_OK;
+}
+
+extern "C" void okb_ctx_destroy(okb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& w : c->wins) {
+    if (w.arena) cudaFree(w.arena);
+    if (w.staging) cudaFreeHost(w.staging);
+  }
+  okb_frontend_release(c);
+  if (c->d_wins) cudaFree(c->d_wins);
+  if (c->d_states) cudaFree(c->d_states);
+  if (c->h_states) cudaFreeHost(c->h_states);
+  if (c->hook_buf) cudaFree(c->hook_buf);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" const char* okb_last_error(const okb_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+extern "C" int64_t okb_kernel_launches(const okb_ctx* c) { return c ? c->launches : 0; }
+extern "C" void* okb_stream(const okb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+// window packing
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct ArenaPlan {
+  size_t total = 0;
+  size_t take(size_t bytes) {
+    const size_t o = total;
+    total = align_up(total + bytes, 256);
+    return o;
+  }
+};
+}  // namespace
+
+extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) {
+  if (!c || !D || win < 0 || win >= c->max_windows) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  const int K = D->n_poses, NSB = D->n_speed_bias, NE = D->n_extrinsics, L = D->n_landmarks, NC = D->n_cameras;
+  if (K < 1 || L < 1 || NC < 1 || NE < 1) { c->set_error("empty window"); return OKB_ERR_INVALID_ARG; }
+  if (K > kMaxFrames) { c->set_error("more than 32 frames per window"); return OKB_ERR_CAPACITY; }
+  for (int e = 0; e < NE; ++e)
+    if (!D->extrinsics_fixed || !D->extrinsics_fixed[e]) {
+      c->set_error("device solver requires fixed extrinsics (sigma_absolute_* = 0 as in the shipped configs)");
+      return OKB_ERR_UNSUPPORTED;
+    }
+  if (D->n_relpose_terms > 0) { c->set_error("relative-pose terms need free extrinsics"); return OKB_ERR_UNSUPPORTED; }
+  int CP = 1;
+  while (CP < NC) CP <<= 1;
+  if (CP > 32) { c->set_error("more than 32 cameras"); return OKB_ERR_CAPACITY; }
+  const int NS = K * CP, NG = (NS + 31) / 32, NSP = NG * 32;
+  const int dc = 6 * K, d = dc + 9 * NSB, dcp = 4 * ((dc + 1 + 3) / 4);
+  if (d > kMaxDense) { c->set_error("reduced system too large"); return OKB_ERR_CAPACITY; }
+  const int NT = dcp / 4, NTT = NT * (NT + 1) / 2;
+  if (NTT > 2 * A_THREADS) { c->set_error("too many frames for the Schur tile kernel"); return OKB_ERR_CAPACITY; }
+  int marg_n = 0, marg_nb = 0, marg_xdim = 0;
+  if (D->marg && D->marg->n > 0) {
+    marg_n = D->marg->n; marg_nb = D->marg->n_blocks;
+    if (marg_n > kMaxMarg) { c->set_error("marginalisation prior too large"); return OKB_ERR_CAPACITY; }
+    for (int b = 0; b < marg_nb; ++b) marg_xdim += (D->marg->block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
+  }
+  const size_t smA = smemA_bytes(NSP, K, dcp);
+  if (smA > (size_t)c->smem_optin) { c->set_error("window does not fit kernel A shared memory"); return OKB_ERR_CAPACITY; }
+
+  // ---- arena plan: [inputs (copied from the staging buffer)] [scratch]
+  ArenaPlan P;
+  WinDev W;
+  std::memset(&W, 0, sizeof W);
+  W.K = K; W.NSB = NSB; W.NE = NE; W.L = L; W.NC = NC; W.CP = CP; W.NS = NS; W.NG = NG; W.NSP = NSP;
+  W.d = d; W.dc = dc; W.dcp = dcp;
+  W.n_imu = D->n_imu_terms; W.n_samples = D->n_imu_samples; W.n_pp = D->n_pose_priors; W.n_sbp = D->n_sb_priors;
+  W.marg_n = marg_n; W.marg_nb = marg_nb; W.marg_xdim = marg_xdim;
+  W.n_chunks = 1; W.lm_per_chunk = L; W.use_cauchy = 1;
+  W.imu_params = D->imu_params;
+  const size_t o_pose = P.take(sizeof(double) * 7 * K);
+  const size_t o_sb = P.take(sizeof(double) * 9 * std::max(NSB, 1));
+  const size_t o_ext = P.take(sizeof(double) * 7 * NE);
+  const size_t o_lm = P.take(sizeof(double) * 4 * L);
+  const size_t o_slots = P.take(sizeof(SlotInfo) * NSP);
+  const size_t o_cams = P.take(sizeof(okb_camera) * NC);
+  const size_t o_obsz = P.take(sizeof(double2) * (size_t)L * NSP);
+  const size_t o_obsw = P.take(sizeof(double) * (size_t)L * NSP);
+  const size_t o_vis = P.take(sizeof(uint32_t) * L);
+  const size_t o_imut = P.take(sizeof(okb_imu_term) * std::max(W.n_imu, 1));
+  const size_t o_samp = P.take(sizeof(okb_imu_sample) * std::max(W.n_samples, 1));
+  const size_t o_pp = P.take(sizeof(okb_pose_prior) * std::max(W.n_pp, 1));
+  const size_t o_sbp = P.take(sizeof(okb_sb_prior) * std::max(W.n_sbp, 1));
+  const size_t o_mkind = P.take(sizeof(int32_t) * std::max(marg_nb, 1));
+  const size_t o_midx = P.take(sizeof(uint32_t) * std::max(marg_nb, 1));
+  const size_t o_mcol = P.take(sizeof(int32_t) * std::max(marg_nb, 1));
+  const size_t o_moff = P.take(sizeof(int32_t) * std::max(marg_nb, 1));
+  const size_t o_mx0 = P.take(sizeof(double) * std::max(marg_xdim, 1));
+  const size_t o_mJ = P.take(sizeof(double) * std::max(marg_n * marg_n, 1));
+  const size_t o_me0 = P.take(sizeof(double) * std::max(marg_n, 1));
+  const size_t o_mH0 = P.take(sizeof(double) * std::max(marg_n * marg_n, 1));
+  const size_t input_bytes = P.total;
+  // scratch / state
+  const size_t o_pose_i = P.take(sizeof(double) * 7 * K), o_sb_i = P.take(sizeof(double) * 9 * std::max(NSB, 1));
+  const size_t o_lm_i = P.take(sizeof(double) * 4 * L);
+  const size_t o_pose_c = P.take(sizeof(double) * 7 * K), o_sb_c = P.take(sizeof(double) * 9 * std::max(NSB, 1));
+  const size_t o_lm_c = P.take(sizeof(double) * 4 * L);
+  size_t o_lmg[2], o_lmE[2], o_gd[2], o_Ed[2];
+  for (int b = 0; b < 2; ++b) { o_lmg[b] = P.take(sizeof(double) * 3 * L); o_lmE[b] = P.take(sizeof(double) * 3 * L); }
+  const size_t o_Rinv = P.take(sizeof(double) * 6 * L);
+  const size_t o_M = P.take(sizeof(double) * 6 * (size_t)L * K);
+  const size_t o_gn = P.take(sizeof(double) * 3 * L);
+  const size_t o_scale = P.take(sizeof(double) * 3 * L);
+  const size_t o_quality = P.take(sizeof(double) * L);
+  const int pstride = 4 + 27 * K + dcp * dcp;
+  const size_t o_part = P.take(sizeof(double) * (size_t)pstride * c->chunk_cap);
+  const size_t o_Hd = P.take(sizeof(double) * (size_t)d * d);
+  for (int b = 0; b < 2; ++b) { o_gd[b] = P.take(sizeof(double) * d); o_Ed[b] = P.take(sizeof(double) * d); }
+  const size_t o_ud = P.take(sizeof(double) * d), o_scd = P.take(sizeof(double) * d);
+  const size_t o_chol = P.take(sizeof(double) * (size_t)d * d);
+  const size_t o_cache = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
+  const size_t o_cache_i = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
+
+  WinStore& S = c->wins[win];
+  if (S.arena_bytes < P.total) {
+    if (S.arena) cudaFree(S.arena);
+    S.arena = nullptr; S.arena_bytes = 0;
+    OKB_CUDA(c, cudaMalloc(&S.arena, P.total));
+    S.arena_bytes = P.total;
+  }
+  if (S.staging_bytes < input_bytes) {
+    if (S.staging) cudaFreeHost(S.staging);
+    S.staging = nullptr; S.staging_bytes = 0;
+    OKB_CUDA(c, cudaMallocHost(&S.staging, input_bytes));
+    S.staging_bytes = input_bytes;
+  }
+  unsigned char* H = S.staging;
+  std::memset(H, 0, input_bytes);
+  std::memcpy(H + o_pose, D->poses, sizeof(double) * 7 * K);
+  if (NSB) std::memcpy(H + o_sb, D->speed_bias, sizeof(double) * 9 * NSB);
+  std::memcpy(H + o_ext, D->extrinsics, sizeof(double) * 7 * NE);
+  std::memcpy(H + o_lm, D->landmarks, sizeof(double) * 4 * L);
+  std::memcpy(H + o_cams, D->cameras, sizeof(okb_camera) * NC);
+  if (W.n_imu) std::memcpy(H + o_imut, D->imu_terms, sizeof(okb_imu_term) * W.n_imu);
+  if (W.n_samples) std::memcpy(H + o_samp, D->imu_samples, sizeof(okb_imu_sample) * W.n_samples);
+  if (W.n_pp) std::memcpy(H + o_pp, D->pose_priors, sizeof(okb_pose_prior) * W.n_pp);
+  if (W.n_sbp) std::memcpy(H + o_sbp, D->sb_priors, sizeof(okb_sb_prior) * W.n_sbp);
+  // slots + observation grid
+  SlotInfo* slots = reinterpret_cast<SlotInfo*>(H + o_slots);
+  for (int s = 0; s < NSP; ++s) slots[s] = SlotInfo{0, 0, 0, 0};
+  double2* oz = reinterpret_cast<double2*>(H + o_obsz);
+  double* ow = reinterpret_cast<double*>(H + o_obsw);
+  uint32_t* vis = reinterpret_cast<uint32_t*>(H + o_vis);
+  for (int i = 0; i < D->n_obs; ++i) {
+    const okb_observation& ob = D->obs[i];
+    if ((int)ob.pose_idx >= K || (int)ob.lm_idx >= L || (int)ob.ext_idx >= NE || (int)ob.cam_idx >= NC) {
+      c->set_error("observation index out of range");
+      return OKB_ERR_INVALID_ARG;
+    }
+    const int s = (int)ob.pose_idx * CP + (int)ob.cam_idx;
+    SlotInfo& si = slots[s];
+    if (!si.valid) si = SlotInfo{(int)ob.pose_idx, (int)ob.ext_idx, (int)ob.cam_idx, 1};
+    else if (si.ext_idx != (int)ob.ext_idx) { c->set_error("inconsistent extrinsics block for a (frame,camera) slot"); return OKB_ERR_INVALID_ARG; }
+    const size_t g = (size_t)ob.lm_idx * NSP + s;
+    if (ow[g] != 0.0) { c->set_error("duplicate observation of a landmark in one (frame,camera)"); return OKB_ERR_UNSUPPORTED; }
+    if (!(ob.sqrt_info > 0.0)) { c->set_error("observation with non-positive sqrt information"); return OKB_ERR_INVALID_ARG; }
+    oz[g] = make_double2(ob.z[0], ob.z[1]);
+    ow[g] = ob.sqrt_info;
+    vis[ob.lm_idx] |= (1u << ob.pose_idx);
+  }
+  for (int t = 0; t < W.n_imu; ++t) {
+    const okb_imu_term& T = D->imu_terms[t];
+    if ((int)T.pose0 >= K || (int)T.pose1 >= K || (int)T.sb0 >= NSB || (int)T.sb1 >= NSB ||
+        T.sample_offset + T.sample_count > (uint32_t)W.n_samples || T.sample_count < 2) {
+      c->set_error("IMU term index out of range");
+      return OKB_ERR_INVALID_ARG;
+    }
+  }
+  if (marg_n) {
+    const okb_marg_prior& M = *D->marg;
+    int32_t* mk = reinterpret_cast<int32_t*>(H + o_mkind);
+    uint32_t* mi = reinterpret_cast<uint32_t*>(H + o_midx);
+    int32_t* mc = reinterpret_cast<int32_t*>(H + o_mcol);
+    int32_t* mo = reinterpret_cast<int32_t*>(H + o_moff);
+    int col = 0, xo = 0;
+    for (int b = 0; b < marg_nb; ++b) {
+      mk[b] = M.block_kind[b]; mi[b] = M.block_idx[b]; mo[b] = xo;
+      const bool fixed = (M.block_kind[b] == OKB_BLOCK_EXTRINSICS);   // extrinsics are fixed in the device solver
+      mc[b] = fixed ? -1 : col;
+      if (!fixed) col += (M.block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
+      xo += (M.block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
+    }
+    if (col != marg_n) { c->set_error("marginalisation prior dimension mismatch"); return OKB_ERR_INVALID_ARG; }
+    std::memcpy(H + o_mx0, M.x0, sizeof(double) * marg_xdim);
+    std::memcpy(H + o_mJ, M.J, sizeof(double) * marg_n * marg_n);
+    std::memcpy(H + o_me0, M.e0, sizeof(double) * marg_n);
+    double* H0 = reinterpret_cast<double*>(H + o_mH0);
+    for (int i = 0; i < marg_n; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double s = 0;
+        for (int r = 0; r < marg_n; ++r) s += M.J[(size_t)r * marg_n + i] * M.J[(size_t)r * marg_n + j];
+        H0[(size_t)i * marg_n + j] = s; H0[(size_t)j * marg_n + i] = s;
+      }
+  }
+  unsigned char* A = S.arena;
+  OKB_CUDA(c, cudaMemcpyAsync(A, H, input_bytes, cudaMemcpyHostToDevice, c->stream));
+  // initial-state copies + zeroed caches
+  OKB_CUDA(c, cudaMemcpyAsync(A + o_pose_i, A + o_pose, sizeof(double) * 7 * K, cudaMemcpyDeviceToDevice, c->stream));
+  if (NSB) OKB_CUDA(c, cudaMemcpyAsync(A + o_sb_i, A + o_sb, sizeof(double) * 9 * NSB, cudaMemcpyDeviceToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(A + o_lm_i, A + o_lm, sizeof(double) * 4 * L, cudaMemcpyDeviceToDevice, c->stream));
+  OKB_CUDA(c, cudaMemsetAsync(A + o_cache, 0, sizeof(ImuCache) * std::max(W.n_imu, 1) * 2, c->stream));
+  OKB_CUDA(c, cudaMemsetAsync(A + o_M, 0, sizeof(double) * 6 * (size_t)L * K, c->stream));
+  OKB_CUDA(c, cudaMemsetAsync(A + o_quality, 0, sizeof(double) * L, c->stream));
+
+  auto dp = [&](size_t o) { return reinterpret_cast<double*>(A + o); };
+  W.pose = dp(o_pose); W.sb = dp(o_sb); W.ext = dp(o_ext); W.lm = dp(o_lm);
+  W.pose_init = dp(o_pose_i); W.sb_init = dp(o_sb_i); W.lm_init = dp(o_lm_i);
+  W.pose_c = dp(o_pose_c); W.sb_c = dp(o_sb_c); W.lm_c = dp(o_lm_c);
+  W.slots = reinterpret_cast<SlotInfo*>(A + o_slots);
+  W.cams = reinterpret_cast<okb_camera*>(A + o_cams);
+  W.obs_z = reinterpret_cast<double2*>(A + o_obsz);
+  W.obs_w = dp(o_obsw);
+  W.lm_vis = reinterpret_cast<uint32_t*>(A + o_vis);
+  for (int b = 0; b < 2; ++b) { W.lm_g[b] = dp(o_lmg[b]); W.lm_E[b] = dp(o_lmE[b]); W.gd[b] = dp(o_gd[b]); W.Ed[b] = dp(o_Ed[b]); }
+  W.lm_Rinv = dp(o_Rinv); W.lm_M = dp(o_M); W.lm_gn = dp(o_gn); W.lm_scale = dp(o_scale); W.quality = dp(o_quality);
+  W.partA = dp(o_part); W.partA_stride = pstride;
+  W.Hd = dp(o_Hd); W.ud = dp(o_ud); W.scale_d = dp(o_scd); W.chol = dp(o_chol);
+  W.imu_terms = reinterpret_cast<okb_imu_term*>(A + o_imut);
+  W.samples = reinterpret_cast<okb_imu_sample*>(A + o_samp);
+  W.imu_cache = reinterpret_cast<ImuCache*>(A + o_cache);
+  W.imu_cache_init = reinterpret_cast<ImuCache*>(A + o_cache_i);
+  W.pp = reinterpret_cast<okb_pose_prior*>(A + o_pp);
+  W.sbp = reinterpret_cast<okb_sb_prior*>(A + o_sbp);
+  W.marg_kind = reinterpret_cast<int32_t*>(A + o_mkind);
+  W.marg_idx = reinterpret_cast<uint32_t*>(A + o_midx);
+  W.marg_col = reinterpret_cast<int32_t*>(A + o_mcol);
+  W.marg_off = reinterpret_cast<int32_t*>(A + o_moff);
+  W.marg_x0 = dp(o_mx0); W.marg_J = dp(o_mJ); W.marg_e0 = dp(o_me0); W.marg_H0 = dp(o_mH0);
+  W.st = c->d_states + win;
+  c->host[win] = W;
+  S.uploaded = true;
+  S.h2d_bytes = input_bytes;
+  OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + win, &c->host[win], sizeof(WinDev), cudaMemcpyHostToDevice, c->stream));
+  // the staging buffer is reused by the next upload of this slot: wait for the copy
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OKB_OK;
+}
+
+static int check_range(okb_ctx* c, int first, int count) {
+  if (!c || first < 0 || count < 1 || first + count > c->max_windows) return OKB_ERR_INVALID_ARG;
+  for (int i = first; i < first + count; ++i)
+    if (!c->wins[i].uploaded) { c->set_error("window slot not uploaded"); return OKB_ERR_INVALID_ARG; }
+  return OKB_OK;
+}
+
+extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
+  int rc = check_range(c, first, count);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  k_reset<<<count, 128, 0, c->stream>>>(c->d_wins, first, 1);
+  c->launches += 1;
+  OKB_CUDA(c, cudaGetLastError());
+  return OKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimize
+// ---------------------------------------------------------------------------------------------
+static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_options& opt, int rounds) {
+  int max_chunks = 1, tpt = 1;
+  size_t smA = 0, smS = 0;
+  bool chol_smem = true;
+  for (int i = first; i < first + count; ++i) {
+    const WinDev& W = c->host[i];
+    max_chunks = std::max(max_chunks, W.n_chunks);
+    const int NT = W.dcp / 4;
+    if (NT * (NT + 1) / 2 > A_THREADS) tpt = 2;
+    smA = std::max(smA, smemA_bytes(W.NSP, W.K, W.dcp));
+    if (smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, true) > (size_t)c->smem_optin) chol_smem = false;
+  }
+  for (int i = first; i < first + count; ++i) {
+    const WinDev& W = c->host[i];
+    smS = std::max(smS, smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, chol_smem));
+  }
+  if (smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
+  for (int r = 0; r < rounds; ++r) {
+    const dim3 gridA(max_chunks, count);
+    if (tpt == 1) k_landmarks<1><<<gridA, A_THREADS, smA, c->stream>>>(c->d_wins, first);
+    else k_landmarks<2><<<gridA, A_THREADS, smA, c->stream>>>(c->d_wins, first);
+    k_solve<<<count, S_THREADS, smS, c->stream>>>(c->d_wins, first, opt, chol_smem ? 1 : 0);
+    c->launches += 2;
+  }
+  OKB_CUDA(c, cudaGetLastError());
+  return OKB_OK;
+}
+
+extern "C" int okb_optimize_async(okb_ctx* c, int first, int count, const okb_solve_options* opt) {
+  int rc = check_range(c, first, count);
+  if (rc) return rc;
+  if (!opt || opt->max_iterations < 0) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  // chunking: enough CTAs for ~2 waves when the batch is small
+  for (int i = first; i < first + count; ++i) {
+    WinDev& W = c->host[i];
+    int chunks = (2 * c->sm_count + count - 1) / count;
+    chunks = std::max(1, std::min(chunks, c->chunk_cap));
+    chunks = std::min(chunks, std::max(1, W.L / (2 * A_WARPS)));
+    W.n_chunks = chunks;
+    W.lm_per_chunk = (W.L + chunks - 1) / chunks;
+    W.use_cauchy = opt->use_cauchy_loss ? 1 : 0;
+  }
+  OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + first, &c->host[first], sizeof(WinDev) * count, cudaMemcpyHostToDevice, c->stream));
+  k_reset<<<count, 128, 0, c->stream>>>(c->d_wins, first, 0);
+  c->launches += 1;
+  c->last_opt = *opt;
+  // round 0 linearises at the initial state; each later round judges one step and proposes the next
+  return launch_rounds(c, first, count, *opt, opt->max_iterations + 1);
+}
+
+extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary* out) {
+  int rc = check_range(c, first, count);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  // Rebuild rounds (linear-solver failures) consume rounds without advancing the iteration count:
+  // keep launching until every window reports done (bounded).
+  for (int guard = 0; guard < 64; ++guard) {
+    OKB_CUDA(c, cudaMemcpyAsync(c->h_states + first, c->d_states + first, sizeof(SolverState) * count, cudaMemcpyDeviceToHost, c->stream));
+    OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+    bool all_done = true;
+    for (int i = first; i < first + count; ++i) all_done = all_done && c->h_states[i].done;
+    if (all_done) break;
+    rc = launch_rounds(c, first, count, c->last_opt, 2);
+    if (rc) return rc;
+  }
+  // post-solve landmark quality (Estimator.cpp:880-894)
+  {
+    size_t smQ = 0;
+    for (int i = first; i < first + count; ++i) smQ = std::max(smQ, (size_t)c->host[i].NSP * sizeof(SlotCtx));
+    const int gx = std::max(1, std::min(64, (2 * c->sm_count + count - 1) / count));
+    k_quality<<<dim3(gx, count), 256, smQ, c->stream>>>(c->d_wins, first);
+    c->launches += 1;
+    OKB_CUDA(c, cudaGetLastError());
+  }
+  if (out) {
+    for (int i = 0; i < count; ++i) {
+      const SolverState& s = c->h_states[first + i];
+      okb_summary& o = out[i];
+      o.initial_cost = s.initial_cost; o.final_cost = s.cost; o.iterations = s.iteration;
+      o.num_successful_steps = s.num_successful; o.termination = s.done ? s.termination : OKB_TERM_FAILURE;
+      o.imu_redo_count = s.imu_redo_final; o.final_radius = s.radius; o.solve_time_s = s.solve_time_s;
+    }
+  }
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OKB_OK;
+}
+
+extern "C" int okb_optimize(okb_ctx* c, int first, int count, const okb_solve_options* opt, okb_summary* out) {
+  int rc = okb_optimize_async(c, first, count, opt);
+  if (rc) return rc;
+  return okb_optimize_finish(c, first, count, out);
+}
+
+extern "C" int okb_window_download(okb_ctx* c, int win, double* poses, double* speed_bias, double* landmarks, double* quality) {
+  int rc = check_range(c, win, 1);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  const WinDev& W = c->host[win];
+  if (poses) OKB_CUDA(c, cudaMemcpyAsync(poses, W.pose, sizeof(double) * 7 * W.K, cudaMemcpyDeviceToHost, c->stream));
+  if (speed_bias && W.NSB) OKB_CUDA(c, cudaMemcpyAsync(speed_bias, W.sb, sizeof(double) * 9 * W.NSB, cudaMemcpyDeviceToHost, c->stream));
+  if (landmarks) OKB_CUDA(c, cudaMemcpyAsync(landmarks, W.lm, sizeof(double) * 4 * W.L, cudaMemcpyDeviceToHost, c->stream));
+  if (quality) OKB_CUDA(c, cudaMemcpyAsync(quality, W.quality, sizeof(double) * W.L, cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-block test hooks (ErrorInterface::EvaluateWithMinimalJacobians mirrors)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_hook_reproj(int n, okb_camera cam, const double* pose, const double* lm, const double* ext, const double* z,
+                              const double* sq, double* r, double* J0, double* J1, double* J2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  reproj_full(cam, pose + 7 * i, lm + 4 * i, ext + 7 * i, z + 2 * i, sq[i], r + 2 * i, J0 + 12 * i, J1 + 6 * i, J2 + 12 * i);
+}
+// one warp
+__global__ void k_hook_imu(okb_imu_params prm, const okb_imu_sample* s, int n, int64_t t0, int64_t t1, const double* in /*32*/,
+                           const double* sb_ref, int have_ref, ImuCache* cache, double* out /* r15 | SF 450 | sqrt 225 | redo */) {
+  __shared__ double buf[3 * 225 + 450 + 450 + 16];
+  WarpCtx cx;
+  ImuWork wk{buf, buf + 225, buf + 450};
+  double* F01 = buf + 675; double* SF = buf + 1125; double* r15 = buf + 1575;
+  if (threadIdx.x == 0) { cache->valid = 0; cache->redo_count = 0; for (int k = 0; k < 9; ++k) cache->sb_ref[k] = 0; }
+  __syncwarp();
+  if (have_ref) imu_preintegrate(cx, s, n, prm, t0, t1, sb_ref, cache, wk);
+  const int before = cache->redo_count;
+  __syncwarp();
+  imu_evaluate(cx, s, n, prm, t0, t1, in, in + 7, in + 16, in + 23, cache, wk, F01, (double*)nullptr, r15, SF);
+  for (int e = threadIdx.x; e < 15; e += 32) out[e] = r15[e];
+  for (int e = threadIdx.x; e < 450; e += 32) out[15 + e] = SF[e];
+  for (int e = threadIdx.x; e < 225; e += 32) out[465 + e] = cache->sqrt_info[e];
+  if (threadIdx.x == 0) out[690] = (double)(cache->redo_count - before);
+}
+__global__ void k_hook_propagate(okb_imu_params prm, const okb_imu_sample* s, int n, int64_t t0, int64_t t1, double* io /*16*/,
+                                 double* cov, double* jac, int want_cov, int want_jac, int* n_used) {
+  __shared__ double buf[3 * 225];
+  WarpCtx cx;
+  ImuWork wk{buf, buf + 225, buf + 450};
+  const int steps = imu_propagate(cx, s, n, prm, t0, t1, io, io + 7, want_cov ? cov : nullptr, want_jac ? jac : nullptr, wk);
+  if (threadIdx.x == 0) *n_used = steps;
+}
+__global__ void k_hook_pose(const double* in /* meas7 S36 pose7 */, double* out /* r6 J36 */) {
+  if (threadIdx.x == 0) pose_error(in, in + 7, in + 43, out, out + 6);
+}
+__global__ void k_hook_relpose(const double* in /* S36 p0 p1 */, double* out /* r6 J0 J1 */) {
+  if (threadIdx.x == 0) relative_pose_error(in, in + 36, in + 43, out, out + 6, out + 42);
+}
+}  // namespace
+
+static int hook_alloc(okb_ctx* c, size_t bytes) {
+  if (c->hook_bytes >= bytes) return OKB_OK;
+  if (c->hook_buf) cudaFree(c->hook_buf);
+  c->hook_buf = nullptr; c->hook_bytes = 0;
+  OKB_CUDA(c, cudaMalloc(&c->hook_buf, bytes));
+  c->hook_bytes = bytes;
+  return OKB_OK;
+}
+
+extern "C" int okb_eval_reprojection(okb_ctx* c, int n, const okb_camera* cam, const double* pose, const double* landmark,
+                                     const double* extrinsics, const double* z, const double* sqrt_info, double* r,
+                                     double* J_pose, double* J_lm, double* J_ext) {
+  if (!c || n < 1 || !cam) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  const size_t nin = (size_t)n * (7 + 4 + 7 + 2 + 1), nout = (size_t)n * (2 + 12 + 6 + 12);
+  int rc = hook_alloc(c, (nin + nout) * sizeof(double));
+  if (rc) return rc;
+  double* d = reinterpret_cast<double*>(c->hook_buf);
+  double *dp = d, *dl = dp + 7 * (size_t)n, *de = dl + 4 * (size_t)n, *dz = de + 7 * (size_t)n, *dq = dz + 2 * (size_t)n;
+  double *dr = dq + n, *d0 = dr + 2 * (size_t)n, *d1 = d0 + 12 * (size_t)n, *d2 = d1 + 6 * (size_t)n;
+  OKB_CUDA(c, cudaMemcpyAsync(dp, pose, sizeof(double) * 7 * n, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dl, landmark, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(de, extrinsics, sizeof(double) * 7 * n, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dz, z, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dq, sqrt_info, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  k_hook_reproj<<<(n + 127) / 128, 128, 0, c->stream>>>(n, *cam, dp, dl, de, dz, dq, dr, d0, d1, d2);
+  c->launches += 1;
+  OKB_CUDA(c, cudaGetLastError());
+  if (r) OKB_CUDA(c, cudaMemcpyAsync(r, dr, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (J_pose) OKB_CUDA(c, cudaMemcpyAsync(J_pose, d0, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (J_lm) OKB_CUDA(c, cudaMemcpyAsync(J_lm, d1, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (J_ext) OKB_CUDA(c, cudaMemcpyAsync(J_ext, d2, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OKB_OK;
+}
+
+extern "C" int okb_eval_imu(okb_ctx* c, const okb_imu_params* prm, const okb_imu_sample* samples, int n_samples, int64_t t0_ns,
+                            int64_t t1_ns, const double* pose0, const double* sb0, const double* pose1, const double* sb1,
+                            const double* sb_ref, double* r, double* J0, double* J1, double* J2, double* J3,
+                            double* sqrt_info_out) {
+  if (!c || !prm || !samples || n_samples < 2) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  const size_t sbytes = align_up(sizeof(okb_imu_sample) * n_samples, 256);
+  const size_t total = sbytes + align_up(sizeof(ImuCache), 256) + sizeof(double) * (32 + 9 + 7 + 700);
+  int rc = hook_alloc(c, total);
+  if (rc) return rc;
+  unsigned char* base = reinterpret_cast<unsigned char*>(c->hook_buf);
+  okb_imu_sample* ds = reinterpret_cast<okb_imu_sample*>(base);
+  ImuCache* dc = reinterpret_cast<ImuCache*>(base + sbytes);
+  double* din = reinterpret_cast<double*>(base + sbytes + align_up(sizeof(ImuCache), 256));
+  double* dref = din + 32;
+  double* dout = dref + 16;
+  double hin[32];
+  std::memcpy(hin, pose0, 56); std::memcpy(hin + 7, sb0, 72); std::memcpy(hin + 16, pose1, 56); std::memcpy(hin + 23, sb1, 72);
+  OKB_CUDA(c, cudaMemcpyAsync(ds, samples, sizeof(okb_imu_sample) * n_samples, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(din, hin, sizeof(hin), cudaMemcpyHostToDevice, c->stream));
+  if (sb_ref) OKB_CUDA(c, cudaMemcpyAsync(dref, sb_ref, 72, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  k_hook_imu<<<1, 32, 0, c->stream>>>(*prm, ds, n_samples, t0_ns, t1_ns, din, dref, sb_ref ? 1 : 0, dc, dout);
+  c->launches += 1;
+  OKB_CUDA(c, cudaGetLastError());
+  std::vector<double> h(691);
+  OKB_CUDA(c, cudaMemcpyAsync(h.data(), dout, sizeof(double) * 691, cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (r) std::memcpy(r, h.data(), 15 * 8);
+  const double* SF = h.data() + 15;
+  for (int rr = 0; rr < 15; ++rr) {
+    for (int cc = 0; cc < 6; ++cc) { if (J0) J0[rr * 6 + cc] = SF[rr * 30 + cc]; if (J2) J2[rr * 6 + cc] = SF[rr * 30 + 15 + cc]; }
+    for (int cc = 0; cc < 9; ++cc) { if (J1) J1[rr * 9 + cc] = SF[rr * 30 + 6 + cc]; if (J3) J3[rr * 9 + cc] = SF[rr * 30 + 21 + cc]; }
+  }
+  if (sqrt_info_out) std::memcpy(sqrt_info_out, h.data() + 465, 225 * 8);
+  return (int)h[690] > 0 ? 1 : 0;   // 1 = the evaluation re-preintegrated (not an error)
+}
+
+extern "C" int okb_imu_propagate(okb_ctx* c, const okb_imu_params* prm, const okb_imu_sample* samples, int n_samples,
+                                 int64_t t0_ns, int64_t t1_ns, double* pose, double* sb, double* covariance, double* jacobian,
+                                 int* n_used) {
+  if (!c || !prm || !samples || n_samples < 2 || !pose || !sb) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  const size_t sbytes = align_up(sizeof(okb_imu_sample) * n_samples, 256);
+  int rc = hook_alloc(c, sbytes + sizeof(double) * (16 + 450 + 2));
+  if (rc) return rc;
+  unsigned char* base = reinterpret_cast<unsigned char*>(c->hook_buf);
+  okb_imu_sample* ds = reinterpret_cast<okb_imu_sample*>(base);
+  double* dio = reinterpret_cast<double*>(base + sbytes);
+  double* dcov = dio + 16;
+  double* djac = dcov + 225;
+  int* dn = reinterpret_cast<int*>(djac + 225);
+  double hio[16];
+  std::memcpy(hio, pose, 56); std::memcpy(hio + 7, sb, 72);
+  OKB_CUDA(c, cudaMemcpyAsync(ds, samples, sizeof(okb_imu_sample) * n_samples, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dio, hio, sizeof hio, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  k_hook_propagate<<<1, 32, 0, c->stream>>>(*prm, ds, n_samples, t0_ns, t1_ns, dio, dcov, djac, covariance ? 1 : 0, jacobian ? 1 : 0, dn);
+  c->launches += 1;
+  OKB_CUDA(c, cudaGetLastError());
+  int hn = 0;
+  OKB_CUDA(c, cudaMemcpyAsync(hio, dio, sizeof hio, cudaMemcpyDeviceToHost, c->stream));
+  if (covariance) OKB_CUDA(c, cudaMemcpyAsync(covariance, dcov, 225 * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (jacobian) OKB_CUDA(c, cudaMemcpyAsync(jacobian, djac, 225 * 8, cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(&hn, dn, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (hn >= 0) { std::memcpy(pose, hio, 56); std::memcpy(sb, hio + 7, 72); }
+  if (n_used) *n_used = hn;
+  return OKB_OK;
+}
+
+extern "C" int okb_eval_pose_error(okb_ctx* c, const double* meas, const double* sqrt_info, const double* pose, double* r, double* J) {
+  if (!c) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  int rc = hook_alloc(c, sizeof(double) * (50 + 42));
+  if (rc) return rc;
+  double* d = reinterpret_cast<double*>(c->hook_buf);
+  double h[50];
+  std::memcpy(h, meas, 56); std::memcpy(h + 7, sqrt_info, 288); std::memcpy(h + 43, pose, 56);
+  OKB_CUDA(c, cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  k_hook_pose<<<1, 32, 0, c->stream>>>(d, d + 50);
+  c->launches += 1;
+  double o[42];
+  OKB_CUDA(c, cudaMemcpyAsync(o, d + 50, sizeof o, cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (r) std::memcpy(r, o, 48);
+  if (J) std::memcpy(J, o + 6, 288);
+  return OKB_OK;
+}
+
+namespace {
+__global__ void k_hook_sb(const double* in /* meas9 S81 sb9 */, double* out /* r9 J81 */) {
+  const int t = threadIdx.x;
+  if (t < 9) {
+    double s = 0;
+    for (int k = 0; k < 9; ++k) s += in[9 + t * 9 + k] * (in[k] - in[90 + k]);
+    out[t] = s;
+  }
+  for (int e = t; e < 81; e += blockDim.x) out[9 + e] = -in[9 + e];
+}
+}  // namespace
+
+extern "C" int okb_eval_speed_bias_error(okb_ctx* c, const double* meas, const double* sqrt_info, const double* sb, double* r, double* J) {
+  if (!c || !meas || !sqrt_info || !sb) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  int rc = hook_alloc(c, sizeof(double) * (99 + 90));
+  if (rc) return rc;
+  double* d = reinterpret_cast<double*>(c->hook_buf);
+  double h[99];
+  std::memcpy(h, meas, 72); std::memcpy(h + 9, sqrt_info, 648); std::memcpy(h + 90, sb, 72);
+  OKB_CUDA(c, cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  k_hook_sb<<<1, 96, 0, c->stream>>>(d, d + 99);
+  c->launches += 1;
+  double o[90];
+  OKB_CUDA(c, cudaMemcpyAsync(o, d + 99, sizeof o, cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (r) std::memcpy(r, o, 72);
+  if (J) std::memcpy(J, o + 9, 648);
+  return OKB_OK;
+}
+
+extern "C" int okb_eval_relative_pose(okb_ctx* c, const double* sqrt_info, const double* pose0, const double* pose1, double* r,
+                                      double* J0, double* J1) {
+  if (!c) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  int rc = hook_alloc(c, sizeof(double) * (50 + 78));
+  if (rc) return rc;
+  double* d = reinterpret_cast<double*>(c->hook_buf);
+  double h[50];
+  std::memcpy(h, sqrt_info, 288); std::memcpy(h + 36, pose0, 56); std::memcpy(h + 43, pose1, 56);
+  OKB_CUDA(c, cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  k_hook_relpose<<<1, 32, 0, c->stream>>>(d, d + 50);
+  c->launches += 1;
+  double o[78];
+  OKB_CUDA(c, cudaMemcpyAsync(o, d + 50, sizeof o, cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (r) std::memcpy(r, o, 48);
+  if (J0) std::memcpy(J0, o + 6, 288);
+  if (J1) std::memcpy(J1, o + 42, 288);
+  return OKB_OK;
+}
+
+namespace {
+__global__ void k_hook_marg(int n, int nb, const int32_t* kind, const int32_t* col, const int32_t* off, const double* x0,
+                            const double* x, const double* J, const double* e0, double* r, double* Jeff) {
+  extern __shared__ double dchi[];
+  const int tid = threadIdx.x;
+  for (int b = tid; b < nb; b += blockDim.x) {
+    if (kind[b] == OKB_BLOCK_SPEED_BIAS) for (int k = 0; k < 9; ++k) dchi[col[b] + k] = x[off[b] + k] - x0[off[b] + k];
+    else pose_minus(x0 + off[b], x + off[b], dchi + col[b]);
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    double s = e0[i];
+    for (int k = 0; k < n; ++k) s += J[(size_t)i * n + k] * dchi[k];
+    r[i] = s;
+  }
+  for (int b = 0; b < nb; ++b) {
+    const int m = (kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
+    double B[9];
+    if (m == 6) marg_pose_rot_block(x0 + off[b], x + off[b], B);
+    for (int e = tid; e < n * m; e += blockDim.x) {
+      const int i = e / m, a = e % m;
+      double s;
+      if (m == 9 || a < 3) s = J[(size_t)i * n + col[b] + a];
+      else { s = 0; for (int k = 0; k < 3; ++k) s += J[(size_t)i * n + col[b] + 3 + k] * B[k * 3 + (a - 3)]; }
+      Jeff[(size_t)i * n + col[b] + a] = s;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int okb_eval_marginalization(okb_ctx* c, const okb_marg_prior* m, const double* x, double* r, double* J_eff) {
+  if (!c || !m || m->n < 1 || m->n > kMaxMarg) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  const int n = m->n, nb = m->n_blocks;
+  std::vector<int32_t> kind(nb), col(nb), off(nb);
+  int cc = 0, xo = 0;
+  for (int b = 0; b < nb; ++b) {
+    kind[b] = m->block_kind[b]; col[b] = cc; off[b] = xo;
+    cc += (kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
+    xo += (kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
+  }
+  if (cc != n) return OKB_ERR_INVALID_ARG;
+  const size_t ints = align_up(sizeof(int32_t) * 3 * nb, 256);
+  const size_t total = ints + sizeof(double) * (2 * xo + (size_t)2 * n * n + 2 * n);
+  int rc = hook_alloc(c, total);
+  if (rc) return rc;
+  unsigned char* base = reinterpret_cast<unsigned char*>(c->hook_buf);
+  int32_t* dk = reinterpret_cast<int32_t*>(base);
+  double* dx0 = reinterpret_cast<double*>(base + ints);
+  double *dx = dx0 + xo, *dJ = dx + xo, *de0 = dJ + (size_t)n * n, *dr = de0 + n, *dJe = dr + n;
+  OKB_CUDA(c, cudaMemcpyAsync(dk, kind.data(), 4 * nb, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dk + nb, col.data(), 4 * nb, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dk + 2 * nb, off.data(), 4 * nb, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dx0, m->x0, 8 * xo, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dx, x, 8 * xo, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(dJ, m->J, 8 * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(de0, m->e0, 8 * n, cudaMemcpyHostToDevice, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  k_hook_marg<<<1, 256, sizeof(double) * n, c->stream>>>(n, nb, dk, dk + nb, dk + 2 * nb, dx0, dx, dJ, de0, dr, dJe);
+  c->launches += 1;
+  OKB_CUDA(c, cudaGetLastError());
+  if (r) OKB_CUDA(c, cudaMemcpyAsync(r, dr, 8 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (J_eff) OKB_CUDA(c, cudaMemcpyAsync(J_eff, dJe, 8 * (size_t)n * n, cudaMemcpyDeviceToHost, c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OKB_OK;
+}

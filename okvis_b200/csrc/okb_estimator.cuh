@@ -1,0 +1,118 @@
+// Device-side data model of one keyframe window and of the batched dogleg/Schur solver.
+// See DESIGN.md ("Data layout in HBM", "Kernels") for the rationale.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "okb_imu.cuh"
+
+namespace okb {
+
+// ---- compile-time limits ------------------------------------------------------------------
+constexpr int kMaxFrames = 32;        // frame visibility mask is one u32
+constexpr int kMaxChunks = 64;        // landmark chunks (CTAs) per window in kernel A
+constexpr int kMaxDense = 512;        // reduced-system dimension limit
+constexpr int kMaxMarg = 160;         // marginalisation prior dimension limit
+
+// Ceres 1.9 defaults used by Estimator::optimize
+constexpr double kInitialRadius = 1e4;
+constexpr double kMinRadius = 1e-32;
+constexpr double kMinRelativeDecrease = 1e-3;
+constexpr double kFunctionTolerance = 1e-6;
+constexpr double kGradientTolerance = 1e-10;
+constexpr double kParameterTolerance = 1e-8;
+constexpr double kMinDiag = 1e-6;
+constexpr double kMaxDiag = 1e32;
+constexpr double kMinMu = 1e-8;
+constexpr double kMaxMu = 1.0;
+constexpr double kMuIncrease = 10.0;
+constexpr int kMaxConsecutiveInvalid = 5;
+
+enum Mode { MODE_INIT = 0, MODE_STEP = 1, MODE_REBUILD = 2 };
+
+struct SlotInfo { int pose_idx, ext_idx, cam_idx, valid; };
+
+// Per-window solver state (device resident, one per window; also read back as the summary).
+struct SolverState {
+  int mode;            // what kernel A must evaluate next / what kernel S must judge
+  int done;            // 1 = terminated
+  int cur;             // buffer index of the linearisation at the committed state (lm_g / lm_E / gd / Ed)
+  int iteration, num_successful, num_invalid, termination;
+  int reuse;           // dogleg reuse_ flag
+  int numeric_fail;    // set by kernel A when a landmark block is not positive definite
+  int imu_redo;
+  int imu_redo_final;
+  double radius, mu, mu_spec;
+  double cost, initial_cost;
+  double x_norm2;      // ||x||^2 of the committed state (ambient)
+  // dogleg scalars of the current linearisation (metric E):
+  double G2, VHV, GU, N2;
+  double a, b;         // step = a * g/E + b * (-u)
+  double model_cost_change, dogleg_step_norm;
+  double cand_step_norm2_dense;   // ||x - x_cand||^2 over the dense blocks
+  double grad_max;
+  unsigned long long t_start_ns, t_last_iter_ns, t_iter_begin_ns;
+  double solve_time_s;
+};
+
+// Everything kernels need to know about one window.  All pointers are device pointers into the
+// window's arena.
+struct WinDev {
+  int K, NSB, NE, L, NC;
+  int CP;              // cameras per frame padded to a power of two
+  int NS;              // slots = K * CP  (slot = frame * CP + cam)
+  int NG;              // slot groups of 32 lanes
+  int NSP;             // NG * 32: padded slots per landmark in the observation grid
+  int d, dc, dcp;      // reduced dims: dc = 6K (pose part), d = dc + 9 NSB, dcp = 4*ceil((dc+1)/4)
+  int n_imu, n_samples, n_pp, n_sbp;
+  int marg_n, marg_nb, marg_xdim;
+  int n_chunks, lm_per_chunk;
+  int use_cauchy;
+  // state
+  double *pose, *sb, *ext, *lm;                // committed  [K][7] [NSB][9] [NE][7] [L][4]
+  double *pose_init, *sb_init, *lm_init;       // as uploaded (okb_window_reset)
+  double *pose_c, *sb_c, *lm_c;                // candidate
+  // graph
+  SlotInfo* slots;                             // [NSP]
+  okb_camera* cams;                            // [NC]
+  double2* obs_z;                              // [L][NSP]
+  double* obs_w;                               // [L][NSP] sqrt information, 0 = no observation
+  uint32_t* lm_vis;                            // [L] bit f set = observed in frame f
+  // per-landmark solver data
+  double* lm_g[2];                             // [L][3] gradient block (double buffered: cur / speculative)
+  double* lm_E[2];                             // [L][3] metric (Ceres diagonal^2 / scale^2)
+  double* lm_Rinv;                             // [L][6] (H_ll + mu E)^-1, symmetric packed
+  double* lm_M;                                // [K][L][6] per-frame sum of rho' A^T A
+  double* lm_gn;                               // [L][3] Gauss-Newton step of the current linearisation
+  double* lm_scale;                            // [L][3] Jacobi scale (fixed after the first linearisation)
+  double* quality;                             // [L]
+  // kernel A -> kernel S partial sums, one record per chunk
+  double* partA;                               // [n_chunks][partA_stride]
+  int partA_stride;                            // 4 + 27*K + dcp*dcp
+  // dense part
+  double* Hd;                                  // [d][d] J^T J restricted to dense blocks (speculative)
+  double* gd[2];                               // [d]
+  double* Ed[2];                               // [d]
+  double* ud;                                  // [d] (H+mu E)^-1 g, dense part
+  double* scale_d;                             // [d]
+  double* chol;                                // [d][d] workspace (used when it does not fit in shared memory)
+  // IMU
+  okb_imu_term* imu_terms;
+  okb_imu_sample* samples;
+  okb_imu_params imu_params;
+  ImuCache* imu_cache;
+  ImuCache* imu_cache_init;
+  int *sb_off;                                 // unused placeholder for alignment
+  // priors
+  okb_pose_prior* pp;
+  okb_sb_prior* sbp;
+  // marginalisation prior
+  int32_t* marg_kind;
+  uint32_t* marg_idx;
+  int32_t* marg_col;                           // [marg_nb] first column of each block
+  int32_t* marg_off;                           // [marg_nb] offset into x0
+  double *marg_x0, *marg_J, *marg_e0, *marg_H0;  // H0 = J^T J
+  SolverState* st;
+};
+
+}  // namespace okb

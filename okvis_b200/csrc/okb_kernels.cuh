@@ -1,0 +1,1071 @@
+// Kernels of the batched dogleg/Schur solver (sm_100a).  Two kernels per solver round:
+//   k_landmarks ("A"): one CTA per (landmark chunk, window).  Warp per landmark, lane per
+//       (frame,camera) slot: reprojection residual + Jacobian factors, Cauchy weighting, landmark
+//       block H_ll / g_l, (H_ll + mu E)^-1, per-frame M_f; Schur complement accumulated as a
+//       register-tiled dense SYRK  S += Y Y^T over shared-memory tiles of Y = W L^-T.
+//   k_solve ("S"): one CTA per window.  IMU / prior / marginalisation terms, step acceptance
+//       (Ceres 1.9 trust-region logic), dense Cholesky of the reduced system, back-substitution,
+//       traditional dogleg step, candidate state.
+// plus k_quality (post-solve landmark quality, Estimator.cpp:880-894) and small utility kernels.
+#pragma once
+#include "okb_estimator.cuh"
+
+namespace okb {
+
+constexpr int A_WARPS = 12;
+constexpr int A_THREADS = A_WARPS * 32;
+constexpr int S_THREADS = 512;
+constexpr int S_WARPS = S_THREADS / 32;
+
+struct SlotCtx {
+  SlotXf xf;
+  CamIntr cam;
+  int frame;
+  int valid;
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is shared scratch of >= 32 doubles; result valid in all threads
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0;
+  for (int i = 0; i < nw; ++i) s += red[i];   // fixed order: deterministic
+  return s;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = red[0];
+  for (int i = 1; i < nw; ++i) s = fmax(s, red[i]);
+  return s;
+}
+
+// shared-memory footprint of kernel A for a window shape
+__host__ __device__ inline size_t smemA_bytes(int NSP, int K, int dcp) {
+  size_t b = 0;
+  b += (size_t)NSP * sizeof(SlotCtx);
+  b = (b + 15) & ~(size_t)15;
+  b += (size_t)K * 4 * sizeof(double);                    // frame translations (+pad)
+  b += (size_t)A_WARPS * 27 * K * sizeof(double);         // per-warp H_pp / g_p accumulators
+  b += (size_t)A_WARPS * K * 9 * sizeof(double);          // per-warp stash of M_f, m_f
+  b += (size_t)3 * A_WARPS * dcp * sizeof(double);        // Y tile, k-major
+  b += 64 * sizeof(double);                               // reduction scratch
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel A
+// ------------------------------------------------------------------------------------------------
+template <int TPT>
+__global__ void __launch_bounds__(A_THREADS, 1) k_landmarks(const WinDev* __restrict__ wins, int win_first) {
+  const WinDev& W = wins[win_first + blockIdx.y];
+  SolverState* st = W.st;
+  if (st->done) return;
+  const int chunk = blockIdx.x;
+  if (chunk >= W.n_chunks) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = W.K, NSP = W.NSP, CP = W.CP, NG = W.NG, dc = W.dc, dcp = W.dcp, L = W.L;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  size_t off = 0;
+  SlotCtx* slots = reinterpret_cast<SlotCtx*>(smem_raw);
+  off += (size_t)NSP * sizeof(SlotCtx);
+  off = (off + 15) & ~(size_t)15;
+  double* tws = reinterpret_cast<double*>(smem_raw + off); off += (size_t)K * 4 * sizeof(double);
+  double* hpp = reinterpret_cast<double*>(smem_raw + off); off += (size_t)A_WARPS * 27 * K * sizeof(double);
+  double* stash = reinterpret_cast<double*>(smem_raw + off); off += (size_t)A_WARPS * K * 9 * sizeof(double);
+  double* Yt = reinterpret_cast<double*>(smem_raw + off); off += (size_t)3 * A_WARPS * dcp * sizeof(double);
+  double* red = reinterpret_cast<double*>(smem_raw + off);
+
+  const int mode = st->mode;
+  const int cur = st->cur;
+  const double step_a = st->a, step_b = st->b;
+  const double mu = (mode == MODE_STEP) ? fmax(kMinMu, 2.0 * st->mu / kMuIncrease) : st->mu;
+  const bool cauchy = W.use_cauchy != 0;
+
+  // ---- prologue: slot transforms at the candidate poses
+  for (int s = tid; s < NSP; s += A_THREADS) {
+    const SlotInfo si = W.slots[s];
+    SlotCtx& sc = slots[s];
+    sc.valid = si.valid;
+    sc.frame = si.valid ? si.pose_idx : 0;
+    if (si.valid) {
+      make_slot_xf(W.pose_c + 7 * si.pose_idx, W.ext + 7 * si.ext_idx, sc.xf);
+      cam_load(W.cams[si.cam_idx], sc.cam);
+    }
+  }
+  for (int f = tid; f < K; f += A_THREADS) {
+    tws[4 * f + 0] = W.pose_c[7 * f + 0]; tws[4 * f + 1] = W.pose_c[7 * f + 1]; tws[4 * f + 2] = W.pose_c[7 * f + 2];
+  }
+  for (int i = tid; i < A_WARPS * 27 * K; i += A_THREADS) hpp[i] = 0.0;
+  __syncthreads();
+
+  // ---- SYRK thread mapping: 4x4 micro-tiles of the lower triangle of the (dcp x dcp) matrix.
+  // TPT = 1: one micro-tile per thread, the tile's columns split KS ways; TPT = 2: two micro-tiles.
+  const int NT = dcp >> 2;
+  const int NTT = NT * (NT + 1) / 2;
+  int KS = 1;
+  if (TPT == 1) { KS = A_THREADS / NTT; if (KS < 1) KS = 1; }
+  const int ks = (TPT == 1) ? tid / NTT : 0;
+  int ti[TPT], tj[TPT];
+  bool syrk_on[TPT];
+  double acc[TPT][16];
+#pragma unroll
+  for (int m = 0; m < TPT; ++m) {
+    const int tt = (TPT == 1) ? tid % NTT : tid + m * A_THREADS;
+    syrk_on[m] = (TPT == 1) ? (ks < KS) : (tt < NTT);
+    const int tq = syrk_on[m] ? tt : 0;
+    int a = (int)((sqrt(8.0 * tq + 1.0) - 1.0) * 0.5);
+    while (a * (a + 1) / 2 > tq) --a;
+    while ((a + 1) * (a + 2) / 2 <= tq) ++a;
+    ti[m] = a;
+    tj[m] = tq - a * (a + 1) / 2;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[m][i] = 0.0;
+  }
+
+  const int lm_begin = chunk * W.lm_per_chunk;
+  const int lm_end = min(L, lm_begin + W.lm_per_chunk);
+  const int ntiles = (lm_end - lm_begin + A_WARPS - 1) / A_WARPS;
+  double cost_acc = 0.0, stepn2 = 0.0;
+  double* my_hpp = hpp + (size_t)warp * 27 * K;
+  double* my_stash = stash + (size_t)warp * K * 9;
+  double* my_Y = Yt + (size_t)3 * warp * dcp;
+  const double* gcur = W.lm_g[cur];
+  const double* Ecur = W.lm_E[cur];
+  double* gspec = W.lm_g[cur ^ 1];
+  double* Espec = W.lm_E[cur ^ 1];
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int l = lm_begin + tile * A_WARPS + warp;
+    for (int i = lane; i < 3 * dcp; i += 32) my_Y[i] = 0.0;
+    for (int i = lane; i < 9 * K; i += 32) my_stash[i] = 0.0;
+    __syncwarp();
+    if (l < lm_end) {
+      // candidate landmark
+      double X[4];
+      {
+        const double4 x4 = *reinterpret_cast<const double4*>(W.lm + 4 * (size_t)l);
+        X[0] = x4.x; X[1] = x4.y; X[2] = x4.z; X[3] = x4.w;
+      }
+      if (mode == MODE_STEP) {
+        double dn = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double dlt = step_a * gcur[3 * (size_t)l + c] / Ecur[3 * (size_t)l + c] + step_b * W.lm_gn[3 * (size_t)l + c];
+          X[c] += dlt;
+          dn += dlt * dlt;
+        }
+        if (lane == 0) stepn2 += dn;
+      }
+      if (lane == 0) *reinterpret_cast<double4*>(W.lm_c + 4 * (size_t)l) = make_double4(X[0], X[1], X[2], X[3]);
+
+      // ---- phase 1: lane = slot
+      for (int g = 0; g < NG; ++g) {
+        const int slot = g * 32 + lane;
+        const SlotCtx& sc = slots[slot];
+        const double2 z = W.obs_z[(size_t)l * NSP + slot];
+        const double wobs = W.obs_w[(size_t)l * NSP + slot];
+        double M[6] = {0, 0, 0, 0, 0, 0}, m[3] = {0, 0, 0};
+        if (wobs > 0.0 && sc.valid) {
+          double r[2], A[6];
+          reproj_slot<true>(sc.xf, sc.cam, X, z.x, z.y, wobs, r, A);
+          const double sq = r[0] * r[0] + r[1] * r[1];
+          double rho1 = 1.0;
+          if (cauchy) { rho1 = 1.0 / (1.0 + sq); cost_acc += 0.5 * log(1.0 + sq); }
+          else cost_acc += 0.5 * sq;
+          M[0] = rho1 * (A[0] * A[0] + A[3] * A[3]);
+          M[1] = rho1 * (A[0] * A[1] + A[3] * A[4]);
+          M[2] = rho1 * (A[0] * A[2] + A[3] * A[5]);
+          M[3] = rho1 * (A[1] * A[1] + A[4] * A[4]);
+          M[4] = rho1 * (A[1] * A[2] + A[4] * A[5]);
+          M[5] = rho1 * (A[2] * A[2] + A[5] * A[5]);
+          m[0] = rho1 * (A[0] * r[0] + A[3] * r[1]);
+          m[1] = rho1 * (A[1] * r[0] + A[4] * r[1]);
+          m[2] = rho1 * (A[2] * r[0] + A[5] * r[1]);
+        }
+        for (int o = 1; o < CP; o <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) M[i] += __shfl_xor_sync(0xffffffffu, M[i], o);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) m[i] += __shfl_xor_sync(0xffffffffu, m[i], o);
+        }
+        if ((lane & (CP - 1)) == 0 && sc.valid) {
+          double* sp = my_stash + 9 * sc.frame;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) sp[i] = M[i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) sp[6 + i] = m[i];
+        }
+      }
+      __syncwarp();
+      // ---- landmark block (replicated on all lanes, fixed summation order)
+      double H[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
+      for (int f = 0; f < K; ++f) {
+        const double* sp = my_stash + 9 * f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) H[i] += sp[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) gl[i] -= sp[6 + i];
+      }
+      double sc3[3], E[3];
+      const double hd[3] = {H[0], H[3], H[5]};
+      if (mode == MODE_INIT) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sc3[c] = 1.0 / (1.0 + sqrt(hd[c]));
+        if (lane == 0) { W.lm_scale[3 * (size_t)l] = sc3[0]; W.lm_scale[3 * (size_t)l + 1] = sc3[1]; W.lm_scale[3 * (size_t)l + 2] = sc3[2]; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sc3[c] = W.lm_scale[3 * (size_t)l + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double s2 = sc3[c] * sc3[c];
+        E[c] = fmin(fmax(s2 * hd[c], kMinDiag), kMaxDiag) / s2;
+      }
+      double R[6] = {H[0] + mu * E[0], H[1], H[2], H[3] + mu * E[1], H[4], H[5] + mu * E[2]};
+      double Lc[6], Li[6];
+      const bool pd = chol3(R, Lc);
+      if (pd) linv3(Lc, Li);
+      else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Li[i] = 0.0;
+        if (lane == 0) st->numeric_fail = 1;
+      }
+      if (lane == 0) {
+        // Rinv = Li^T Li
+        double* Ro = W.lm_Rinv + 6 * (size_t)l;
+        Ro[0] = Li[0] * Li[0] + Li[1] * Li[1] + Li[3] * Li[3];
+        Ro[1] = Li[1] * Li[2] + Li[3] * Li[4];
+        Ro[2] = Li[3] * Li[5];
+        Ro[3] = Li[2] * Li[2] + Li[4] * Li[4];
+        Ro[4] = Li[4] * Li[5];
+        Ro[5] = Li[5] * Li[5];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { gspec[3 * (size_t)l + c] = gl[c]; Espec[3 * (size_t)l + c] = E[c]; }
+        // z = L^-1 g_l  -> augmented row dc of the Y tile
+        my_Y[0 * dcp + dc] = Li[0] * gl[0];
+        my_Y[1 * dcp + dc] = Li[1] * gl[0] + Li[2] * gl[1];
+        my_Y[2 * dcp + dc] = Li[3] * gl[0] + Li[4] * gl[1] + Li[5] * gl[2];
+      }
+      // ---- phase 2: lane = frame
+      const uint32_t vis = W.lm_vis[l];
+      for (int f = lane; f < K; f += 32) {
+        if (!((vis >> f) & 1u)) continue;
+        const double* sp = my_stash + 9 * f;
+        const double M0 = sp[0], M1 = sp[1], M2 = sp[2], M3 = sp[3], M4 = sp[4], M5 = sp[5];
+        const double m0 = sp[6], m1 = sp[7], m2 = sp[8];
+        double* Mo = W.lm_M + ((size_t)f * L + l) * 6;
+        Mo[0] = M0; Mo[1] = M1; Mo[2] = M2; Mo[3] = M3; Mo[4] = M4; Mo[5] = M5;
+        const double w = X[3];
+        const double p0 = X[0] - tws[4 * f] * w, p1 = X[1] - tws[4 * f + 1] * w, p2 = X[2] - tws[4 * f + 2] * w;
+        // Q = M [p]x  (3x3): columns of [p]x are (0,p2,-p1), (-p2,0,p0), (p1,-p0,0)
+        const double Q00 = M1 * p2 - M2 * p1, Q01 = -M0 * p2 + M2 * p0, Q02 = M0 * p1 - M1 * p0;
+        const double Q10 = M3 * p2 - M4 * p1, Q11 = -M1 * p2 + M4 * p0, Q12 = M1 * p1 - M3 * p0;
+        const double Q20 = M4 * p2 - M5 * p1, Q21 = -M2 * p2 + M5 * p0, Q22 = M2 * p1 - M4 * p0;
+        // H_rr = [p]x^T Q = -[p]x Q : rows of -[p]x are (0,p2,-p1), (-p2,0,p0), (p1,-p0,0)
+        double* hp = my_hpp + f;
+        const double w2 = w * w;
+        hp[0 * K] += w2 * M0; hp[1 * K] += w2 * M1; hp[2 * K] += w2 * M2;
+        hp[3 * K] += w2 * M3; hp[4 * K] += w2 * M4; hp[5 * K] += w2 * M5;
+        // H_tr = -w Q (3x3 row-major)
+        hp[6 * K] -= w * Q00; hp[7 * K] -= w * Q01; hp[8 * K] -= w * Q02;
+        hp[9 * K] -= w * Q10; hp[10 * K] -= w * Q11; hp[11 * K] -= w * Q12;
+        hp[12 * K] -= w * Q20; hp[13 * K] -= w * Q21; hp[14 * K] -= w * Q22;
+        // H_rr (symmetric packed)
+        hp[15 * K] += p2 * Q10 - p1 * Q20;
+        hp[16 * K] += p2 * Q11 - p1 * Q21;
+        hp[17 * K] += p2 * Q12 - p1 * Q22;
+        hp[18 * K] += -p2 * Q01 + p0 * Q21;
+        hp[19 * K] += -p2 * Q02 + p0 * Q22;
+        hp[20 * K] += p1 * Q02 - p0 * Q12;
+        // g_p = [w m ; p x m]
+        hp[21 * K] += w * m0; hp[22 * K] += w * m1; hp[23 * K] += w * m2;
+        hp[24 * K] += p1 * m2 - p2 * m1; hp[25 * K] += p2 * m0 - p0 * m2; hp[26 * K] += p0 * m1 - p1 * m0;
+        // N = M L^-T : column j of L^-T is row j of L^-1 ... N[:,j] = sum_k M[:,k] Li[j][k]
+        const double N00 = M0 * Li[0], N01 = M0 * Li[1] + M1 * Li[2], N02 = M0 * Li[3] + M1 * Li[4] + M2 * Li[5];
+        const double N10 = M1 * Li[0], N11 = M1 * Li[1] + M3 * Li[2], N12 = M1 * Li[3] + M3 * Li[4] + M4 * Li[5];
+        const double N20 = M2 * Li[0], N21 = M2 * Li[1] + M4 * Li[2], N22 = M2 * Li[3] + M4 * Li[4] + M5 * Li[5];
+        // Y_f = W L^-T = -[w N ; [p]x N]
+        double* y0 = my_Y + 0 * dcp + 6 * f;
+        double* y1 = my_Y + 1 * dcp + 6 * f;
+        double* y2 = my_Y + 2 * dcp + 6 * f;
+        y0[0] = -w * N00; y0[1] = -w * N10; y0[2] = -w * N20;
+        y1[0] = -w * N01; y1[1] = -w * N11; y1[2] = -w * N21;
+        y2[0] = -w * N02; y2[1] = -w * N12; y2[2] = -w * N22;
+        // [p]x N column j = p x N[:,j]
+        y0[3] = -(p1 * N20 - p2 * N10); y0[4] = -(p2 * N00 - p0 * N20); y0[5] = -(p0 * N10 - p1 * N00);
+        y1[3] = -(p1 * N21 - p2 * N11); y1[4] = -(p2 * N01 - p0 * N21); y1[5] = -(p0 * N11 - p1 * N01);
+        y2[3] = -(p1 * N22 - p2 * N12); y2[4] = -(p2 * N02 - p0 * N22); y2[5] = -(p0 * N12 - p1 * N02);
+      }
+    }
+    __syncthreads();
+    // ---- SYRK over the tile: acc(ti,tj) += Y[4ti..][k] * Y[4tj..][k]
+#pragma unroll
+    for (int m = 0; m < TPT; ++m) {
+      if (syrk_on[m]) {
+        const int ncols = 3 * A_WARPS;
+        for (int k = ks; k < ncols; k += KS) {
+          const double* row = Yt + (size_t)k * dcp;
+          const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * ti[m]);
+          const double2 a23 = *reinterpret_cast<const double2*>(row + 4 * ti[m] + 2);
+          const double2 b01 = *reinterpret_cast<const double2*>(row + 4 * tj[m]);
+          const double2 b23 = *reinterpret_cast<const double2*>(row + 4 * tj[m] + 2);
+          const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+          const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[m][i * 4 + j] += a[i] * b[j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: chunk partials
+  double* part = W.partA + (size_t)chunk * W.partA_stride;
+  const double csum = block_sum(cost_acc, red);
+  const double ssum = block_sum(stepn2, red);
+  if (tid == 0) { part[0] = csum; part[1] = ssum; part[2] = 0.0; part[3] = 0.0; }
+  for (int i = tid; i < 27 * K; i += A_THREADS) {
+    double s = 0;
+    for (int w8 = 0; w8 < A_WARPS; ++w8) s += hpp[(size_t)w8 * 27 * K + i];
+    part[4 + i] = s;
+  }
+  double* Sp = part + 4 + 27 * K;
+  for (int s = 0; s < KS; ++s) {
+#pragma unroll
+    for (int m = 0; m < TPT; ++m) {
+      if (syrk_on[m] && ks == s) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double* p = Sp + (size_t)(4 * ti[m] + i) * dcp + 4 * tj[m] + j;
+            *p = (s == 0) ? acc[m][i * 4 + j] : (*p + acc[m][i * 4 + j]);
+          }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel S
+// ------------------------------------------------------------------------------------------------
+struct SShared {
+  double red[64];
+  // broadcast scalars
+  double cand_cost, cost_lm, stepn2_lm, cost_dense;
+  int adopt, terminate, commit_only, fail, spec;
+};
+
+// r = S e etc. are tiny; one warp handles all priors.
+__device__ void dense_priors(const WinDev& W, double* Hd, double* gd, double* cost_out) {
+  const int lane = threadIdx.x & 31, d = W.d;
+  double cost = 0.0;
+  for (int i = 0; i < W.n_pp; ++i) {
+    const okb_pose_prior& pr = W.pp[i];
+    double r[6], J[36];
+    pose_error(pr.meas, pr.sqrt_info, W.pose_c + 7 * pr.pose_idx, r, J);   // replicated per lane (tiny)
+    const int o = 6 * pr.pose_idx;
+    for (int e = lane; e < 36; e += 32) {
+      const int a = e / 6, b = e % 6;
+      double s = 0;
+      for (int k = 0; k < 6; ++k) s += J[k * 6 + a] * J[k * 6 + b];
+      Hd[(size_t)(o + a) * d + o + b] += s;
+    }
+    if (lane < 6) {
+      double s = 0;
+      for (int k = 0; k < 6; ++k) s += J[k * 6 + lane] * r[k];
+      gd[o + lane] += s;
+    }
+    for (int k = 0; k < 6; ++k) cost += 0.5 * r[k] * r[k];
+    __syncwarp();
+  }
+  for (int i = 0; i < W.n_sbp; ++i) {
+    const okb_sb_prior& pr = W.sbp[i];
+    const double* x = W.sb_c + 9 * pr.sb_idx;
+    double e9[9], r[9];
+    for (int k = 0; k < 9; ++k) e9[k] = pr.meas[k] - x[k];
+    for (int a = 0; a < 9; ++a) {
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += pr.sqrt_info[a * 9 + k] * e9[k];
+      r[a] = s;
+    }
+    const int o = W.dc + 9 * pr.sb_idx;
+    for (int e = lane; e < 81; e += 32) {   // J = -S  => J^T J = S^T S
+      const int a = e / 9, b = e % 9;
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s += pr.sqrt_info[k * 9 + a] * pr.sqrt_info[k * 9 + b];
+      Hd[(size_t)(o + a) * d + o + b] += s;
+    }
+    if (lane < 9) {
+      double s = 0;
+      for (int k = 0; k < 9; ++k) s -= pr.sqrt_info[k * 9 + lane] * r[k];
+      gd[o + lane] += s;
+    }
+    for (int k = 0; k < 9; ++k) cost += 0.5 * r[k] * r[k];
+    __syncwarp();
+  }
+  *cost_out = cost;
+}
+
+constexpr int kImuScratch = 3 * 225 + 450 + 450 + 16;   // doubles per IMU warp
+__host__ __device__ inline int imu_scratch_warps(int n_imu) {
+  int w = (n_imu + 1) / 2;
+  if (w < 1) w = 1;
+  return w > 8 ? 8 : w;
+}
+__host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_imu, bool chol_in_smem) {
+  size_t b = sizeof(SShared);
+  b = (b + 15) & ~(size_t)15;
+  b += (size_t)8 * d * sizeof(double);                     // gd, Ed, ud, rhs, vd, tmp, delta, colk
+  b += (size_t)K * 4 * sizeof(double);                     // committed frame translations
+  b += (size_t)3 * (n_marg > 0 ? n_marg : 1) * sizeof(double);   // marg: dchi, e, Jte
+  size_t imu = (size_t)imu_scratch_warps(n_imu) * kImuScratch * sizeof(double);
+  size_t ch = chol_in_smem ? (size_t)d * d * sizeof(double) : 0;
+  b += imu > ch ? imu : ch;
+  return b;
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict__ wins, int win_first, okb_solve_options opt,
+                                                        int chol_in_smem) {
+  const WinDev& W = wins[win_first + blockIdx.x];
+  SolverState* st = W.st;
+  if (st->done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = W.K, d = W.d, dc = W.dc, dcp = W.dcp, L = W.L;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  size_t off = 0;
+  SShared* sh = reinterpret_cast<SShared*>(smem_raw); off += sizeof(SShared);
+  off = (off + 15) & ~(size_t)15;
+  double* s_g = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
+  double* s_E = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
+  double* s_u = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
+  double* s_rhs = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
+  double* s_v = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
+  double* s_tmp = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
+  double* s_delta = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
+  double* s_col = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
+  double* s_tws = reinterpret_cast<double*>(smem_raw + off); off += (size_t)K * 4 * 8;
+  const int nm = W.marg_n > 0 ? W.marg_n : 1;
+  double* s_dchi = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
+  double* s_me = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
+  double* s_mJte = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
+  double* s_big = reinterpret_cast<double*>(smem_raw + off);   // IMU scratch, later the Cholesky matrix
+
+  const int mode = st->mode;
+  const int spec = st->cur ^ 1;
+  double* Hd = W.Hd;
+  double* gd = W.gd[spec];
+
+  // ================= phase 1: dense terms at the candidate =================
+  for (int i = tid; i < d * d; i += S_THREADS) Hd[i] = 0.0;
+  for (int i = tid; i < d; i += S_THREADS) gd[i] = 0.0;
+  __syncthreads();
+  double cost_dense_local = 0.0;   // accumulated by lane 0 of each warp / thread 0
+  // IMU terms: two colour rounds so that neighbouring terms never add to the same block concurrently
+  {
+    WarpCtx cx;
+    const int nw_imu = imu_scratch_warps(W.n_imu);
+    double* wbuf = s_big + (size_t)(warp < nw_imu ? warp : 0) * kImuScratch;
+    ImuWork wk{wbuf, wbuf + 225, wbuf + 450};
+    double* F01 = wbuf + 675;
+    double* SF = wbuf + 675 + 450;
+    double* r15 = wbuf + 675 + 900;
+    for (int colour = 0; colour < 2; ++colour) {
+      for (int t = 2 * warp + colour; warp < nw_imu && t < W.n_imu; t += 2 * nw_imu) {
+        const okb_imu_term& T = W.imu_terms[t];
+        imu_evaluate(cx, W.samples + T.sample_offset, (int)T.sample_count, W.imu_params, T.t0_ns, T.t1_ns,
+                     W.pose_c + 7 * T.pose0, W.sb_c + 9 * T.sb0, W.pose_c + 7 * T.pose1, W.sb_c + 9 * T.sb1,
+                     W.imu_cache + t, wk, F01, (double*)nullptr, r15, SF);
+        // H += SF^T SF (30x30), g += SF^T r
+        const int offs[4] = {6 * (int)T.pose0, dc + 9 * (int)T.sb0, 6 * (int)T.pose1, dc + 9 * (int)T.sb1};
+        for (int e = lane; e < 900; e += 32) {
+          const int a = e / 30, b = e % 30;
+          double s = 0;
+          for (int k = 0; k < 15; ++k) s += SF[k * 30 + a] * SF[k * 30 + b];
+          const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
+          const int bb = (b < 6) ? 0 : (b < 15) ? 1 : (b < 21) ? 2 : 3;
+          const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
+          const int lb = b - ((bb == 0) ? 0 : (bb == 1) ? 6 : (bb == 2) ? 15 : 21);
+          atomicAdd(&Hd[(size_t)(offs[ba] + la) * d + offs[bb] + lb], s);
+        }
+        if (lane < 30) {
+          const int a = lane;
+          double s = 0;
+          for (int k = 0; k < 15; ++k) s += SF[k * 30 + a] * r15[k];
+          const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
+          const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
+          atomicAdd(&gd[offs[ba] + la], s);
+        }
+        if (lane == 0) {
+          double c = 0;
+          for (int k = 0; k < 15; ++k) c += r15[k] * r15[k];
+          cost_dense_local += 0.5 * c;
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+  }
+  // priors (warp 0)
+  if (warp == 0) {
+    double c = 0;
+    dense_priors(W, Hd, gd, &c);
+    if (lane == 0) cost_dense_local += c;
+  }
+  __syncthreads();
+  // marginalisation prior
+  if (W.marg_n > 0) {
+    const int n = W.marg_n;
+    // Delta chi
+    for (int b = tid; b < W.marg_nb; b += S_THREADS) {
+      const int kind = W.marg_kind[b], col = W.marg_col[b], xo = W.marg_off[b];
+      if (col < 0) continue;
+      if (kind == OKB_BLOCK_SPEED_BIAS) {
+        const double* x = W.sb_c + 9 * W.marg_idx[b];
+        for (int k = 0; k < 9; ++k) s_dchi[col + k] = x[k] - W.marg_x0[xo + k];
+      } else {
+        const double* x = (kind == OKB_BLOCK_POSE) ? W.pose_c + 7 * W.marg_idx[b] : W.ext + 7 * W.marg_idx[b];
+        pose_minus(W.marg_x0 + xo, x, s_dchi + col);
+      }
+    }
+    __syncthreads();
+    for (int r0 = tid; r0 < n; r0 += S_THREADS) {
+      double s = W.marg_e0[r0];
+      for (int c = 0; c < n; ++c) s += W.marg_J[(size_t)r0 * n + c] * s_dchi[c];
+      s_me[r0] = s;
+    }
+    __syncthreads();
+    for (int c = tid; c < n; c += S_THREADS) {   // J^T e
+      double s = 0;
+      for (int r0 = 0; r0 < n; ++r0) s += W.marg_J[(size_t)r0 * n + c] * s_me[r0];
+      s_mJte[c] = s;
+    }
+    __syncthreads();
+    // H_eff = B^T H0 B, g_eff = B^T J^T e, B = blockdiag(I3, Brot) for poses, I9 for speed/bias.
+    // Work block-pair by block-pair; each thread computes entries of one (bi,bj) pair.
+    for (int bp = 0; bp < W.marg_nb * W.marg_nb; ++bp) {
+      const int bi = bp / W.marg_nb, bj = bp % W.marg_nb;
+      const int ci = W.marg_col[bi], cj = W.marg_col[bj];
+      if (ci < 0 || cj < 0) continue;
+      const int ki = W.marg_kind[bi], kj = W.marg_kind[bj];
+      if (ki == OKB_BLOCK_EXTRINSICS || kj == OKB_BLOCK_EXTRINSICS) continue;  // fixed extrinsics only (v1)
+      const int mi = (ki == OKB_BLOCK_SPEED_BIAS) ? 9 : 6, mj = (kj == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
+      const int oi = (ki == OKB_BLOCK_POSE) ? 6 * (int)W.marg_idx[bi] : dc + 9 * (int)W.marg_idx[bi];
+      const int oj = (kj == OKB_BLOCK_POSE) ? 6 * (int)W.marg_idx[bj] : dc + 9 * (int)W.marg_idx[bj];
+      double Bi[9], Bj[9];
+      if (ki == OKB_BLOCK_POSE) marg_pose_rot_block(W.marg_x0 + W.marg_off[bi], W.pose_c + 7 * W.marg_idx[bi], Bi);
+      if (kj == OKB_BLOCK_POSE) marg_pose_rot_block(W.marg_x0 + W.marg_off[bj], W.pose_c + 7 * W.marg_idx[bj], Bj);
+      for (int e = tid; e < mi * mj; e += S_THREADS) {
+        const int a = e / mj, b = e % mj;
+        // (B_i^T H0_ij B_j)[a][b]
+        double s = 0;
+        const bool ra = (ki == OKB_BLOCK_POSE && a >= 3), rb = (kj == OKB_BLOCK_POSE && b >= 3);
+        if (!ra && !rb) s = W.marg_H0[(size_t)(ci + a) * n + cj + b];
+        else if (ra && !rb) { for (int k = 0; k < 3; ++k) s += Bi[k * 3 + (a - 3)] * W.marg_H0[(size_t)(ci + 3 + k) * n + cj + b]; }
+        else if (!ra && rb) { for (int k = 0; k < 3; ++k) s += W.marg_H0[(size_t)(ci + a) * n + cj + 3 + k] * Bj[k * 3 + (b - 3)]; }
+        else {
+          for (int k = 0; k < 3; ++k)
+            for (int k2 = 0; k2 < 3; ++k2) s += Bi[k * 3 + (a - 3)] * W.marg_H0[(size_t)(ci + 3 + k) * n + cj + 3 + k2] * Bj[k2 * 3 + (b - 3)];
+        }
+        Hd[(size_t)(oi + a) * d + oj + b] += s;
+      }
+      if (bi == bj) {
+        for (int a = tid; a < mi; a += S_THREADS) {
+          double s = 0;
+          if (ki == OKB_BLOCK_POSE && a >= 3) { for (int k = 0; k < 3; ++k) s += Bi[k * 3 + (a - 3)] * s_mJte[ci + 3 + k]; }
+          else s = s_mJte[ci + a];
+          gd[oi + a] += s;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      double c = 0;
+      for (int r0 = 0; r0 < n; ++r0) c += s_me[r0] * s_me[r0];
+      cost_dense_local += 0.5 * c;
+    }
+  }
+  const double cost_dense = block_sum(cost_dense_local, sh->red);
+
+  // ================= phase 2: gather kernel-A partials =================
+  double cost_lm = 0.0, stepn2_lm = 0.0;
+  for (int c = 0; c < W.n_chunks; ++c) {   // fixed order, replicated in all threads (tiny)
+    cost_lm += W.partA[(size_t)c * W.partA_stride + 0];
+    stepn2_lm += W.partA[(size_t)c * W.partA_stride + 1];
+  }
+  // H_pp / g_p block contributions
+  for (int i = tid; i < 27 * K; i += S_THREADS) {
+    double s = 0;
+    for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + 4 + i];
+    const int e = i / K, f = i % K, o = 6 * f;
+    if (e < 6) {          // H_tt symmetric packed
+      const int a = (e < 3) ? 0 : (e < 5) ? 1 : 2;
+      const int b = (e < 3) ? e : (e < 5) ? e - 2 : 2;
+      Hd[(size_t)(o + a) * d + o + b] += s;
+      if (a != b) Hd[(size_t)(o + b) * d + o + a] += s;
+    } else if (e < 15) {  // H_tr 3x3
+      const int a = (e - 6) / 3, b = (e - 6) % 3;
+      Hd[(size_t)(o + a) * d + o + 3 + b] += s;
+      Hd[(size_t)(o + 3 + b) * d + o + a] += s;
+    } else if (e < 21) {  // H_rr symmetric packed
+      const int q = e - 15;
+      const int a = (q < 3) ? 0 : (q < 5) ? 1 : 2;
+      const int b = (q < 3) ? q : (q < 5) ? q - 2 : 2;
+      Hd[(size_t)(o + 3 + a) * d + o + 3 + b] += s;
+      if (a != b) Hd[(size_t)(o + 3 + b) * d + o + 3 + a] += s;
+    } else {              // g_p
+      gd[o + (e - 21)] += s;
+    }
+  }
+  __syncthreads();
+
+  // ================= phase 3: judge =================
+  if (tid == 0) {
+    const unsigned long long now = globaltimer_ns();
+    sh->adopt = 0; sh->terminate = 0; sh->commit_only = 0; sh->fail = 0;
+    const double cand_cost = cost_lm + cost_dense;
+    sh->cand_cost = cand_cost;
+    if (mode == MODE_INIT) {
+      st->t_start_ns = now; st->t_iter_begin_ns = now; st->t_last_iter_ns = 0;
+      st->cost = cand_cost; st->initial_cost = cand_cost;
+      sh->adopt = 1;
+    } else if (mode == MODE_REBUILD) {
+      st->cost = cand_cost;
+      sh->adopt = 1;
+    } else {
+      const double step_norm = sqrt(stepn2_lm + st->cand_step_norm2_dense);
+      const double cost_change = st->cost - cand_cost;
+      if (step_norm <= kParameterTolerance * (sqrt(st->x_norm2) + kParameterTolerance)) {
+        st->termination = OKB_TERM_PARAMETER_TOL; sh->terminate = 1;
+      } else if (fabs(cost_change) < kFunctionTolerance * st->cost) {
+        st->termination = OKB_TERM_FUNCTION_TOL; sh->terminate = 1;
+      } else {
+        const double rel = cost_change / st->model_cost_change;
+        if (rel > kMinRelativeDecrease) {
+          st->num_successful += 1;
+          if (rel < 0.25) st->radius *= 0.5;
+          if (rel > 0.75) st->radius = fmax(st->radius, 3.0 * st->dogleg_step_norm);
+          st->mu = fmax(kMinMu, 2.0 * st->mu / kMuIncrease);
+          st->reuse = 0;
+          st->cost = cand_cost;
+          sh->adopt = 1;
+        } else {
+          st->radius *= 0.5;
+          st->reuse = 1;
+        }
+        if (st->radius < kMinRadius) {
+          st->termination = OKB_TERM_MIN_RADIUS;
+          if (sh->adopt) sh->commit_only = 1; else sh->terminate = 1;
+        }
+      }
+      st->t_last_iter_ns = now - st->t_iter_begin_ns;
+    }
+    if (st->numeric_fail && sh->adopt) sh->fail = 1;
+    st->numeric_fail = 0;
+  }
+  __syncthreads();
+  if (sh->terminate) {
+    if (tid == 0) { st->done = 1; st->solve_time_s = 1e-9 * (double)(globaltimer_ns() - st->t_start_ns); }
+    return;
+  }
+  const int adopt = sh->adopt;
+  int cur = st->cur;
+
+  // ================= phase 4: adopt the speculative linearisation =================
+  if (adopt) {
+    // commit dense parameters
+    for (int i = tid; i < 7 * K; i += S_THREADS) W.pose[i] = W.pose_c[i];
+    for (int i = tid; i < 9 * W.NSB; i += S_THREADS) W.sb[i] = W.sb_c[i];
+    cur = spec;
+    __syncthreads();
+    if (tid == 0) st->cur = cur;
+    for (int f = tid; f < K; f += S_THREADS) {
+      s_tws[4 * f] = W.pose[7 * f]; s_tws[4 * f + 1] = W.pose[7 * f + 1]; s_tws[4 * f + 2] = W.pose[7 * f + 2];
+    }
+    // metric E_d (and, once, the Jacobi scale)
+    for (int i = tid; i < d; i += S_THREADS) {
+      const double hjj = Hd[(size_t)i * d + i];
+      double sc;
+      if (mode == MODE_INIT) { sc = 1.0 / (1.0 + sqrt(hjj)); W.scale_d[i] = sc; }
+      else sc = W.scale_d[i];
+      const double s2 = sc * sc;
+      const double E = fmin(fmax(s2 * hjj, kMinDiag), kMaxDiag) / s2;
+      W.Ed[cur][i] = E;
+      s_E[i] = E;
+      s_g[i] = gd[i];
+      s_v[i] = gd[i] / E;
+    }
+    __syncthreads();
+    // VHV (dense-dense part): v^T H v
+    double vhv_loc = 0.0;
+    for (int i = tid; i < d; i += S_THREADS) {
+      double s = 0;
+      for (int j = 0; j < d; ++j) s += Hd[(size_t)i * d + j] * s_v[j];
+      vhv_loc += s_v[i] * s;
+    }
+    const double VHV_dd = block_sum(vhv_loc, sh->red);
+    // reduced system M = Hd + mu E - [Sacc], rhs = g - [sum Y z]
+    double* Mx = chol_in_smem ? s_big : W.chol;
+    const double mu = st->mu;
+    for (int i = tid; i < d * d; i += S_THREADS) {
+      const int r0 = i / d, c0 = i % d;
+      double v = Hd[i];
+      if (r0 == c0) v += mu * s_E[r0];
+      if (r0 < dc && c0 < dc) {
+        const int rr = r0 >= c0 ? r0 : c0, cc = r0 >= c0 ? c0 : r0;
+        double s = 0;
+        for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + 4 + 27 * K + (size_t)rr * dcp + cc];
+        v -= s;
+      }
+      Mx[i] = v;
+    }
+    for (int i = tid; i < d; i += S_THREADS) {
+      double v = s_g[i];
+      if (i < dc) {
+        double s = 0;
+        for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + 4 + 27 * K + (size_t)dc * dcp + i];
+        v -= s;
+      }
+      s_rhs[i] = v;
+    }
+    __syncthreads();
+    // ---- dense Cholesky (lower), right-looking
+    int chol_fail = sh->fail;
+    if (!chol_fail) {
+      const int ty = tid >> 5, tx = tid & 31;
+      for (int k = 0; k < d; ++k) {
+        const double piv = Mx[(size_t)k * d + k];
+        if (!(piv > 0.0)) { chol_fail = 1; break; }   // uniform: every thread reads the same value
+        const double inv = 1.0 / sqrt(piv);
+        __syncthreads();
+        for (int i = k + tid; i < d; i += S_THREADS) {
+          const double v = (i == k) ? sqrt(piv) : Mx[(size_t)i * d + k] * inv;
+          Mx[(size_t)i * d + k] = v;
+          s_col[i] = v;
+        }
+        __syncthreads();
+        for (int i = k + 1 + ty; i < d; i += S_WARPS) {
+          const double lik = s_col[i];
+          for (int j = k + 1 + tx; j <= i; j += 32) Mx[(size_t)i * d + j] -= lik * s_col[j];
+        }
+        __syncthreads();
+      }
+    }
+    if (!chol_fail) {
+      // forward / backward substitution (column oriented)
+      for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = s_rhs[i];
+      __syncthreads();
+      for (int k = 0; k < d; ++k) {
+        if (tid == 0) s_tmp[k] = s_tmp[k] / Mx[(size_t)k * d + k];
+        __syncthreads();
+        const double zk = s_tmp[k];
+        for (int i = k + 1 + tid; i < d; i += S_THREADS) s_tmp[i] -= Mx[(size_t)i * d + k] * zk;
+        __syncthreads();
+      }
+      for (int k = d - 1; k >= 0; --k) {
+        if (tid == 0) s_tmp[k] = s_tmp[k] / Mx[(size_t)k * d + k];
+        __syncthreads();
+        const double uk = s_tmp[k];
+        for (int i = tid; i < k; i += S_THREADS) s_tmp[i] -= Mx[(size_t)k * d + i] * uk;
+        __syncthreads();
+      }
+      for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
+      __syncthreads();
+    }
+    // ---- landmarks: commit, back-substitute, scalar reductions
+    double N2 = 0, GU = 0, G2 = 0, VHV = 0, xn2 = 0, gmax = 0;
+    int bad = 0;
+    const double* gl_ = W.lm_g[cur];
+    const double* El_ = W.lm_E[cur];
+    for (int l = tid; l < L; l += S_THREADS) {
+      const double4 X = *reinterpret_cast<const double4*>(W.lm_c + 4 * (size_t)l);
+      *reinterpret_cast<double4*>(W.lm + 4 * (size_t)l) = X;
+      xn2 += X.x * X.x + X.y * X.y + X.z * X.z + X.w * X.w;
+      if (chol_fail) continue;
+      const double g0 = gl_[3 * (size_t)l], g1 = gl_[3 * (size_t)l + 1], g2 = gl_[3 * (size_t)l + 2];
+      const double E0 = El_[3 * (size_t)l], E1 = El_[3 * (size_t)l + 1], E2 = El_[3 * (size_t)l + 2];
+      const double v0 = g0 / E0, v1 = g1 / E1, v2 = g2 / E2;
+      double q0 = 0, q1 = 0, q2 = 0;        // sum_f M_f (G_f u_f)
+      double hv = 0;                        // sum_f v^T M_f (v - 2 G_f v_f)
+      uint32_t vis = W.lm_vis[l];
+      while (vis) {
+        const int f = __ffs(vis) - 1;
+        vis &= vis - 1;
+        const double* Mo = W.lm_M + ((size_t)f * L + l) * 6;
+        const double M0 = Mo[0], M1 = Mo[1], M2 = Mo[2], M3 = Mo[3], M4 = Mo[4], M5 = Mo[5];
+        const double p0 = X.x - s_tws[4 * f] * X.w, p1 = X.y - s_tws[4 * f + 1] * X.w, p2 = X.z - s_tws[4 * f + 2] * X.w;
+        const double* uf = s_u + 6 * f;
+        const double* vf = s_v + 6 * f;
+        // G y = w y_t + y_r x p
+        const double a0 = X.w * uf[0] + (uf[4] * p2 - uf[5] * p1);
+        const double a1 = X.w * uf[1] + (uf[5] * p0 - uf[3] * p2);
+        const double a2 = X.w * uf[2] + (uf[3] * p1 - uf[4] * p0);
+        q0 += M0 * a0 + M1 * a1 + M2 * a2;
+        q1 += M1 * a0 + M3 * a1 + M4 * a2;
+        q2 += M2 * a0 + M4 * a1 + M5 * a2;
+        const double b0 = v0 - 2.0 * (X.w * vf[0] + (vf[4] * p2 - vf[5] * p1));
+        const double b1 = v1 - 2.0 * (X.w * vf[1] + (vf[5] * p0 - vf[3] * p2));
+        const double b2 = v2 - 2.0 * (X.w * vf[2] + (vf[3] * p1 - vf[4] * p0));
+        hv += v0 * (M0 * b0 + M1 * b1 + M2 * b2) + v1 * (M1 * b0 + M3 * b1 + M4 * b2) + v2 * (M2 * b0 + M4 * b1 + M5 * b2);
+      }
+      const double* Ri = W.lm_Rinv + 6 * (size_t)l;
+      const double t0 = g0 + q0, t1 = g1 + q1, t2 = g2 + q2;
+      const double u0 = Ri[0] * t0 + Ri[1] * t1 + Ri[2] * t2;
+      const double u1 = Ri[1] * t0 + Ri[3] * t1 + Ri[4] * t2;
+      const double u2 = Ri[2] * t0 + Ri[4] * t1 + Ri[5] * t2;
+      W.lm_gn[3 * (size_t)l] = -u0; W.lm_gn[3 * (size_t)l + 1] = -u1; W.lm_gn[3 * (size_t)l + 2] = -u2;
+      if (!(isfinite(u0) && isfinite(u1) && isfinite(u2))) bad = 1;
+      N2 += E0 * u0 * u0 + E1 * u1 * u1 + E2 * u2 * u2;
+      GU += g0 * u0 + g1 * u1 + g2 * u2;
+      G2 += g0 * v0 + g1 * v1 + g2 * v2;
+      VHV += hv;
+      gmax = fmax(gmax, fmax(fabs(g0), fmax(fabs(g1), fabs(g2))));
+    }
+    for (int i = tid; i < d; i += S_THREADS) {
+      if (chol_fail) break;
+      const double u = s_u[i], g = s_g[i], E = s_E[i];
+      if (!isfinite(u)) bad = 1;
+      N2 += E * u * u; GU += g * u; G2 += g * g / E;
+      gmax = fmax(gmax, fabs(g));
+    }
+    for (int i = tid; i < 7 * K; i += S_THREADS) xn2 += W.pose[i] * W.pose[i];
+    for (int i = tid; i < 9 * W.NSB; i += S_THREADS) xn2 += W.sb[i] * W.sb[i];
+    N2 = block_sum(N2, sh->red);
+    GU = block_sum(GU, sh->red);
+    G2 = block_sum(G2, sh->red);
+    VHV = block_sum(VHV, sh->red) + VHV_dd;
+    xn2 = block_sum(xn2, sh->red);
+    gmax = block_max(gmax, sh->red);
+    const double badsum = block_sum((double)bad, sh->red);
+    if (tid == 0) {
+      st->x_norm2 = xn2;
+      st->grad_max = gmax;
+      st->numeric_fail = 0;
+      if (chol_fail || badsum > 0) {
+        sh->fail = 1;
+      } else {
+        st->G2 = G2; st->VHV = VHV; st->GU = GU; st->N2 = N2;
+        sh->fail = 0;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ================= phase 5: loop top (callbacks, iteration limit), dogleg step =================
+  if (tid == 0) {
+    const unsigned long long now = globaltimer_ns();
+    int finish = 0;
+    if (sh->commit_only) finish = 1;                       // min radius reached after an accepted step
+    else if (sh->fail) {
+      // linear solver failure: DoglegStrategy raises mu and retries inside ComputeStep; if mu is
+      // exhausted the step is invalid (counts as an iteration, StepIsInvalid raises mu again).
+      st->mu *= kMuIncrease;
+      if (st->mu >= kMaxMu) {
+        st->iteration += 1;
+        st->num_invalid += 1;
+        if (st->num_invalid >= kMaxConsecutiveInvalid) { st->termination = OKB_TERM_FAILURE; finish = 1; }
+        st->mu *= kMuIncrease;
+      }
+      st->reuse = 0;
+      st->mode = MODE_REBUILD;
+      st->a = 0; st->b = 0;
+      sh->spec = -1;   // no candidate computation
+    } else {
+      if (adopt && st->grad_max <= kGradientTolerance) { st->termination = OKB_TERM_GRADIENT_TOL; finish = 1; }
+      // IterationCallback on the summary of the iteration that just ended
+      const double elapsed = 1e-9 * (double)(now - st->t_start_ns);
+      const double last = 1e-9 * (double)st->t_last_iter_ns;
+      if (!finish && opt.time_limit_s >= 0.0 && st->iteration >= opt.min_iterations && elapsed + last > opt.time_limit_s) {
+        st->termination = OKB_TERM_TIME_LIMIT; finish = 1;
+      }
+      if (!finish && st->iteration >= opt.max_iterations) { st->termination = OKB_TERM_NO_CONVERGENCE; finish = 1; }
+      if (!finish) {
+        st->iteration += 1;
+        st->t_iter_begin_ns = now;
+        // ---- traditional dogleg in the metric E (== Ceres' diagonal-scaled space)
+        const double G2 = st->G2, VHV = st->VHV, GU = st->GU, N2 = st->N2, mu = st->mu, radius = st->radius;
+        const double alpha = G2 / VHV;
+        const double gnorm = sqrt(G2), gn_norm = sqrt(N2);
+        double a, b, dl;
+        if (gn_norm <= radius) { a = 0.0; b = 1.0; dl = gn_norm; }
+        else if (gnorm * alpha >= radius) { a = -radius / gnorm; b = 0.0; dl = radius; }
+        else {
+          const double b_dot_a = alpha * GU;                   // -alpha * (ghat . GN), ghat.GN = -GU
+          const double a_sq = alpha * alpha * G2;
+          const double bma = a_sq - 2.0 * b_dot_a + N2;
+          const double c = b_dot_a - a_sq;
+          const double dd = sqrt(c * c + bma * (radius * radius - a_sq));
+          const double beta = (c <= 0) ? (dd - c) / bma : (radius * radius - a_sq) / (dd + c);
+          a = -alpha * (1.0 - beta); b = beta;
+          dl = sqrt(fmax(0.0, a * a * G2 - 2.0 * a * b * GU + b * b * N2));
+        }
+        // model cost change = -step^T g - 0.5 step^T H step, step = a v + b (-u)
+        const double sg = a * G2 - b * GU;
+        const double vHu = G2 - mu * GU, uHu = GU - mu * N2;
+        const double sHs = a * a * VHV - 2.0 * a * b * vHu + b * b * uHu;
+        const double mcc = -sg - 0.5 * sHs;
+        st->a = a; st->b = b; st->dogleg_step_norm = dl; st->model_cost_change = mcc;
+        if (!(mcc >= 0.0)) {
+          st->num_invalid += 1;
+          if (st->num_invalid >= kMaxConsecutiveInvalid) { st->termination = OKB_TERM_FAILURE; finish = 1; }
+          st->mu *= kMuIncrease;          // StepIsInvalid
+          st->reuse = 0;
+          st->mode = MODE_REBUILD;
+          st->a = 0; st->b = 0;
+          sh->spec = -1;
+        } else {
+          st->num_invalid = 0;
+          st->mode = MODE_STEP;
+          sh->spec = 1;
+        }
+      }
+    }
+    if (finish) {
+      int redo = 0;
+      for (int t = 0; t < W.n_imu; ++t) redo += W.imu_cache[t].redo_count;
+      st->imu_redo_final = redo - st->imu_redo;
+      st->done = 1;
+      st->solve_time_s = 1e-9 * (double)(globaltimer_ns() - st->t_start_ns);
+      sh->spec = 0;
+    }
+  }
+  __syncthreads();
+  const int what = sh->spec;
+  if (what == 0) return;
+
+  // ================= phase 6: candidate dense parameters =================
+  {
+    const double a = st->a, b = st->b;
+    const double* gcur = W.gd[cur];
+    const double* Ecur = W.Ed[cur];
+    for (int i = tid; i < d; i += S_THREADS) s_delta[i] = (what == 1) ? (a * gcur[i] / Ecur[i] - b * W.ud[i]) : 0.0;
+    __syncthreads();
+    double sn2 = 0.0;
+    for (int f = tid; f < K; f += S_THREADS) {
+      double o[7];
+      if (what == 1) pose_plus(W.pose + 7 * f, s_delta + 6 * f, o);
+      else for (int k = 0; k < 7; ++k) o[k] = W.pose[7 * f + k];
+      for (int k = 0; k < 7; ++k) {
+        const double dlt = o[k] - W.pose[7 * f + k];
+        sn2 += dlt * dlt;
+        W.pose_c[7 * f + k] = o[k];
+      }
+    }
+    for (int i = tid; i < 9 * W.NSB; i += S_THREADS) {
+      const double dlt = s_delta[dc + i];
+      W.sb_c[i] = W.sb[i] + dlt;
+      sn2 += dlt * dlt;
+    }
+    sn2 = block_sum(sn2, sh->red);
+    if (tid == 0) st->cand_step_norm2_dense = sn2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Post-solve landmark quality: H = sum J_lm^T J_lm (sqrt-information weighted, no robust weight)
+// at the final estimate; quality = sqrt(lambda_min)/sqrt(lambda_max), 0 if lambda_min < 1e-12.
+// Warp per landmark, lane per slot.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_quality(const WinDev* __restrict__ wins, int win_first) {
+  const WinDev& W = wins[win_first + blockIdx.y];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SlotCtx* slots = reinterpret_cast<SlotCtx*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int s = tid; s < W.NSP; s += blockDim.x) {
+    const SlotInfo si = W.slots[s];
+    SlotCtx& sc = slots[s];
+    sc.valid = si.valid; sc.frame = si.valid ? si.pose_idx : 0;
+    if (si.valid) { make_slot_xf(W.pose + 7 * si.pose_idx, W.ext + 7 * si.ext_idx, sc.xf); cam_load(W.cams[si.cam_idx], sc.cam); }
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  for (int l = blockIdx.x * nw + warp; l < W.L; l += gridDim.x * nw) {
+    const double4 x4 = *reinterpret_cast<const double4*>(W.lm + 4 * (size_t)l);
+    const double X[4] = {x4.x, x4.y, x4.z, x4.w};
+    double H[6] = {0, 0, 0, 0, 0, 0};
+    for (int g = 0; g < W.NG; ++g) {
+      const int slot = g * 32 + lane;
+      const SlotCtx& sc = slots[slot];
+      const double2 z = W.obs_z[(size_t)l * W.NSP + slot];
+      const double wobs = W.obs_w[(size_t)l * W.NSP + slot];
+      if (wobs > 0.0 && sc.valid) {
+        double r[2], A[6];
+        reproj_slot<true>(sc.xf, sc.cam, X, z.x, z.y, wobs, r, A);
+        H[0] += A[0] * A[0] + A[3] * A[3]; H[1] += A[0] * A[1] + A[3] * A[4]; H[2] += A[0] * A[2] + A[3] * A[5];
+        H[3] += A[1] * A[1] + A[4] * A[4]; H[4] += A[1] * A[2] + A[4] * A[5]; H[5] += A[2] * A[2] + A[5] * A[5];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) H[i] = warp_sum(H[i]);
+    if (lane == 0) {
+      double ev[3];
+      eig3sym(H, ev);
+      W.quality[l] = (ev[0] < 1.0e-12) ? 0.0 : sqrt(ev[0]) / sqrt(ev[2]);
+    }
+  }
+}
+
+// resets the solver state (and optionally the parameter state) of a range of windows
+__global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int restore_params) {
+  const WinDev& W = wins[win_first + blockIdx.x];
+  const int tid = threadIdx.x;
+  if (restore_params) {
+    for (int i = tid; i < 7 * W.K; i += blockDim.x) W.pose[i] = W.pose_init[i];
+    for (int i = tid; i < 9 * W.NSB; i += blockDim.x) W.sb[i] = W.sb_init[i];
+    for (int i = tid; i < 4 * W.L; i += blockDim.x) W.lm[i] = W.lm_init[i];
+    const int nb = (int)(sizeof(ImuCache) / sizeof(double));
+    for (int t = 0; t < W.n_imu; ++t) {
+      double* dst = reinterpret_cast<double*>(W.imu_cache + t);
+      const double* src = reinterpret_cast<const double*>(W.imu_cache_init + t);
+      for (int i = tid; i < nb; i += blockDim.x) dst[i] = src[i];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 7 * W.K; i += blockDim.x) W.pose_c[i] = W.pose[i];
+  for (int i = tid; i < 9 * W.NSB; i += blockDim.x) W.sb_c[i] = W.sb[i];
+  if (tid == 0) {
+    SolverState* st = W.st;
+    st->mode = MODE_INIT; st->done = 0; st->cur = 0;
+    st->iteration = 0; st->num_successful = 0; st->num_invalid = 0; st->termination = OKB_TERM_NO_CONVERGENCE;
+    st->reuse = 0; st->numeric_fail = 0;
+    st->radius = kInitialRadius; st->mu = kMinMu; st->mu_spec = kMinMu;
+    st->cost = 0; st->initial_cost = 0; st->x_norm2 = 0;
+    st->G2 = st->VHV = st->GU = st->N2 = 0; st->a = 0; st->b = 0;
+    st->model_cost_change = 0; st->dogleg_step_norm = 0; st->cand_step_norm2_dense = 0; st->grad_max = 0;
+    st->t_start_ns = 0; st->t_last_iter_ns = 0; st->t_iter_begin_ns = 0; st->solve_time_s = 0;
+    int redo = 0;
+    for (int t = 0; t < W.n_imu; ++t) redo += W.imu_cache[t].redo_count;
+    st->imu_redo = redo;   // baseline; the summary reports the difference
+    st->imu_redo_final = 0;
+  }
+}
+
+}  // namespace okb
