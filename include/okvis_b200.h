@@ -214,6 +214,13 @@ int okb_optimize_finish(okb_ctx* ctx, int win_first, int win_count, okb_summary*
 int okb_window_download(okb_ctx* ctx, int win, double* poses, double* speed_bias,
                         double* landmarks, double* quality);
 
+/* Optional per-kernel device timing: CUDA events on the context stream around every solver kernel
+ * launch.  okb_profile_enable(ctx,1) clears the counters; okb_profile_read synchronises and returns
+ * out[0] = ms in k_landmarks, out[1] = its launches, out[2] = ms in k_solve, out[3] = launches,
+ * out[4] = ms in k_quality, out[5] = launches. */
+int okb_profile_enable(okb_ctx* ctx, int on);
+int okb_profile_read(okb_ctx* ctx, double out[6]);
+
 /* ------------------------------------------------- single-block test hooks
  * Mirror ErrorInterface::EvaluateWithMinimalJacobians (okvis_ceres/include/okvis/ceres/ErrorInterface.hpp:93-95).
  * All run on the device through the same device functions the solver uses.  Jacobians are the

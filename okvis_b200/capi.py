@@ -64,6 +64,15 @@ class Context:
     def stream(self):
         return lib().okb_stream(self._h)
 
+    def profile_enable(self, on=True):
+        self._check(lib().okb_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        out = np.zeros(6)
+        self._check(lib().okb_profile_read(self._h, _p(out)))
+        return dict(landmarks_ms=out[0], landmarks_launches=int(out[1]), solve_ms=out[2], solve_launches=int(out[3]),
+                    quality_ms=out[4], quality_launches=int(out[5]))
+
     # ---------------------------------------------------------------- estimator path
     def upload(self, win, window):
         d = window.desc()

@@ -35,6 +35,10 @@ struct okb_ctx {
   size_t hook_bytes = 0;
   okb_frontend_state* frontend = nullptr;
   int64_t launches = 0;
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
+  std::vector<int> prof_kind;             // kernel id per pair
+  size_t prof_used = 0;
   std::string error;
   void set_error(const std::string& e) { error = e; }
 };

@@ -84,6 +84,7 @@ extern "C" void okb_ctx_destroy(okb_ctx* c) {
   if (c->d_states) cudaFree(c->d_states);
   if (c->h_states) cudaFreeHost(c->h_states);
   if (c->hook_buf) cudaFree(c->hook_buf);
+  for (auto e : c->prof_events) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -313,6 +314,47 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   return OKB_OK;
 }
 
+// ---- optional event timing around solver kernels
+static void prof_begin(okb_ctx* c, int kind) {
+  if (!c->profile) return;
+  if (c->prof_used + 2 > c->prof_events.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    c->prof_events.push_back(a); c->prof_events.push_back(b);
+  }
+  c->prof_kind.push_back(kind);
+  cudaEventRecord(c->prof_events[c->prof_used], c->stream);
+}
+static void prof_end(okb_ctx* c) {
+  if (!c->profile) return;
+  cudaEventRecord(c->prof_events[c->prof_used + 1], c->stream);
+  c->prof_used += 2;
+}
+extern "C" int okb_profile_enable(okb_ctx* c, int on) {
+  if (!c) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->profile = on != 0;
+  c->prof_used = 0;
+  c->prof_kind.clear();
+  return OKB_OK;
+}
+extern "C" int okb_profile_read(okb_ctx* c, double out[6]) {
+  if (!c || !out) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 6; ++i) out[i] = 0.0;
+  for (size_t i = 0; i < c->prof_kind.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->prof_events[2 * i], c->prof_events[2 * i + 1]);
+    out[2 * c->prof_kind[i]] += ms;
+    out[2 * c->prof_kind[i] + 1] += 1.0;
+  }
+  c->prof_used = 0;
+  c->prof_kind.clear();
+  return OKB_OK;
+}
+
 static int check_range(okb_ctx* c, int first, int count) {
   if (!c || first < 0 || count < 1 || first + count > c->max_windows) return OKB_ERR_INVALID_ARG;
   for (int i = first; i < first + count; ++i)
@@ -352,9 +394,13 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
   if (smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
   for (int r = 0; r < rounds; ++r) {
     const dim3 gridA(max_chunks, count);
+    prof_begin(c, 0);
     if (tpt == 1) k_landmarks<1><<<gridA, A_THREADS, smA, c->stream>>>(c->d_wins, first);
     else k_landmarks<2><<<gridA, A_THREADS, smA, c->stream>>>(c->d_wins, first);
+    prof_end(c);
+    prof_begin(c, 1);
     k_solve<<<count, S_THREADS, smS, c->stream>>>(c->d_wins, first, opt, chol_smem ? 1 : 0);
+    prof_end(c);
     c->launches += 2;
   }
   OKB_CUDA(c, cudaGetLastError());
@@ -404,7 +450,9 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
     size_t smQ = 0;
     for (int i = first; i < first + count; ++i) smQ = std::max(smQ, (size_t)c->host[i].NSP * sizeof(SlotCtx));
     const int gx = std::max(1, std::min(64, (2 * c->sm_count + count - 1) / count));
+    prof_begin(c, 2);
     k_quality<<<dim3(gx, count), 256, smQ, c->stream>>>(c->d_wins, first);
+    prof_end(c);
     c->launches += 1;
     OKB_CUDA(c, cudaGetLastError());
   }

@@ -1,3 +1,689 @@
-// Frontend path (BRISK-style detect/describe + Hamming matching) -- implemented in a later commit.
+// Frontend path of libokvis_b200.so (sm_100a): Harris detect -> uniformity -> gravity-aligned
+// 48/64-byte binary descriptor, and the DenseMatcher Hamming brute force.
+//   okb_detect_describe   <- Frontend::detectAndDescribe (okvis_frontend/src/Frontend.cpp:92-114)
+//   okb_hamming_match     <- DenseMatcher::match          (okvis_matcher/include/okvis/implementation/DenseMatcher.hpp:48-225,
+//                                                          okvis_matcher/src/DenseMatcher.cpp:69-110)
+//   okb_hamming_candidates<- VioKeyframeWindowMatchingAlgorithm::specificDescriptorDistance (…hpp:246-254)
+// The detector / descriptor follow this project's own specification (DESIGN.md "Frontend spec"):
+// brisk 2.0.5 is not part of the reference tree.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <mutex>
+#include <vector>
+
 #include "okb_ctx.h"
-void okb_frontend_release(okb_ctx*) {}
+#include "okb_math.cuh"
+
+using namespace okb;
+
+#define FE_CUDA(ctx, call)                                                      \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      (ctx)->set_error(std::string(#call) + ": " + cudaGetErrorString(e_));     \
+      return OKB_ERR_CUDA;                                                      \
+    }                                                                           \
+  } while (0)
+
+namespace {
+constexpr int kBorder = 16;
+constexpr int kRotBins = 1024;
+constexpr int kPts = 60;
+constexpr int kMaxSlots = 8;          // concurrent camera slots
+constexpr int kMaxCand = 1 << 17;     // NMS candidates per image
+
+struct Pattern {
+  int half[kPts];
+  std::vector<uint8_t> pi, pj;
+  std::vector<int16_t> lut;
+};
+
+Pattern make_pattern(int desc_bytes) {
+  Pattern P;
+  double px[kPts], py[kPts];
+  const double rList[5] = {0.0, 2.9 * 0.85, 4.9 * 0.85, 7.4 * 0.85, 10.8 * 0.85};
+  const int nList[5] = {1, 10, 14, 15, 20};
+  int idx = 0;
+  for (int ring = 0; ring < 5; ++ring) {
+    const double sigma = 1.3 * (ring == 0 ? rList[1] * std::sin(M_PI / nList[1]) : rList[ring] * std::sin(M_PI / nList[ring]));
+    for (int a = 0; a < nList[ring]; ++a) {
+      const double alpha = 2.0 * M_PI * a / nList[ring];
+      px[idx] = rList[ring] * std::cos(alpha);
+      py[idx] = rList[ring] * std::sin(alpha);
+      P.half[idx] = std::max(1, (int)std::lround(sigma));
+      ++idx;
+    }
+  }
+  struct Pr { double d; int i, j; };
+  std::vector<Pr> all;
+  for (int i = 0; i < kPts; ++i)
+    for (int j = i + 1; j < kPts; ++j) {
+      const double dx = px[i] - px[j], dy = py[i] - py[j];
+      all.push_back({dx * dx + dy * dy, i, j});
+    }
+  std::stable_sort(all.begin(), all.end(), [](const Pr& a, const Pr& b) {
+    if (a.d != b.d) return a.d < b.d;
+    if (a.i != b.i) return a.i < b.i;
+    return a.j < b.j;
+  });
+  for (int k = 0; k < 8 * desc_bytes; ++k) { P.pi.push_back((uint8_t)all[k].i); P.pj.push_back((uint8_t)all[k].j); }
+  P.lut.resize((size_t)kRotBins * kPts * 2);
+  for (int r = 0; r < kRotBins; ++r) {
+    const double ang = 2.0 * M_PI * r / kRotBins, c = std::cos(ang), s = std::sin(ang);
+    for (int p = 0; p < kPts; ++p) {
+      P.lut[((size_t)r * kPts + p) * 2 + 0] = (int16_t)std::lround(px[p] * c - py[p] * s);
+      P.lut[((size_t)r * kPts + p) * 2 + 1] = (int16_t)std::lround(px[p] * s + py[p] * c);
+    }
+  }
+  return P;
+}
+
+struct SlotBuffers {
+  cudaStream_t stream = nullptr;
+  int W = 0, H = 0;
+  uint8_t* d_img = nullptr;
+  int32_t* d_score = nullptr;
+  uint32_t* d_integral = nullptr;
+  unsigned long long *d_keys = nullptr, *d_keys_sorted = nullptr;
+  int* d_count = nullptr;          // [0] candidates, [1] accepted
+  void* d_cub = nullptr;
+  size_t cub_bytes = 0;
+  okb_keypoint* d_kp = nullptr;
+  uint8_t* d_desc = nullptr;
+  int kp_cap = 0, desc_cap = 0;
+  uint8_t* h_img = nullptr;        // pinned
+  okb_keypoint* h_kp = nullptr;    // pinned
+  uint8_t* h_desc = nullptr;       // pinned
+  int* h_count = nullptr;          // pinned
+  std::mutex mtx;
+};
+}  // namespace
+
+struct okb_frontend_state {
+  SlotBuffers slots[kMaxSlots];
+  // pattern (device), per descriptor length
+  int pat_bytes = 0;
+  int* d_half = nullptr;
+  uint8_t *d_pi = nullptr, *d_pj = nullptr;
+  int16_t* d_lut = nullptr;
+  std::mutex pat_mtx;
+  // matcher buffers
+  uint8_t *d_A = nullptr, *d_B = nullptr, *d_skipA = nullptr, *d_skipB = nullptr;
+  size_t capA = 0, capB = 0;
+  okb_pair *d_topk = nullptr, *d_pairs = nullptr;
+  size_t cap_topk = 0, cap_pairs = 0;
+  uint32_t *d_rowptr = nullptr, *d_col = nullptr;
+  uint16_t* d_dist = nullptr;
+  size_t cap_rows = 0, cap_cand = 0;
+  std::mutex match_mtx;
+};
+
+void okb_frontend_release(okb_ctx* c) {
+  if (!c->frontend) return;
+  okb_frontend_state* F = c->frontend;
+  for (auto& s : F->slots) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    cudaFree(s.d_img); cudaFree(s.d_score); cudaFree(s.d_integral); cudaFree(s.d_keys); cudaFree(s.d_keys_sorted);
+    cudaFree(s.d_count); cudaFree(s.d_cub); cudaFree(s.d_kp); cudaFree(s.d_desc);
+    if (s.h_img) cudaFreeHost(s.h_img);
+    if (s.h_kp) cudaFreeHost(s.h_kp);
+    if (s.h_desc) cudaFreeHost(s.h_desc);
+    if (s.h_count) cudaFreeHost(s.h_count);
+  }
+  cudaFree(F->d_half); cudaFree(F->d_pi); cudaFree(F->d_pj); cudaFree(F->d_lut);
+  cudaFree(F->d_A); cudaFree(F->d_B); cudaFree(F->d_skipA); cudaFree(F->d_skipB); cudaFree(F->d_topk); cudaFree(F->d_pairs);
+  cudaFree(F->d_rowptr); cudaFree(F->d_col); cudaFree(F->d_dist);
+  delete F;
+  c->frontend = nullptr;
+}
+
+static okb_frontend_state* fe(okb_ctx* c) {
+  static std::mutex m;
+  std::lock_guard<std::mutex> lk(m);
+  if (!c->frontend) c->frontend = new okb_frontend_state();
+  return c->frontend;
+}
+
+// =================================================================================================
+// detector kernels
+// =================================================================================================
+namespace {
+constexpr int HT_X = 32, HT_Y = 8;
+
+// Integer Harris score: Scharr gradients, 5x5 binomial window.  One thread per pixel; the tile's
+// gradient products live in shared memory.
+__global__ void __launch_bounds__(HT_X* HT_Y) k_harris(const uint8_t* __restrict__ img, int W, int H, int32_t* __restrict__ score) {
+  __shared__ uint8_t tile[HT_Y + 6][HT_X + 6 + 2];
+  __shared__ int32_t sxx[HT_Y + 4][HT_X + 4], syy[HT_Y + 4][HT_X + 4], sxy[HT_Y + 4][HT_X + 4];
+  const int bx = blockIdx.x * HT_X, by = blockIdx.y * HT_Y;
+  const int tid = threadIdx.y * HT_X + threadIdx.x;
+  for (int i = tid; i < (HT_Y + 6) * (HT_X + 6); i += HT_X * HT_Y) {
+    const int ty = i / (HT_X + 6), tx = i % (HT_X + 6);
+    const int gx = min(max(bx + tx - 3, 0), W - 1), gy = min(max(by + ty - 3, 0), H - 1);
+    tile[ty][tx] = img[(size_t)gy * W + gx];
+  }
+  __syncthreads();
+  for (int i = tid; i < (HT_Y + 4) * (HT_X + 4); i += HT_X * HT_Y) {
+    const int ty = i / (HT_X + 4), tx = i % (HT_X + 4);
+    const int gxp = bx + tx - 2, gyp = by + ty - 2;          // pixel whose gradient this is
+    int vxx = 0, vyy = 0, vxy = 0;
+    if (gxp >= 1 && gxp < W - 1 && gyp >= 1 && gyp < H - 1) {
+      const int cy = ty + 1, cx = tx + 1;                     // tile coordinates of that pixel
+      const int gx = 3 * ((int)tile[cy - 1][cx + 1] - (int)tile[cy - 1][cx - 1]) + 10 * ((int)tile[cy][cx + 1] - (int)tile[cy][cx - 1]) +
+                     3 * ((int)tile[cy + 1][cx + 1] - (int)tile[cy + 1][cx - 1]);
+      const int gy = 3 * ((int)tile[cy + 1][cx - 1] - (int)tile[cy - 1][cx - 1]) + 10 * ((int)tile[cy + 1][cx] - (int)tile[cy - 1][cx]) +
+                     3 * ((int)tile[cy + 1][cx + 1] - (int)tile[cy - 1][cx + 1]);
+      vxx = gx * gx; vyy = gy * gy; vxy = gx * gy;
+    }
+    sxx[ty][tx] = vxx; syy[ty][tx] = vyy; sxy[ty][tx] = vxy;
+  }
+  __syncthreads();
+  const int x = bx + threadIdx.x, y = by + threadIdx.y;
+  if (x >= W || y >= H) return;
+  int32_t out = 0;
+  if (x >= 3 && x < W - 3 && y >= 3 && y < H - 3) {
+    const int w5[5] = {1, 4, 6, 4, 1};
+    long long a = 0, b = 0, c = 0;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) {
+        const long long wgt = w5[dy] * w5[dx];
+        a += wgt * sxx[threadIdx.y + dy][threadIdx.x + dx];
+        b += wgt * syy[threadIdx.y + dy][threadIdx.x + dx];
+        c += wgt * sxy[threadIdx.y + dy][threadIdx.x + dx];
+      }
+    a >>= 8; b >>= 8; c >>= 8;
+    long long s = (a * b - c * c) - (((a + b) * (a + b)) >> 4);
+    s >>= 12;
+    if (s > 2147483647LL) s = 2147483647LL;
+    if (s < -2147483647LL) s = -2147483647LL;
+    out = (int32_t)s;
+  }
+  score[(size_t)y * W + x] = out;
+}
+
+// 3x3 strict NMS + threshold + border -> sortable 64-bit keys (score desc, raster index asc)
+__global__ void k_nms(const int32_t* __restrict__ score, int W, int H, int32_t thr, unsigned long long* keys, int* count, int cap) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < kBorder || x >= W - kBorder || y < kBorder || y >= H - kBorder) return;
+  const int32_t s = score[(size_t)y * W + x];
+  if (s < thr) return;
+  bool mx = true;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      if (dy == 0 && dx == 0) continue;
+      mx = mx && (s > score[(size_t)(y + dy) * W + x + dx]);
+    }
+  if (!mx) return;
+  const int slot = atomicAdd(count, 1);
+  if (slot < cap) keys[slot] = ((unsigned long long)(uint32_t)s << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(y * W + x));
+}
+
+// Greedy uniformity in sorted order with an occupancy bitmap in shared memory (one CTA per image).
+__global__ void __launch_bounds__(256) k_uniformity(const unsigned long long* __restrict__ keys, const int* __restrict__ count, int cap,
+                                                    int W, int H, double radius, int max_kp, okb_keypoint* kps, int* n_out) {
+  extern __shared__ uint32_t occ[];   // W*H bits
+  __shared__ int s_next, s_idx, s_acc;
+  const int nwords = (W * H + 31) / 32;
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) occ[i] = 0u;
+  if (threadIdx.x == 0) { s_next = 0; s_acc = 0; }
+  __syncthreads();
+  const int n = min(*count, cap);
+  const double r2 = radius * radius;
+  const int R = (int)ceil(radius);
+  while (true) {
+    if (threadIdx.x == 0) {
+      int i = s_next, found = -1;
+      while (i < n && s_acc < max_kp) {
+        const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull);
+        if (!((occ[idx >> 5] >> (idx & 31)) & 1u)) { found = (int)idx; break; }
+        ++i;
+      }
+      s_idx = found;
+      if (found >= 0) {
+        const unsigned long long k = keys[i];
+        okb_keypoint kp;
+        kp.x = (float)(found % W); kp.y = (float)(found / W); kp.size = 12.0f; kp.angle = 0.0f;
+        kp.response = (float)(int32_t)(uint32_t)(k >> 32); kp.octave = 0;
+        kps[s_acc] = kp;
+        s_acc += 1;
+        s_next = i + 1;
+      }
+    }
+    __syncthreads();
+    const int idx = s_idx;
+    if (idx < 0) break;
+    const int cx = idx % W, cy = idx / W;
+    const int side = 2 * R + 1;
+    for (int e = threadIdx.x; e < side * side; e += blockDim.x) {
+      const int dy = e / side - R, dx = e % side - R;
+      const int x = cx + dx, y = cy + dy;
+      if (x < 0 || x >= W || y < 0 || y >= H) continue;
+      if ((double)(dx * dx + dy * dy) < r2) {
+        const uint32_t p = (uint32_t)(y * W + x);
+        atomicOr(&occ[p >> 5], 1u << (p & 31));
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_out = s_acc;
+}
+
+// integral image (H+1) x (W+1), uint32
+__global__ void k_integral_rows(const uint8_t* __restrict__ img, int W, int H, uint32_t* II) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y > H) return;
+  uint32_t* row = II + (size_t)y * (W + 1);
+  if (y == 0) { for (int x = 0; x <= W; ++x) row[x] = 0; return; }
+  uint32_t s = 0;
+  row[0] = 0;
+  for (int x = 0; x < W; ++x) { s += img[(size_t)(y - 1) * W + x]; row[x + 1] = s; }
+}
+__global__ void k_integral_cols(int W, int H, uint32_t* II) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x > W) return;
+  uint32_t s = 0;
+  for (int y = 0; y <= H; ++y) { s += II[(size_t)y * (W + 1) + x]; II[(size_t)y * (W + 1) + x] = s; }
+}
+
+__device__ void undistort_gn(const CamIntr& cam, double d0, double d1, double* pu) {
+  double x0 = d0, x1 = d1;
+  for (int i = 0; i < 5; ++i) {
+    double xt[2], E[4];
+    distort<true>(cam, x0, x1, xt, E);
+    const double e0 = d0 - xt[0], e1 = d1 - xt[1];
+    const double a = E[0] * E[0] + E[2] * E[2], b = E[0] * E[1] + E[2] * E[3], d = E[1] * E[1] + E[3] * E[3];
+    const double r0 = E[0] * e0 + E[2] * e1, r1 = E[1] * e0 + E[3] * e1;
+    const double det = a * d - b * b;
+    x0 += (d * r0 - b * r1) / det;
+    x1 += (-b * r0 + a * r1) / det;
+    if (e0 * e0 + e1 * e1 < 1e-15) break;
+  }
+  pu[0] = x0; pu[1] = x1;
+}
+
+// warp per keypoint: gravity angle, 60 box-smoothed samples, 8*desc_bytes comparisons via ballot
+__global__ void __launch_bounds__(128) k_describe(const uint32_t* __restrict__ II, int W, int H, okb_camera camera, const double* gC,
+                                                  int rot_inv, const int* __restrict__ half, const uint8_t* __restrict__ pi,
+                                                  const uint8_t* __restrict__ pj, const int16_t* __restrict__ lut, int desc_bytes,
+                                                  okb_keypoint* kps, const int* n_kp, uint8_t* desc) {
+  __shared__ uint32_t sS[4][64], sA[4][64];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int k = blockIdx.x * 4 + wib;
+  if (k >= *n_kp) return;
+  const int x = (int)kps[k].x, y = (int)kps[k].y;
+  float ang = 0.0f;
+  if (rot_inv) {
+    if (lane == 0) {
+      CamIntr cam;
+      cam_load(camera, cam);
+      double pu[2];
+      undistort_gn(cam, ((double)x - cam.cu) / cam.fu, ((double)y - cam.cv) / cam.fv, pu);
+      const double ep[3] = {pu[0], pu[1], 1.0};
+      double ip[2], J[6];
+      project<true>(cam, ep, ip, J);
+      const double e0 = J[0] * gC[0] + J[1] * gC[1] + J[2] * gC[2];
+      const double e1 = J[3] * gC[0] + J[4] * gC[1] + J[5] * gC[2];
+      ang = (float)(atan2(e1, e0) / 3.14159265358979323846 * 180.0);
+      kps[k].angle = ang;
+    }
+    ang = __shfl_sync(0xffffffffu, ang, 0);
+  }
+  const int bin = ((int)lround((double)ang / 360.0 * kRotBins)) & (kRotBins - 1);
+  for (int p = lane; p < kPts; p += 32) {
+    const int cx = x + lut[((size_t)bin * kPts + p) * 2], cy = y + lut[((size_t)bin * kPts + p) * 2 + 1];
+    const int h = half[p];
+    const int x0 = max(cx - h, 0), x1 = min(cx + h, W - 1), y0 = max(cy - h, 0), y1 = min(cy + h, H - 1);
+    sS[wib][p] = II[(size_t)(y1 + 1) * (W + 1) + x1 + 1] - II[(size_t)y0 * (W + 1) + x1 + 1] - II[(size_t)(y1 + 1) * (W + 1) + x0] +
+                 II[(size_t)y0 * (W + 1) + x0];
+    sA[wib][p] = (uint32_t)((x1 - x0 + 1) * (y1 - y0 + 1));
+  }
+  __syncwarp();
+  uint32_t* out = reinterpret_cast<uint32_t*>(desc + (size_t)k * desc_bytes);
+  for (int w = 0; w < desc_bytes / 4; ++w) {
+    const int b = 32 * w + lane;
+    const int i = pi[b], j = pj[b];
+    const bool bit = (unsigned long long)sS[wib][i] * sA[wib][j] > (unsigned long long)sS[wib][j] * sA[wib][i];
+    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0) out[w] = word;
+  }
+}
+}  // namespace
+
+static int ensure_pattern(okb_ctx* c, okb_frontend_state* F, int desc_bytes) {
+  std::lock_guard<std::mutex> lk(F->pat_mtx);
+  if (F->pat_bytes == desc_bytes) return OKB_OK;
+  Pattern P = make_pattern(desc_bytes);
+  cudaFree(F->d_half); cudaFree(F->d_pi); cudaFree(F->d_pj); cudaFree(F->d_lut);
+  FE_CUDA(c, cudaMalloc(&F->d_half, sizeof(int) * kPts));
+  FE_CUDA(c, cudaMalloc(&F->d_pi, P.pi.size()));
+  FE_CUDA(c, cudaMalloc(&F->d_pj, P.pj.size()));
+  FE_CUDA(c, cudaMalloc(&F->d_lut, P.lut.size() * sizeof(int16_t)));
+  FE_CUDA(c, cudaMemcpy(F->d_half, P.half, sizeof(int) * kPts, cudaMemcpyHostToDevice));
+  FE_CUDA(c, cudaMemcpy(F->d_pi, P.pi.data(), P.pi.size(), cudaMemcpyHostToDevice));
+  FE_CUDA(c, cudaMemcpy(F->d_pj, P.pj.data(), P.pj.size(), cudaMemcpyHostToDevice));
+  FE_CUDA(c, cudaMemcpy(F->d_lut, P.lut.data(), P.lut.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+  F->pat_bytes = desc_bytes;
+  return OKB_OK;
+}
+
+extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img, int width, int height, int stride,
+                                   const okb_camera* cam, const double R_CW[9], const okb_detect_params* prm,
+                                   okb_keypoint* out_kp, uint8_t* out_desc, int max_out, int* n_out) {
+  if (!c || !img || !cam || !R_CW || !prm || !out_kp || !out_desc || !n_out) return OKB_ERR_INVALID_ARG;
+  if (cam_slot < 0 || cam_slot >= kMaxSlots || width < 64 || height < 64 || stride < width) return OKB_ERR_INVALID_ARG;
+  if (prm->desc_bytes < 4 || prm->desc_bytes > 128 || (prm->desc_bytes % 4) != 0) return OKB_ERR_INVALID_ARG;
+  if ((size_t)width * height > (size_t)1 << 21) { c->set_error("image too large for the uniformity bitmap"); return OKB_ERR_CAPACITY; }
+  cudaSetDevice(c->device);
+  okb_frontend_state* F = fe(c);
+  int rc = ensure_pattern(c, F, prm->desc_bytes);
+  if (rc) return rc;
+  SlotBuffers& S = F->slots[cam_slot];
+  std::lock_guard<std::mutex> lk(S.mtx);   // the reference guards each camera's detector with a mutex (Frontend.cpp:97)
+  const int W = width, H = height;
+  const int maxk = std::min(prm->max_keypoints, max_out);
+  if (maxk < 1) return OKB_ERR_INVALID_ARG;
+  if (!S.stream) FE_CUDA(c, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+  if (S.W != W || S.H != H) {
+    cudaFree(S.d_img); cudaFree(S.d_score); cudaFree(S.d_integral); cudaFree(S.d_keys); cudaFree(S.d_keys_sorted); cudaFree(S.d_count);
+    cudaFree(S.d_cub);
+    if (S.h_img) cudaFreeHost(S.h_img);
+    if (S.h_count) cudaFreeHost(S.h_count);
+    FE_CUDA(c, cudaMalloc(&S.d_img, (size_t)W * H));
+    FE_CUDA(c, cudaMalloc(&S.d_score, sizeof(int32_t) * W * H));
+    FE_CUDA(c, cudaMalloc(&S.d_integral, sizeof(uint32_t) * (W + 1) * (H + 1)));
+    FE_CUDA(c, cudaMalloc(&S.d_keys, sizeof(unsigned long long) * kMaxCand));
+    FE_CUDA(c, cudaMalloc(&S.d_keys_sorted, sizeof(unsigned long long) * kMaxCand));
+    FE_CUDA(c, cudaMalloc(&S.d_count, sizeof(int) * 2 + sizeof(double) * 4));
+    S.cub_bytes = 0;
+    cub::DeviceRadixSort::SortKeysDescending(nullptr, S.cub_bytes, S.d_keys, S.d_keys_sorted, kMaxCand);
+    FE_CUDA(c, cudaMalloc(&S.d_cub, S.cub_bytes));
+    FE_CUDA(c, cudaMallocHost(&S.h_img, (size_t)W * H));
+    FE_CUDA(c, cudaMallocHost(&S.h_count, sizeof(int) * 2));
+    S.W = W; S.H = H;
+  }
+  if (S.kp_cap < maxk || S.desc_cap < maxk * prm->desc_bytes) {
+    cudaFree(S.d_kp); cudaFree(S.d_desc);
+    if (S.h_kp) cudaFreeHost(S.h_kp);
+    if (S.h_desc) cudaFreeHost(S.h_desc);
+    FE_CUDA(c, cudaMalloc(&S.d_kp, sizeof(okb_keypoint) * maxk));
+    FE_CUDA(c, cudaMalloc(&S.d_desc, (size_t)maxk * prm->desc_bytes));
+    FE_CUDA(c, cudaMallocHost(&S.h_kp, sizeof(okb_keypoint) * maxk));
+    FE_CUDA(c, cudaMallocHost(&S.h_desc, (size_t)maxk * prm->desc_bytes));
+    S.kp_cap = maxk; S.desc_cap = maxk * prm->desc_bytes;
+  }
+  for (int y = 0; y < H; ++y) std::memcpy(S.h_img + (size_t)y * W, img + (size_t)y * stride, W);
+  cudaStream_t st = S.stream;
+  FE_CUDA(c, cudaMemcpyAsync(S.d_img, S.h_img, (size_t)W * H, cudaMemcpyHostToDevice, st));
+  FE_CUDA(c, cudaMemsetAsync(S.d_count, 0, sizeof(int) * 2, st));
+  FE_CUDA(c, cudaMemsetAsync(S.d_keys, 0, sizeof(unsigned long long) * kMaxCand, st));   // unused keys sort last
+  // gravity direction in the camera frame: R_CW * (0,0,-1)
+  double gC[3] = {-R_CW[2], -R_CW[5], -R_CW[8]};
+  double* d_gC = reinterpret_cast<double*>(S.d_count + 2);
+  FE_CUDA(c, cudaMemcpyAsync(d_gC, gC, sizeof gC, cudaMemcpyHostToDevice, st));
+  const dim3 hb(HT_X, HT_Y), hg((W + HT_X - 1) / HT_X, (H + HT_Y - 1) / HT_Y);
+  k_harris<<<hg, hb, 0, st>>>(S.d_img, W, H, S.d_score);
+  const dim3 nb(32, 8), ng((W + 31) / 32, (H + 7) / 8);
+  k_nms<<<ng, nb, 0, st>>>(S.d_score, W, H, (int32_t)std::ceil(prm->absolute_threshold), S.d_keys, S.d_count, kMaxCand);
+  cub::DeviceRadixSort::SortKeysDescending(S.d_cub, S.cub_bytes, S.d_keys, S.d_keys_sorted, kMaxCand, 0, 64, st);
+  const size_t occ_bytes = sizeof(uint32_t) * (((size_t)W * H + 31) / 32);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_uniformity, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr_set = true; }
+  if (occ_bytes > (size_t)c->smem_optin) { c->set_error("image too large for the uniformity bitmap"); return OKB_ERR_CAPACITY; }
+  k_uniformity<<<1, 256, occ_bytes, st>>>(S.d_keys_sorted, S.d_count, kMaxCand, W, H, prm->uniformity_radius, maxk, S.d_kp, S.d_count + 1);
+  k_integral_rows<<<(H + 1 + 127) / 128, 128, 0, st>>>(S.d_img, W, H, S.d_integral);
+  k_integral_cols<<<(W + 1 + 127) / 128, 128, 0, st>>>(W, H, S.d_integral);
+  k_describe<<<(maxk + 3) / 4, 128, 0, st>>>(S.d_integral, W, H, *cam, d_gC, prm->rotation_invariance, F->d_half, F->d_pi, F->d_pj,
+                                             F->d_lut, prm->desc_bytes, S.d_kp, S.d_count + 1, S.d_desc);
+  c->launches += 6 + 3;   // + the radix-sort passes issued by CUB
+  FE_CUDA(c, cudaGetLastError());
+  FE_CUDA(c, cudaMemcpyAsync(S.h_count, S.d_count, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  FE_CUDA(c, cudaMemcpyAsync(S.h_kp, S.d_kp, sizeof(okb_keypoint) * maxk, cudaMemcpyDeviceToHost, st));
+  FE_CUDA(c, cudaMemcpyAsync(S.h_desc, S.d_desc, (size_t)maxk * prm->desc_bytes, cudaMemcpyDeviceToHost, st));
+  FE_CUDA(c, cudaStreamSynchronize(st));
+  if (S.h_count[0] > kMaxCand) { c->set_error("too many corner candidates"); return OKB_ERR_CAPACITY; }
+  const int n = S.h_count[1];
+  std::memcpy(out_kp, S.h_kp, sizeof(okb_keypoint) * n);
+  std::memcpy(out_desc, S.h_desc, (size_t)n * prm->desc_bytes);
+  *n_out = n;
+  return OKB_OK;
+}
+
+// =================================================================================================
+// matcher kernels
+// =================================================================================================
+namespace {
+constexpr int MT = 128;          // threads per CTA = A rows per CTA
+constexpr int MB_TILE = 128;     // B descriptors staged per shared-memory tile
+constexpr int MAX_WORDS = 32;    // descriptor words (<= 128 bytes)
+constexpr int MAX_BEST = 8;
+
+// thread per A: sequential scan over B with the reference's insertion rule (listBIteration)
+template <int NW>
+__global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict__ A, int nA, const uint32_t* __restrict__ B, int nB,
+                                                     const uint8_t* __restrict__ skipA, const uint8_t* __restrict__ skipB, float list_thr,
+                                                     int num_best, okb_pair* __restrict__ topk) {
+  __shared__ uint32_t sB[MB_TILE][NW + 1];
+  __shared__ uint8_t sSkip[MB_TILE];
+  const int a = blockIdx.x * MT + threadIdx.x;
+  const bool active = a < nA && !(skipA && skipA[a]);
+  uint32_t wa[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) wa[w] = (a < nA) ? A[(size_t)a * NW + w] : 0u;
+  int bi[MAX_BEST];
+  float bd[MAX_BEST];
+#pragma unroll
+  for (int k = 0; k < MAX_BEST; ++k) { bi[k] = -1; bd[k] = list_thr; }
+  for (int b0 = 0; b0 < nB; b0 += MB_TILE) {
+    const int nb = min(MB_TILE, nB - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * NW; i += MT) sB[i / NW][i % NW] = B[(size_t)b0 * NW + i];
+    for (int i = threadIdx.x; i < nb; i += MT) sSkip[i] = skipB ? skipB[b0 + i] : 0;
+    __syncthreads();
+    if (!active) continue;
+    for (int j = 0; j < nb; ++j) {
+      if (sSkip[j]) continue;
+      int dist = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) dist += __popc(wa[w] ^ sB[j][w]);
+      const float t = (float)dist;
+      float worst = bd[0];
+#pragma unroll
+      for (int k = 1; k < MAX_BEST; ++k) if (k == num_best - 1) worst = bd[k];
+      if (t < worst) {
+        // lower_bound on distance, shift the tail, insert before equal distances
+#pragma unroll
+        for (int k = MAX_BEST - 1; k > 0; --k) {
+          if (k < num_best && bd[k - 1] >= t) { bd[k] = bd[k - 1]; bi[k] = bi[k - 1]; }
+        }
+        int pos = 0;
+#pragma unroll
+        for (int k = 0; k < MAX_BEST; ++k) if (k < num_best && bd[k] < t) pos = k + 1;
+#pragma unroll
+        for (int k = 0; k < MAX_BEST; ++k) if (k == pos) { bd[k] = t; bi[k] = b0 + j; }
+      }
+    }
+  }
+  if (a < nA) {
+    for (int k = 0; k < num_best; ++k) {
+      okb_pair p;
+      p.index_a = active ? bi[k] : -1;
+      p.distance = active ? bd[k] : list_thr;
+      topk[(size_t)a * num_best + k] = p;
+    }
+  }
+}
+
+// sequential greedy assignment, A ascending (assignbest, DenseMatcher.cpp:69-110; tail recursion unrolled)
+__global__ void k_assign(const okb_pair* __restrict__ topk, int nA, int nB, int num_best, const uint8_t* __restrict__ skipA,
+                         okb_pair* pairs) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int b = 0; b < nB; ++b) { pairs[b].index_a = -1; pairs[b].distance = 3.402823466e+38f; }
+  for (int a0 = 0; a0 < nA; ++a0) {
+    if (skipA && skipA[a0]) continue;
+    int a = a0, start = 0;
+    while (a >= 0) {
+      int next = -1;
+      for (int idx = start; idx < num_best; ++idx) {
+        const okb_pair cand = topk[(size_t)a * num_best + idx];
+        if (cand.index_a == -1) break;
+        const int b = cand.index_a;
+        if (pairs[b].index_a == -1) { pairs[b].index_a = a; pairs[b].distance = cand.distance; break; }
+        if (cand.distance < pairs[b].distance) {
+          next = pairs[b].index_a;
+          pairs[b].index_a = a; pairs[b].distance = cand.distance;
+          break;
+        }
+      }
+      a = next;
+      start = 1;
+    }
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(MT) k_cand_count(const uint32_t* __restrict__ A, int nA, const uint32_t* __restrict__ B, int nB,
+                                                   float thr, uint32_t* counts, const uint32_t* row_ptr, uint32_t* col, uint16_t* dist,
+                                                   int cap, int fill) {
+  __shared__ uint32_t sB[MB_TILE][NW + 1];
+  const int a = blockIdx.x * MT + threadIdx.x;
+  uint32_t wa[NW];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) wa[w] = (a < nA) ? A[(size_t)a * NW + w] : 0u;
+  uint32_t n = 0;
+  const uint32_t base = (fill && a < nA) ? row_ptr[a] : 0;
+  for (int b0 = 0; b0 < nB; b0 += MB_TILE) {
+    const int nb = min(MB_TILE, nB - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * NW; i += MT) sB[i / NW][i % NW] = B[(size_t)b0 * NW + i];
+    __syncthreads();
+    if (a >= nA) continue;
+    for (int j = 0; j < nb; ++j) {
+      int d = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) d += __popc(wa[w] ^ sB[j][w]);
+      if ((float)d < thr) {
+        if (fill && base + n < (uint32_t)cap) { col[base + n] = (uint32_t)(b0 + j); dist[base + n] = (uint16_t)d; }
+        ++n;
+      }
+    }
+  }
+  if (!fill && a < nA) counts[a] = n;
+}
+
+__global__ void k_exclusive_scan(const uint32_t* counts, int n, uint32_t* row_ptr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t s = 0;
+  for (int i = 0; i < n; ++i) { row_ptr[i] = s; s += counts[i]; }
+  row_ptr[n] = s;
+}
+}  // namespace
+
+template <typename T>
+static int grow(okb_ctx* c, T** p, size_t* cap, size_t need) {
+  if (*cap >= need) return OKB_OK;
+  cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  FE_CUDA(c, cudaMalloc(p, need * sizeof(T)));
+  *cap = need;
+  return OKB_OK;
+}
+
+#define DISPATCH_NW(nw, CALL)                 \
+  switch (nw) {                               \
+    case 8: { constexpr int NW = 8; CALL; } break;   \
+    case 12: { constexpr int NW = 12; CALL; } break; \
+    case 16: { constexpr int NW = 16; CALL; } break; \
+    case 32: { constexpr int NW = 32; CALL; } break; \
+    default: c->set_error("descriptor length must be 32, 48, 64 or 128 bytes"); return OKB_ERR_UNSUPPORTED; \
+  }
+
+static int upload_descriptors(okb_ctx* c, okb_frontend_state* F, const uint8_t* A, int nA, const uint8_t* B, int nB, int bytes,
+                              const uint8_t* skipA, const uint8_t* skipB) {
+  int rc;
+  if ((rc = grow(c, &F->d_A, &F->capA, (size_t)nA * bytes + nA))) return rc;
+  if ((rc = grow(c, &F->d_B, &F->capB, (size_t)nB * bytes + nB))) return rc;
+  FE_CUDA(c, cudaMemcpyAsync(F->d_A, A, (size_t)nA * bytes, cudaMemcpyHostToDevice, c->stream));
+  FE_CUDA(c, cudaMemcpyAsync(F->d_B, B, (size_t)nB * bytes, cudaMemcpyHostToDevice, c->stream));
+  if (skipA) FE_CUDA(c, cudaMemcpyAsync(F->d_A + (size_t)nA * bytes, skipA, nA, cudaMemcpyHostToDevice, c->stream));
+  if (skipB) FE_CUDA(c, cudaMemcpyAsync(F->d_B + (size_t)nB * bytes, skipB, nB, cudaMemcpyHostToDevice, c->stream));
+  return OKB_OK;
+}
+
+extern "C" int okb_hamming_match(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, const uint8_t* skipA,
+                                 const uint8_t* skipB, float threshold, int num_best, int use_ratio, float ratio_threshold,
+                                 okb_pair* out_topk, okb_pair* out_pairs) {
+  (void)ratio_threshold;   // the ratio test itself belongs to the serial epilogue on the caller's side
+  if (!c || !A || !B || nA < 1 || nB < 1 || num_best < 1 || num_best > MAX_BEST || !out_pairs) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  okb_frontend_state* F = fe(c);
+  std::lock_guard<std::mutex> lk(F->match_mtx);
+  int rc = upload_descriptors(c, F, A, nA, B, nB, desc_bytes, skipA, skipB);
+  if (rc) return rc;
+  if ((rc = grow(c, &F->d_topk, &F->cap_topk, (size_t)nA * num_best))) return rc;
+  if ((rc = grow(c, &F->d_pairs, &F->cap_pairs, (size_t)nB))) return rc;
+  const uint8_t* dSA = skipA ? F->d_A + (size_t)nA * desc_bytes : nullptr;
+  const uint8_t* dSB = skipB ? F->d_B + (size_t)nB * desc_bytes : nullptr;
+  // DenseMatcher.hpp(impl):188-193: with the ratio test the lists are built without a threshold
+  const float list_thr = use_ratio ? 3.402823466e+38f : threshold;
+  const int nw = desc_bytes / 4;
+  if (desc_bytes % 4) { c->set_error("descriptor length must be a multiple of 4"); return OKB_ERR_UNSUPPORTED; }
+  DISPATCH_NW(nw, (k_hamming_topk<NW><<<(nA + MT - 1) / MT, MT, 0, c->stream>>>(
+                      reinterpret_cast<const uint32_t*>(F->d_A), nA, reinterpret_cast<const uint32_t*>(F->d_B), nB, dSA, dSB, list_thr,
+                      num_best, F->d_topk)));
+  k_assign<<<1, 32, 0, c->stream>>>(F->d_topk, nA, nB, num_best, dSA, F->d_pairs);
+  c->launches += 2;
+  FE_CUDA(c, cudaGetLastError());
+  if (out_topk) FE_CUDA(c, cudaMemcpyAsync(out_topk, F->d_topk, sizeof(okb_pair) * nA * num_best, cudaMemcpyDeviceToHost, c->stream));
+  FE_CUDA(c, cudaMemcpyAsync(out_pairs, F->d_pairs, sizeof(okb_pair) * nB, cudaMemcpyDeviceToHost, c->stream));
+  FE_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OKB_OK;
+}
+
+extern "C" int okb_hamming_candidates(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, float threshold,
+                                      uint32_t* row_ptr, uint32_t* col_idx, uint16_t* dist, int cap) {
+  if (!c || !A || !B || nA < 1 || nB < 1 || !row_ptr || cap < 0) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  okb_frontend_state* F = fe(c);
+  std::lock_guard<std::mutex> lk(F->match_mtx);
+  int rc = upload_descriptors(c, F, A, nA, B, nB, desc_bytes, nullptr, nullptr);
+  if (rc) return rc;
+  if ((rc = grow(c, &F->d_rowptr, &F->cap_rows, (size_t)2 * nA + 2))) return rc;
+  if (cap > 0) {
+    size_t cc = F->cap_cand;
+    if ((rc = grow(c, &F->d_col, &cc, (size_t)cap))) return rc;
+    cc = F->cap_cand;
+    if ((rc = grow(c, &F->d_dist, &cc, (size_t)cap))) return rc;
+    F->cap_cand = std::max(F->cap_cand, (size_t)cap);
+  }
+  uint32_t* d_counts = F->d_rowptr + nA + 1;
+  const int nw = desc_bytes / 4;
+  if (desc_bytes % 4) { c->set_error("descriptor length must be a multiple of 4"); return OKB_ERR_UNSUPPORTED; }
+  DISPATCH_NW(nw, (k_cand_count<NW><<<(nA + MT - 1) / MT, MT, 0, c->stream>>>(
+                      reinterpret_cast<const uint32_t*>(F->d_A), nA, reinterpret_cast<const uint32_t*>(F->d_B), nB, threshold, d_counts,
+                      nullptr, nullptr, nullptr, 0, 0)));
+  k_exclusive_scan<<<1, 32, 0, c->stream>>>(d_counts, nA, F->d_rowptr);
+  if (cap > 0) {
+    DISPATCH_NW(nw, (k_cand_count<NW><<<(nA + MT - 1) / MT, MT, 0, c->stream>>>(
+                        reinterpret_cast<const uint32_t*>(F->d_A), nA, reinterpret_cast<const uint32_t*>(F->d_B), nB, threshold, d_counts,
+                        F->d_rowptr, F->d_col, F->d_dist, cap, 1)));
+  }
+  c->launches += 3;
+  FE_CUDA(c, cudaGetLastError());
+  FE_CUDA(c, cudaMemcpyAsync(row_ptr, F->d_rowptr, sizeof(uint32_t) * (nA + 1), cudaMemcpyDeviceToHost, c->stream));
+  FE_CUDA(c, cudaStreamSynchronize(c->stream));
+  const uint32_t total = row_ptr[nA];
+  const uint32_t ncopy = std::min<uint32_t>(total, (uint32_t)cap);
+  if (ncopy && col_idx) FE_CUDA(c, cudaMemcpyAsync(col_idx, F->d_col, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost, c->stream));
+  if (ncopy && dist) FE_CUDA(c, cudaMemcpyAsync(dist, F->d_dist, sizeof(uint16_t) * ncopy, cudaMemcpyDeviceToHost, c->stream));
+  FE_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (total > (uint32_t)cap) { c->set_error("candidate capacity too small"); return OKB_ERR_CAPACITY; }
+  return OKB_OK;
+}

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <vector>
 
+#include "oracle_brisk.hpp"
 #include "oracle_errors.hpp"
 #include "oracle_matcher.hpp"
 #include "oracle_solver.hpp"
@@ -157,6 +158,11 @@ int oko_hamming_candidates(const uint8_t* A, int nA, const uint8_t* B, int nB, i
   }
   row_ptr[nA] = n;
   return n;
+}
+
+int oko_detect_describe(const uint8_t* img, int W, int H, int stride, const okb_camera* cam, const double* R_CW,
+                        const okb_detect_params* prm, okb_keypoint* kps, uint8_t* desc, int max_out) {
+  return detect_describe(img, W, H, stride, *cam, R_CW, *prm, kps, desc, max_out);
 }
 
 }  // extern "C"

@@ -284,3 +284,22 @@ def hamming_candidates(A, B, threshold=60.0, cap=None):
           C.c_float(threshold), C.c_void_p(row_ptr.ctypes.data), C.c_void_p(col.ctypes.data),
           C.c_void_p(dist.ctypes.data), C.c_int(cap))
     return row_ptr, col[:n].copy(), dist[:n].copy()
+
+
+def detect_describe(img, cam, R_CW, uniformity_radius=40.0, absolute_threshold=800.0, max_keypoints=400, desc_bytes=48,
+                    rotation_invariance=True):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    prm = abi.DetectParams()
+    prm.uniformity_radius, prm.absolute_threshold = uniformity_radius, absolute_threshold
+    prm.max_keypoints, prm.desc_bytes, prm.rotation_invariance = max_keypoints, desc_bytes, int(rotation_invariance)
+    cam_arr = np.array([cam], dtype=abi.camera_dtype)
+    R = np.ascontiguousarray(np.asarray(R_CW, dtype=np.float64).reshape(9))
+    kps = np.zeros(max_keypoints, abi.keypoint_dtype)
+    desc = np.zeros((max_keypoints, desc_bytes), np.uint8)
+    f = lib().oko_detect_describe
+    f.restype = C.c_int
+    n = f(C.c_void_p(img.ctypes.data), C.c_int(w), C.c_int(h), C.c_int(img.strides[0]), C.c_void_p(cam_arr.ctypes.data),
+          C.c_void_p(R.ctypes.data), C.byref(prm), C.c_void_p(kps.ctypes.data), C.c_void_p(desc.ctypes.data),
+          C.c_int(max_keypoints))
+    return kps[:n].copy(), desc[:n].copy()
