@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- keyframe-window optimize() throughput (BASELINE.json metric) on N B200s.
+
+A "step" = one pass of the hot path over one batch: Estimator::optimize(10 iterations) on every
+resident 10-keyframe / 2000-landmark stereo window (BASELINE.json configs[1]; synthetic, seeded).
+  value : iterations/s (accepted + rejected dogleg iterations, as Ceres counts them) with the windows
+          already resident in HBM, timed with CUDA events on the library's stream, max over ranks.
+  e2e   : the same metric through the C-ABI with HOST buffers: okb_window_upload (H2D) +
+          okb_optimize + okb_window_download (D2H) inside the timed region.
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+`--impl reference` times the CPU oracle (the restated okvis_ceres path; the real reference cannot be
+built here) on the box's host cores on the same workload.
+Windows shard across ranks with no data-path collective (independent windows): weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "keyframe-window optimize() iters/sec (10KF/2k-lm stereo)"
+ITERS = 10
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = threading.Event()
+        self.sm, self.sm_max, self.reasons = [], [], set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.sm.append(float(out[0]))
+                self.sm_max.append(float(out[1]))
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.sm_max)), "reasons": sorted(self.reasons)}
+
+
+def make_windows(n_distinct, base_idx):
+    from okvis_b200 import synthetic
+    return [synthetic.make_window(2, base_idx + i) for i in range(n_distinct)]
+
+
+def run_reference(args):
+    """CPU arm: the oracle (restated reference path) on the host cores, all threads."""
+    from oracle import oracle_py as op
+    from concurrent.futures import ThreadPoolExecutor
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_win = max(1, min(cores, 16))
+    windows = make_windows(min(n_win, 8), 0)
+
+    def solve_one(i):
+        p = op.OracleProblem(windows[i % len(windows)])
+        s = p.solve(ITERS, 1)
+        p.state(with_quality=True)     # Estimator::optimize also runs the landmark-quality pass
+        p.close()
+        return s["iterations"]
+
+    times, iters = [], 0
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for step in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            it = sum(ex.map(solve_one, range(n_win)))
+            dt = time.perf_counter() - t
+            if step >= args.warmup:
+                times.append(dt)
+                iters += it
+    total = sum(times)
+    value = iters / total
+    w = windows[0]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg-2: 10-keyframe stereo (2x752x480), 2000 landmarks, 200 Hz IMU window, optimize(10)",
+                   "windows_per_step": n_win, "n_obs": int(len(w.obs)), "iterations_per_optimize": ITERS},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port",
+                         "sample": "%d windows x optimize(%d) per step, one oracle thread per window" % (n_win, ITERS)},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated-reference CPU path (oracle/): the original Ceres/SuiteSparse binary cannot be built here",
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    from okvis_b200 import capi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    ctx = capi.Context(local_rank, B)
+    # independent windows: rank r gets its own window indices (window w -> GPU w mod n)
+    windows = make_windows(args.distinct, 100 * rank)
+    for i in range(B):
+        ctx.upload(i, windows[i % len(windows)])
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        ctx.reset(0, B)
+        return ctx.optimize(0, B, max_iterations=ITERS)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    ctx.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            iters += sum(s["iterations"] for s in step())
+        ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.result() if rank == 0 else None
+
+    # ---- e2e through the C-ABI with host buffers (upload + optimize + download every step)
+    Be = min(B, args.e2e_batch)
+    e2e_steps = max(1, args.steps // 2)
+    h2d = d2h = 0
+
+    def e2e_step():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        for i in range(Be):
+            w = windows[i % len(windows)]
+            ctx.upload(i, w)
+            h2d += ctx.h2d_bytes(i)
+        ss = ctx.optimize(0, Be, max_iterations=ITERS)
+        for i in range(Be):
+            out = ctx.download(i)
+            d2h += sum(v.nbytes for v in out.values())
+        d2h += Be * 48
+        return sum(s["iterations"] for s in ss)
+
+    e2e_step()
+    barrier()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_iters = 0
+    t_host = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ee0.record(stream)
+        for _ in range(e2e_steps):
+            e_iters += e2e_step()
+        ee1.record(stream)
+    torch.cuda.synchronize(dev)
+    e2e_wall = time.perf_counter() - t_host     # host packing is part of the end-to-end path
+    barrier()
+    # restore the resident batch for any later use
+    t = torch.tensor([elapsed_ms, e2e_wall * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(iters), float(e_iters), float(launches)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+    iters_all, e_iters_all, launches_all = float(cnt[0]), float(cnt[1]), int(cnt[2])
+
+    if rank == 0:
+        peak, peak_kind = load_peaks()
+        w = windows[0]
+        bytes_iter = float(np.mean([x.algorithmic_bytes_per_iteration() for x in windows]))
+        flops_iter = float(np.mean([x.algorithmic_flops_per_iteration() for x in windows]))
+        # kernel A ("Jacobian + JtJ/Schur build"): one launch processes one linearisation of all B windows
+        lm_ms = prof["landmarks_ms"] / max(prof["landmarks_launches"], 1)
+        sv_ms = prof["solve_ms"] / max(prof["solve_launches"], 1)
+        achieved = B * bytes_iter / (lm_ms * 1e-3) / 1e9
+        total_k = prof["landmarks_ms"] + prof["solve_ms"] + prof["quality_ms"]
+        # CPU baseline: bounded sample of the same workload on this box's host cores
+        from oracle import oracle_py as op
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        n_cpu = 0
+        cpu_iters = 0
+        while time.perf_counter() - t0 < 8.0 and n_cpu < 64:
+            p = op.OracleProblem(windows[n_cpu % len(windows)])
+            s = p.solve(ITERS, cores)
+            p.state(with_quality=True)
+            p.close()
+            cpu_iters += s["iterations"]
+            n_cpu += 1
+        cpu_dt = time.perf_counter() - t0
+        line = {
+            "metric": METRIC, "value": iters_all / (elapsed_ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg-2: 10-keyframe stereo (2x752x480), 2000 landmarks, 200 Hz IMU window, optimize(10)",
+                       "windows_per_gpu": B, "n_obs": int(len(w.obs)), "iterations_per_optimize": ITERS,
+                       "parallelism": "independent windows, %d per GPU, no collective" % B,
+                       "l2": "inputs larger than L2 (%.0f MB resident per GPU)" % (B * 3.0)},
+            "e2e": {"value": e_iters_all / (e2e_ms * 1e-3), "unit": "iterations/s", "h2d_bytes_per_step": int(h2d) * world,
+                    "d2h_bytes_per_step": int(d2h) * world, "windows_per_gpu": Be, "steps": e2e_steps},
+            "gpu_launches": launches_all,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_landmarks (residuals + Jacobian factors + J^T J + Schur SYRK)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_kind, "avg_launch_ms": lm_ms, "algorithmic_bytes_per_window_iteration": bytes_iter,
+                         "fp64_gflops": B * flops_iter / (lm_ms * 1e-3) / 1e9,
+                         "share_of_kernel_time": prof["landmarks_ms"] / max(total_k, 1e-9),
+                         "k_solve_avg_launch_ms": sv_ms, "k_solve_share": prof["solve_ms"] / max(total_k, 1e-9)},
+            "cpu_baseline": {"value": cpu_iters / cpu_dt, "unit": "iterations/s", "cores": cores, "kind": "port",
+                             "sample": "%d windows x optimize(%d), %d OpenMP threads (oracle)" % (n_cpu, ITERS, cores)},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=592, help="resident windows per GPU (4 per SM)")
+    ap.add_argument("--e2e-batch", type=int, default=148)
+    ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic windows per rank (replicated to fill the batch)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -198,6 +198,8 @@ void* okb_stream(const okb_ctx* ctx);
 
 /* Packs and uploads one window into slot `win` (0 <= win < max_windows). */
 int okb_window_upload(okb_ctx* ctx, int win, const okb_window_desc* desc);
+/* Bytes the last okb_window_upload of this slot copied host -> device (0 if the slot is empty). */
+int64_t okb_window_h2d_bytes(const okb_ctx* ctx, int win);
 /* Restores the uploaded initial state of the slot on the device (no host traffic); used to
  * repeat a solve on resident data. */
 int okb_window_reset(okb_ctx* ctx, int win_first, int win_count);
@@ -220,6 +222,9 @@ int okb_window_download(okb_ctx* ctx, int win, double* poses, double* speed_bias
  * out[4] = ms in k_quality, out[5] = launches. */
 int okb_profile_enable(okb_ctx* ctx, int on);
 int okb_profile_read(okb_ctx* ctx, double out[6]);
+/* Diagnostics: nanoseconds the reduced-solve kernel spent per internal phase during the last optimize of
+ * `win` (dense terms, partial gather, assembly, Cholesky, substitution, back-substitution, dogleg). */
+int okb_debug_phase_ns(okb_ctx* ctx, int win, double out[8]);
 
 /* ------------------------------------------------- single-block test hooks
  * Mirror ErrorInterface::EvaluateWithMinimalJacobians (okvis_ceres/include/okvis/ceres/ErrorInterface.hpp:93-95).

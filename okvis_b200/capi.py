@@ -79,6 +79,17 @@ class Context:
         self._check(lib().okb_window_upload(self._h, int(win), C.byref(d)))
         self._windows[win] = window
 
+    def debug_phase_us(self, win):
+        out = np.zeros(8)
+        self._check(lib().okb_debug_phase_ns(self._h, int(win), _p(out)))
+        names = ["dense_terms", "gather", "assemble", "cholesky", "substitution", "backsub", "dogleg", "_"]
+        return {n: v * 1e-3 for n, v in zip(names, out)}
+
+    def h2d_bytes(self, win):
+        f = lib().okb_window_h2d_bytes
+        f.restype = C.c_int64
+        return int(f(self._h, int(win)))
+
     def reset(self, first=0, count=1):
         self._check(lib().okb_window_reset(self._h, int(first), int(count)))
 

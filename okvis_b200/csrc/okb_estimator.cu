@@ -188,6 +188,7 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   const size_t o_chol = P.take(sizeof(double) * (size_t)d * d);
   const size_t o_cache = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
   const size_t o_cache_i = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
+  const size_t o_imu_out = P.take(sizeof(double) * kImuOut * std::max(W.n_imu, 1));
 
   WinStore& S = c->wins[win];
   if (S.arena_bytes < P.total) {
@@ -297,6 +298,7 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   W.samples = reinterpret_cast<okb_imu_sample*>(A + o_samp);
   W.imu_cache = reinterpret_cast<ImuCache*>(A + o_cache);
   W.imu_cache_init = reinterpret_cast<ImuCache*>(A + o_cache_i);
+  W.imu_out = dp(o_imu_out);
   W.pp = reinterpret_cast<okb_pose_prior*>(A + o_pp);
   W.sbp = reinterpret_cast<okb_sb_prior*>(A + o_sbp);
   W.marg_kind = reinterpret_cast<int32_t*>(A + o_mkind);
@@ -362,6 +364,11 @@ static int check_range(okb_ctx* c, int first, int count) {
   return OKB_OK;
 }
 
+extern "C" int64_t okb_window_h2d_bytes(const okb_ctx* c, int win) {
+  if (!c || win < 0 || win >= c->max_windows || !c->wins[win].uploaded) return 0;
+  return (int64_t)(c->wins[win].h2d_bytes + sizeof(WinDev));
+}
+
 extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
   int rc = check_range(c, first, count);
   if (rc) return rc;
@@ -376,12 +383,13 @@ extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
 // optimize
 // ---------------------------------------------------------------------------------------------
 static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_options& opt, int rounds) {
-  int max_chunks = 1, tpt = 1;
+  int max_chunks = 1, tpt = 1, max_imu = 0;
   size_t smA = 0, smS = 0;
   bool chol_smem = true;
   for (int i = first; i < first + count; ++i) {
     const WinDev& W = c->host[i];
     max_chunks = std::max(max_chunks, W.n_chunks);
+    max_imu = std::max(max_imu, W.n_imu);
     const int NT = W.dcp / 4;
     if (NT * (NT + 1) / 2 > A_THREADS) tpt = 2;
     smA = std::max(smA, smemA_bytes(W.NSP, W.K, W.dcp));
@@ -398,6 +406,10 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
     if (tpt == 1) k_landmarks<1><<<gridA, A_THREADS, smA, c->stream>>>(c->d_wins, first);
     else k_landmarks<2><<<gridA, A_THREADS, smA, c->stream>>>(c->d_wins, first);
     prof_end(c);
+    if (max_imu > 0) {
+      k_imu<<<dim3(max_imu, count), 32, 0, c->stream>>>(c->d_wins, first);
+      c->launches += 1;
+    }
     prof_begin(c, 1);
     k_solve<<<count, S_THREADS, smS, c->stream>>>(c->d_wins, first, opt, chol_smem ? 1 : 0);
     prof_end(c);
@@ -466,6 +478,13 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
     }
   }
   OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OKB_OK;
+}
+
+// diagnostics: accumulated k_solve phase times (ns) of the last optimize of `win`
+extern "C" int okb_debug_phase_ns(okb_ctx* c, int win, double out[8]) {
+  if (!c || win < 0 || win >= c->max_windows || !out) return OKB_ERR_INVALID_ARG;
+  for (int i = 0; i < 8; ++i) out[i] = (double)c->h_states[win].phase_ns[i];
   return OKB_OK;
 }
 

@@ -53,6 +53,7 @@ struct SolverState {
   double grad_max;
   unsigned long long t_start_ns, t_last_iter_ns, t_iter_begin_ns;
   double solve_time_s;
+  unsigned long long phase_ns[8];   // accumulated k_solve phase times (diagnostics)
 };
 
 // Everything kernels need to know about one window.  All pointers are device pointers into the
@@ -102,6 +103,7 @@ struct WinDev {
   okb_imu_params imu_params;
   ImuCache* imu_cache;
   ImuCache* imu_cache_init;
+  double* imu_out;                             // [n_imu][kImuOut] written by k_imu, consumed by k_solve
   int *sb_off;                                 // unused placeholder for alignment
   // priors
   okb_pose_prior* pp;

@@ -58,12 +58,14 @@ Pattern make_pattern(int desc_bytes) {
       ++idx;
     }
   }
-  struct Pr { double d; int i, j; };
+  // squared distances are quantised to 1e-6 so that the ordering of (mathematically) equal
+  // distances does not depend on the compiler's floating-point contraction
+  struct Pr { long long d; int i, j; };
   std::vector<Pr> all;
   for (int i = 0; i < kPts; ++i)
     for (int j = i + 1; j < kPts; ++j) {
       const double dx = px[i] - px[j], dy = py[i] - py[j];
-      all.push_back({dx * dx + dy * dy, i, j});
+      all.push_back({std::llround((dx * dx + dy * dy) * 1e6), i, j});
     }
   std::stable_sort(all.begin(), all.end(), [](const Pr& a, const Pr& b) {
     if (a.d != b.d) return a.d < b.d;
@@ -434,9 +436,9 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   k_nms<<<ng, nb, 0, st>>>(S.d_score, W, H, (int32_t)std::ceil(prm->absolute_threshold), S.d_keys, S.d_count, kMaxCand);
   cub::DeviceRadixSort::SortKeysDescending(S.d_cub, S.cub_bytes, S.d_keys, S.d_keys_sorted, kMaxCand, 0, 64, st);
   const size_t occ_bytes = sizeof(uint32_t) * (((size_t)W * H + 31) / 32);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_uniformity, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin); attr_set = true; }
-  if (occ_bytes > (size_t)c->smem_optin) { c->set_error("image too large for the uniformity bitmap"); return OKB_ERR_CAPACITY; }
+  if (occ_bytes + 1024 > (size_t)c->smem_optin) { c->set_error("image too large for the uniformity bitmap"); return OKB_ERR_CAPACITY; }
+  if (occ_bytes > 48 * 1024 - 64)
+    FE_CUDA(c, cudaFuncSetAttribute(k_uniformity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occ_bytes));
   k_uniformity<<<1, 256, occ_bytes, st>>>(S.d_keys_sorted, S.d_count, kMaxCand, W, H, prm->uniformity_radius, maxk, S.d_kp, S.d_count + 1);
   k_integral_rows<<<(H + 1 + 127) / 128, 128, 0, st>>>(S.d_img, W, H, S.d_integral);
   k_integral_cols<<<(W + 1 + 127) / 128, 128, 0, st>>>(W, H, S.d_integral);

@@ -16,6 +16,8 @@ constexpr int A_WARPS = 12;
 constexpr int A_THREADS = A_WARPS * 32;
 constexpr int S_THREADS = 512;
 constexpr int S_WARPS = S_THREADS / 32;
+constexpr int kImuScratch = 3 * 225 + 450 + 450 + 16;   // doubles of shared scratch per IMU warp
+constexpr int kImuOut = 932;     // doubles per IMU term produced by k_imu: H30 | g30 | cost | pad
 
 struct SlotCtx {
   SlotXf xf;
@@ -374,6 +376,47 @@ __global__ void __launch_bounds__(A_THREADS, 1) k_landmarks(const WinDev* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kernel I: one warp per IMU term (255 registers available, no spills): residual, the four minimal
+// Jacobians, and the term's contribution  [J0 J1 J2 J3]^T [J0 J1 J2 J3] (30x30), J^T r (30), cost.
+// Re-preintegrates exactly when the reference's Evaluate() would.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_imu(const WinDev* __restrict__ wins, int win_first) {
+  const WinDev& W = wins[win_first + blockIdx.y];
+  if (W.st->done) return;
+  const int t = blockIdx.x;
+  if (t >= W.n_imu) return;
+  __shared__ double buf[kImuScratch];
+  WarpCtx cx;
+  ImuWork wk{buf, buf + 225, buf + 450};
+  double* F01 = buf + 675;
+  double* SF = buf + 675 + 450;
+  double* r15 = buf + 675 + 900;
+  const okb_imu_term& T = W.imu_terms[t];
+  imu_evaluate(cx, W.samples + T.sample_offset, (int)T.sample_count, W.imu_params, T.t0_ns, T.t1_ns, W.pose_c + 7 * T.pose0,
+               W.sb_c + 9 * T.sb0, W.pose_c + 7 * T.pose1, W.sb_c + 9 * T.sb1, W.imu_cache + t, wk, F01, (double*)nullptr, r15, SF);
+  double* out = W.imu_out + (size_t)t * kImuOut;
+  const int lane = threadIdx.x;
+  for (int e = lane; e < 900; e += 32) {
+    const int a = e / 30, b = e % 30;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 15; ++k) s += SF[k * 30 + a] * SF[k * 30 + b];
+    out[e] = s;
+  }
+  if (lane < 30) {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 15; ++k) s += SF[k * 30 + lane] * r15[k];
+    out[900 + lane] = s;
+  }
+  if (lane == 0) {
+    double c = 0;
+    for (int k = 0; k < 15; ++k) c += r15[k] * r15[k];
+    out[930] = 0.5 * c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Kernel S
 // ------------------------------------------------------------------------------------------------
 struct SShared {
@@ -434,19 +477,13 @@ __device__ void dense_priors(const WinDev& W, double* Hd, double* gd, double* co
   *cost_out = cost;
 }
 
-constexpr int kImuScratch = 3 * 225 + 450 + 450 + 16;   // doubles per IMU warp
-__host__ __device__ inline int imu_scratch_warps(int n_imu) {
-  int w = (n_imu + 1) / 2;
-  if (w < 1) w = 1;
-  return w > 8 ? 8 : w;
-}
 __host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_imu, bool chol_in_smem) {
   size_t b = sizeof(SShared);
   b = (b + 15) & ~(size_t)15;
   b += (size_t)8 * d * sizeof(double);                     // gd, Ed, ud, rhs, vd, tmp, delta, colk
   b += (size_t)K * 4 * sizeof(double);                     // committed frame translations
   b += (size_t)3 * (n_marg > 0 ? n_marg : 1) * sizeof(double);   // marg: dchi, e, Jte
-  size_t imu = (size_t)imu_scratch_warps(n_imu) * kImuScratch * sizeof(double);
+  size_t imu = 1024;
   size_t ch = chol_in_smem ? (size_t)d * d * sizeof(double) : 0;
   b += imu > ch ? imu : ch;
   return b;
@@ -479,6 +516,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   double* s_mJte = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
   double* s_big = reinterpret_cast<double*>(smem_raw + off);   // IMU scratch, later the Cholesky matrix
 
+  unsigned long long t_ph = globaltimer_ns();
+#define PHASE_MARK(i) do { if (tid == 0) { const unsigned long long n_ = globaltimer_ns(); st->phase_ns[i] += n_ - t_ph; t_ph = n_; } } while (0)
   const int mode = st->mode;
   const int spec = st->cur ^ 1;
   double* Hd = W.Hd;
@@ -488,51 +527,29 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   for (int i = tid; i < d * d; i += S_THREADS) Hd[i] = 0.0;
   for (int i = tid; i < d; i += S_THREADS) gd[i] = 0.0;
   __syncthreads();
-  double cost_dense_local = 0.0;   // accumulated by lane 0 of each warp / thread 0
-  // IMU terms: two colour rounds so that neighbouring terms never add to the same block concurrently
-  {
-    WarpCtx cx;
-    const int nw_imu = imu_scratch_warps(W.n_imu);
-    double* wbuf = s_big + (size_t)(warp < nw_imu ? warp : 0) * kImuScratch;
-    ImuWork wk{wbuf, wbuf + 225, wbuf + 450};
-    double* F01 = wbuf + 675;
-    double* SF = wbuf + 675 + 450;
-    double* r15 = wbuf + 675 + 900;
-    for (int colour = 0; colour < 2; ++colour) {
-      for (int t = 2 * warp + colour; warp < nw_imu && t < W.n_imu; t += 2 * nw_imu) {
-        const okb_imu_term& T = W.imu_terms[t];
-        imu_evaluate(cx, W.samples + T.sample_offset, (int)T.sample_count, W.imu_params, T.t0_ns, T.t1_ns,
-                     W.pose_c + 7 * T.pose0, W.sb_c + 9 * T.sb0, W.pose_c + 7 * T.pose1, W.sb_c + 9 * T.sb1,
-                     W.imu_cache + t, wk, F01, (double*)nullptr, r15, SF);
-        // H += SF^T SF (30x30), g += SF^T r
-        const int offs[4] = {6 * (int)T.pose0, dc + 9 * (int)T.sb0, 6 * (int)T.pose1, dc + 9 * (int)T.sb1};
-        for (int e = lane; e < 900; e += 32) {
-          const int a = e / 30, b = e % 30;
-          double s = 0;
-          for (int k = 0; k < 15; ++k) s += SF[k * 30 + a] * SF[k * 30 + b];
-          const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
-          const int bb = (b < 6) ? 0 : (b < 15) ? 1 : (b < 21) ? 2 : 3;
-          const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
-          const int lb = b - ((bb == 0) ? 0 : (bb == 1) ? 6 : (bb == 2) ? 15 : 21);
-          atomicAdd(&Hd[(size_t)(offs[ba] + la) * d + offs[bb] + lb], s);
-        }
-        if (lane < 30) {
-          const int a = lane;
-          double s = 0;
-          for (int k = 0; k < 15; ++k) s += SF[k * 30 + a] * r15[k];
-          const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
-          const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
-          atomicAdd(&gd[offs[ba] + la], s);
-        }
-        if (lane == 0) {
-          double c = 0;
-          for (int k = 0; k < 15; ++k) c += r15[k] * r15[k];
-          cost_dense_local += 0.5 * c;
-        }
-        __syncwarp();
+  double cost_dense_local = 0.0;   // accumulated by thread 0
+  // IMU terms were evaluated by k_imu (one warp per term); add their 30x30 blocks term by term
+  for (int t = 0; t < W.n_imu; ++t) {
+    const okb_imu_term& T = W.imu_terms[t];
+    const double* out = W.imu_out + (size_t)t * kImuOut;
+    const int offs[4] = {6 * (int)T.pose0, dc + 9 * (int)T.sb0, 6 * (int)T.pose1, dc + 9 * (int)T.sb1};
+    for (int e = tid; e < 930; e += S_THREADS) {
+      if (e < 900) {
+        const int a = e / 30, b = e % 30;
+        const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
+        const int bb = (b < 6) ? 0 : (b < 15) ? 1 : (b < 21) ? 2 : 3;
+        const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
+        const int lb = b - ((bb == 0) ? 0 : (bb == 1) ? 6 : (bb == 2) ? 15 : 21);
+        Hd[(size_t)(offs[ba] + la) * d + offs[bb] + lb] += out[e];
+      } else {
+        const int a = e - 900;
+        const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
+        const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
+        gd[offs[ba] + la] += out[e];
       }
-      __syncthreads();
     }
+    if (tid == 0) cost_dense_local += out[930];
+    __syncthreads();
   }
   // priors (warp 0)
   if (warp == 0) {
@@ -615,6 +632,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   }
   const double cost_dense = block_sum(cost_dense_local, sh->red);
 
+  PHASE_MARK(0);
   // ================= phase 2: gather kernel-A partials =================
   double cost_lm = 0.0, stepn2_lm = 0.0;
   for (int c = 0; c < W.n_chunks; ++c) {   // fixed order, replicated in all threads (tiny)
@@ -647,6 +665,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   }
   __syncthreads();
 
+  PHASE_MARK(1);
   // ================= phase 3: judge =================
   if (tid == 0) {
     const unsigned long long now = globaltimer_ns();
@@ -693,7 +712,13 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   }
   __syncthreads();
   if (sh->terminate) {
-    if (tid == 0) { st->done = 1; st->solve_time_s = 1e-9 * (double)(globaltimer_ns() - st->t_start_ns); }
+    if (tid == 0) {
+      int redo = 0;
+      for (int t = 0; t < W.n_imu; ++t) redo += W.imu_cache[t].redo_count;
+      st->imu_redo_final = redo - st->imu_redo;
+      st->done = 1;
+      st->solve_time_s = 1e-9 * (double)(globaltimer_ns() - st->t_start_ns);
+    }
     return;
   }
   const int adopt = sh->adopt;
@@ -757,6 +782,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       s_rhs[i] = v;
     }
     __syncthreads();
+    PHASE_MARK(2);
     // ---- dense Cholesky (lower), right-looking
     int chol_fail = sh->fail;
     if (!chol_fail) {
@@ -779,6 +805,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
         __syncthreads();
       }
     }
+    PHASE_MARK(3);
     if (!chol_fail) {
       // forward / backward substitution (column oriented)
       for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = s_rhs[i];
@@ -800,6 +827,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
       __syncthreads();
     }
+    PHASE_MARK(4);
     // ---- landmarks: commit, back-substitute, scalar reductions
     double N2 = 0, GU = 0, G2 = 0, VHV = 0, xn2 = 0, gmax = 0;
     int bad = 0;
@@ -879,6 +907,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     __syncthreads();
   }
 
+  PHASE_MARK(5);
   // ================= phase 5: loop top (callbacks, iteration limit), dogleg step =================
   if (tid == 0) {
     const unsigned long long now = globaltimer_ns();
@@ -987,6 +1016,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     sn2 = block_sum(sn2, sh->red);
     if (tid == 0) st->cand_step_norm2_dense = sn2;
   }
+  PHASE_MARK(6);
+#undef PHASE_MARK
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1027,7 +1058,7 @@ __global__ void __launch_bounds__(256) k_quality(const WinDev* __restrict__ wins
     for (int i = 0; i < 6; ++i) H[i] = warp_sum(H[i]);
     if (lane == 0) {
       double ev[3];
-      eig3sym(H, ev);
+      eig3sym_closed(H, ev);
       W.quality[l] = (ev[0] < 1.0e-12) ? 0.0 : sqrt(ev[0]) / sqrt(ev[2]);
     }
   }
@@ -1060,6 +1091,7 @@ __global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int rest
     st->cost = 0; st->initial_cost = 0; st->x_norm2 = 0;
     st->G2 = st->VHV = st->GU = st->N2 = 0; st->a = 0; st->b = 0;
     st->model_cost_change = 0; st->dogleg_step_norm = 0; st->cand_step_norm2_dense = 0; st->grad_max = 0;
+    for (int i = 0; i < 8; ++i) st->phase_ns[i] = 0;
     st->t_start_ns = 0; st->t_last_iter_ns = 0; st->t_iter_begin_ns = 0; st->solve_time_s = 0;
     int redo = 0;
     for (int t = 0; t < W.n_imu; ++t) redo += W.imu_cache[t].redo_count;

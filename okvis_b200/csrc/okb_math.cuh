@@ -181,6 +181,25 @@ OKB_HD void eig3sym(const double* S, double* ev) {
   ev[0] = e0; ev[1] = e1; ev[2] = e2;
 }
 
+// closed-form (trigonometric) eigenvalues of a symmetric 3x3, ascending; branch-light for kernels
+OKB_HD void eig3sym_closed(const double* S, double* ev) {
+  const double a00 = S[0], a01 = S[1], a02 = S[2], a11 = S[3], a12 = S[4], a22 = S[5];
+  const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+  const double q = (a00 + a11 + a22) / 3.0;
+  const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+  const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
+  if (!(p2 > 0.0)) { ev[0] = ev[1] = ev[2] = q; return; }
+  const double p = sqrt(p2 / 6.0);
+  const double ip = 1.0 / p;
+  const double c00 = b00 * ip, c01 = a01 * ip, c02 = a02 * ip, c11 = b11 * ip, c12 = a12 * ip, c22 = b22 * ip;
+  double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+  r = fmin(1.0, fmax(-1.0, r));
+  const double phi = acos(r) / 3.0;
+  const double e2 = q + 2.0 * p * cos(phi);
+  const double e0 = q + 2.0 * p * cos(phi + 2.0943951023931953);
+  ev[0] = e0; ev[2] = e2; ev[1] = 3.0 * q - e0 - e2;
+}
+
 // ---------------------------------------------------------------- camera models
 struct CamIntr {  // compact per-slot copy of okb_camera
   double fu, fv, cu, cv;

@@ -53,12 +53,13 @@ inline BriskPattern make_pattern(int desc_bytes) {
       ++idx;
     }
   }
-  struct Pr { double d; int i, j; };
+  // squared distances quantised to 1e-6 (ordering of equal distances must not depend on FP contraction)
+  struct Pr { long long d; int i, j; };
   std::vector<Pr> all;
   for (int i = 0; i < kPatternPoints; ++i)
     for (int j = i + 1; j < kPatternPoints; ++j) {
       const double dx = P.px[i] - P.px[j], dy = P.py[i] - P.py[j];
-      all.push_back({dx * dx + dy * dy, i, j});
+      all.push_back({std::llround((dx * dx + dy * dy) * 1e6), i, j});
     }
   std::stable_sort(all.begin(), all.end(), [](const Pr& a, const Pr& b) {
     if (a.d != b.d) return a.d < b.d;
