@@ -25,6 +25,8 @@ struct okb_ctx {
   int smem_optin = 0;
   int chunk_cap = 1;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_imu = nullptr;     // k_imu runs beside the landmark kernels
+  cudaEvent_t ev_round = nullptr, ev_imu = nullptr;
   std::vector<WinStore> wins;
   std::vector<okb::WinDev> host;      // host mirror of d_wins
   okb::WinDev* d_wins = nullptr;

@@ -47,6 +47,13 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
     delete c;
     return OKB_ERR_CUDA;
   }
+  if (cudaStreamCreateWithFlags(&c->stream_imu, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_round, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_imu, cudaEventDisableTiming) != cudaSuccess) {
+    g_create_error = "cudaStreamCreate / cudaEventCreate failed";
+    delete c;
+    return OKB_ERR_CUDA;
+  }
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device_id);
   c->sm_count = prop.multiProcessorCount;
@@ -63,8 +70,8 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
     return OKB_ERR_CUDA;
   }
   cudaMemset(c->d_states, 0, sizeof(SolverState) * max_windows);
-  cudaFuncSetAttribute(k_landmarks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-  cudaFuncSetAttribute(k_landmarks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_schur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_schur<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   cudaFuncSetAttribute(k_quality, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   *out = c;
@@ -85,6 +92,9 @@ extern "C" void okb_ctx_destroy(okb_ctx* c) {
   if (c->h_states) cudaFreeHost(c->h_states);
   if (c->hook_buf) cudaFree(c->hook_buf);
   for (auto e : c->prof_events) cudaEventDestroy(e);
+  if (c->ev_round) cudaEventDestroy(c->ev_round);
+  if (c->ev_imu) cudaEventDestroy(c->ev_imu);
+  if (c->stream_imu) cudaStreamDestroy(c->stream_imu);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -126,14 +136,14 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   const int dc = 6 * K, d = dc + 9 * NSB, dcp = 4 * ((dc + 1 + 3) / 4);
   if (d > kMaxDense) { c->set_error("reduced system too large"); return OKB_ERR_CAPACITY; }
   const int NT = dcp / 4, NTT = NT * (NT + 1) / 2;
-  if (NTT > 2 * A_THREADS) { c->set_error("too many frames for the Schur tile kernel"); return OKB_ERR_CAPACITY; }
+  if (NTT > 2 * A2_THREADS) { c->set_error("too many frames for the Schur tile kernel"); return OKB_ERR_CAPACITY; }
   int marg_n = 0, marg_nb = 0, marg_xdim = 0;
   if (D->marg && D->marg->n > 0) {
     marg_n = D->marg->n; marg_nb = D->marg->n_blocks;
     if (marg_n > kMaxMarg) { c->set_error("marginalisation prior too large"); return OKB_ERR_CAPACITY; }
     for (int b = 0; b < marg_nb; ++b) marg_xdim += (D->marg->block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
   }
-  const size_t smA = smemA_bytes(NSP, K, dcp);
+  const size_t smA = smemA2_bytes(K, dcp);
   if (smA > (size_t)c->smem_optin) { c->set_error("window does not fit kernel A shared memory"); return OKB_ERR_CAPACITY; }
 
   // ---- arena plan: [inputs (copied from the staging buffer)] [scratch]
@@ -152,8 +162,8 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   const size_t o_lm = P.take(sizeof(double) * 4 * L);
   const size_t o_slots = P.take(sizeof(SlotInfo) * NSP);
   const size_t o_cams = P.take(sizeof(okb_camera) * NC);
-  const size_t o_obsz = P.take(sizeof(double2) * (size_t)L * NSP);
-  const size_t o_obsw = P.take(sizeof(double) * (size_t)L * NSP);
+  const size_t o_obsz = P.take(sizeof(double2) * (size_t)L * NS);
+  const size_t o_obsw = P.take(sizeof(double) * (size_t)L * NS);
   const size_t o_vis = P.take(sizeof(uint32_t) * L);
   const size_t o_imut = P.take(sizeof(okb_imu_term) * std::max(W.n_imu, 1));
   const size_t o_samp = P.take(sizeof(okb_imu_sample) * std::max(W.n_samples, 1));
@@ -177,10 +187,14 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   for (int b = 0; b < 2; ++b) { o_lmg[b] = P.take(sizeof(double) * 3 * L); o_lmE[b] = P.take(sizeof(double) * 3 * L); }
   const size_t o_Rinv = P.take(sizeof(double) * 6 * L);
   const size_t o_M = P.take(sizeof(double) * 6 * (size_t)L * K);
+  const size_t o_mf = P.take(sizeof(double) * 3 * (size_t)L * K);
   const size_t o_gn = P.take(sizeof(double) * 3 * L);
+  const size_t o_Li = P.take(sizeof(double) * 9 * L);
   const size_t o_scale = P.take(sizeof(double) * 3 * L);
   const size_t o_quality = P.take(sizeof(double) * L);
-  const int pstride = 4 + 27 * K + dcp * dcp;
+  const int pstride = dcp * dcp;
+  const int n_cx = (L + L1_THREADS - 1) / L1_THREADS;
+  const size_t o_partH = P.take(sizeof(double) * (size_t)n_cx * K * kPartH);
   const size_t o_part = P.take(sizeof(double) * (size_t)pstride * c->chunk_cap);
   const size_t o_Hd = P.take(sizeof(double) * (size_t)d * d);
   for (int b = 0; b < 2; ++b) { o_gd[b] = P.take(sizeof(double) * d); o_Ed[b] = P.take(sizeof(double) * d); }
@@ -230,7 +244,7 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
     SlotInfo& si = slots[s];
     if (!si.valid) si = SlotInfo{(int)ob.pose_idx, (int)ob.ext_idx, (int)ob.cam_idx, 1};
     else if (si.ext_idx != (int)ob.ext_idx) { c->set_error("inconsistent extrinsics block for a (frame,camera) slot"); return OKB_ERR_INVALID_ARG; }
-    const size_t g = (size_t)ob.lm_idx * NSP + s;
+    const size_t g = (size_t)s * L + ob.lm_idx;
     if (ow[g] != 0.0) { c->set_error("duplicate observation of a landmark in one (frame,camera)"); return OKB_ERR_UNSUPPORTED; }
     if (!(ob.sqrt_info > 0.0)) { c->set_error("observation with non-positive sqrt information"); return OKB_ERR_INVALID_ARG; }
     oz[g] = make_double2(ob.z[0], ob.z[1]);
@@ -291,7 +305,7 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   W.obs_w = dp(o_obsw);
   W.lm_vis = reinterpret_cast<uint32_t*>(A + o_vis);
   for (int b = 0; b < 2; ++b) { W.lm_g[b] = dp(o_lmg[b]); W.lm_E[b] = dp(o_lmE[b]); W.gd[b] = dp(o_gd[b]); W.Ed[b] = dp(o_Ed[b]); }
-  W.lm_Rinv = dp(o_Rinv); W.lm_M = dp(o_M); W.lm_gn = dp(o_gn); W.lm_scale = dp(o_scale); W.quality = dp(o_quality);
+  W.lm_Rinv = dp(o_Rinv); W.lm_M = dp(o_M); W.lm_mf = dp(o_mf); W.partH = dp(o_partH); W.lm_gn = dp(o_gn); W.lm_Li = dp(o_Li); W.lm_scale = dp(o_scale); W.quality = dp(o_quality);
   W.partA = dp(o_part); W.partA_stride = pstride;
   W.Hd = dp(o_Hd); W.ud = dp(o_ud); W.scale_d = dp(o_scd); W.chol = dp(o_chol);
   W.imu_terms = reinterpret_cast<okb_imu_term*>(A + o_imut);
@@ -383,7 +397,7 @@ extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
 // optimize
 // ---------------------------------------------------------------------------------------------
 static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_options& opt, int rounds) {
-  int max_chunks = 1, tpt = 1, max_imu = 0;
+  int max_chunks = 1, tpt = 1, max_imu = 0, max_cx = 1, max_K = 1;
   size_t smA = 0, smS = 0;
   bool chol_smem = true;
   for (int i = first; i < first + count; ++i) {
@@ -391,8 +405,10 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
     max_chunks = std::max(max_chunks, W.n_chunks);
     max_imu = std::max(max_imu, W.n_imu);
     const int NT = W.dcp / 4;
-    if (NT * (NT + 1) / 2 > A_THREADS) tpt = 2;
-    smA = std::max(smA, smemA_bytes(W.NSP, W.K, W.dcp));
+    if (NT * (NT + 1) / 2 > A2_THREADS) tpt = 2;
+    smA = std::max(smA, smemA2_bytes(W.K, W.dcp));
+    max_cx = std::max(max_cx, (W.L + L1_THREADS - 1) / L1_THREADS);
+    max_K = std::max(max_K, W.K);
     if (smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, true) > (size_t)c->smem_optin) chol_smem = false;
   }
   for (int i = first; i < first + count; ++i) {
@@ -402,14 +418,21 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
   if (smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
   for (int r = 0; r < rounds; ++r) {
     const dim3 gridA(max_chunks, count);
-    prof_begin(c, 0);
-    if (tpt == 1) k_landmarks<1><<<gridA, A_THREADS, smA, c->stream>>>(c->d_wins, first);
-    else k_landmarks<2><<<gridA, A_THREADS, smA, c->stream>>>(c->d_wins, first);
-    prof_end(c);
-    if (max_imu > 0) {
-      k_imu<<<dim3(max_imu, count), 32, 0, c->stream>>>(c->d_wins, first);
+    if (max_imu > 0) {   // IMU terms only depend on the previous round's candidate: run beside the landmark kernels
+      cudaEventRecord(c->ev_round, c->stream);
+      cudaStreamWaitEvent(c->stream_imu, c->ev_round, 0);
+      k_imu<<<dim3(max_imu, count), 32, 0, c->stream_imu>>>(c->d_wins, first);
+      cudaEventRecord(c->ev_imu, c->stream_imu);
       c->launches += 1;
     }
+    prof_begin(c, 0);
+    k_linearize<<<dim3(max_cx, max_K, count), L1_THREADS, 0, c->stream>>>(c->d_wins, first);
+    k_lmblock<<<dim3(max_cx, count), 128, 0, c->stream>>>(c->d_wins, first);
+    if (tpt == 1) k_schur<1><<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first);
+    else k_schur<2><<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first);
+    prof_end(c);
+    c->launches += 2;
+    if (max_imu > 0) cudaStreamWaitEvent(c->stream, c->ev_imu, 0);
     prof_begin(c, 1);
     k_solve<<<count, S_THREADS, smS, c->stream>>>(c->d_wins, first, opt, chol_smem ? 1 : 0);
     prof_end(c);
@@ -429,7 +452,7 @@ extern "C" int okb_optimize_async(okb_ctx* c, int first, int count, const okb_so
     WinDev& W = c->host[i];
     int chunks = (2 * c->sm_count + count - 1) / count;
     chunks = std::max(1, std::min(chunks, c->chunk_cap));
-    chunks = std::min(chunks, std::max(1, W.L / (2 * A_WARPS)));
+    chunks = std::min(chunks, std::max(1, W.L / (2 * A2_TILE)));
     W.n_chunks = chunks;
     W.lm_per_chunk = (W.L + chunks - 1) / chunks;
     W.use_cauchy = opt->use_cauchy_loss ? 1 : 0;
@@ -460,10 +483,14 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
   // post-solve landmark quality (Estimator.cpp:880-894)
   {
     size_t smQ = 0;
-    for (int i = first; i < first + count; ++i) smQ = std::max(smQ, (size_t)c->host[i].NSP * sizeof(SlotCtx));
-    const int gx = std::max(1, std::min(64, (2 * c->sm_count + count - 1) / count));
+    int maxL = 1;
+    for (int i = first; i < first + count; ++i) {
+      smQ = std::max(smQ, (size_t)c->host[i].NS * sizeof(SlotCtx));
+      maxL = std::max(maxL, c->host[i].L);
+    }
+    const int gx = std::max(1, std::min((maxL + 127) / 128, (4 * c->sm_count + count - 1) / count));
     prof_begin(c, 2);
-    k_quality<<<dim3(gx, count), 256, smQ, c->stream>>>(c->d_wins, first);
+    k_quality<<<dim3(gx, count), 128, smQ, c->stream>>>(c->d_wins, first);
     prof_end(c);
     c->launches += 1;
     OKB_CUDA(c, cudaGetLastError());

@@ -76,20 +76,23 @@ struct WinDev {
   // graph
   SlotInfo* slots;                             // [NSP]
   okb_camera* cams;                            // [NC]
-  double2* obs_z;                              // [L][NSP]
-  double* obs_w;                               // [L][NSP] sqrt information, 0 = no observation
+  double2* obs_z;                              // [NS][L]  slot-major: coalesced for thread-per-landmark kernels
+  double* obs_w;                               // [NS][L] sqrt information, 0 = no observation
   uint32_t* lm_vis;                            // [L] bit f set = observed in frame f
   // per-landmark solver data
   double* lm_g[2];                             // [L][3] gradient block (double buffered: cur / speculative)
   double* lm_E[2];                             // [L][3] metric (Ceres diagonal^2 / scale^2)
   double* lm_Rinv;                             // [L][6] (H_ll + mu E)^-1, symmetric packed
   double* lm_M;                                // [K][L][6] per-frame sum of rho' A^T A
+  double* lm_mf;                               // [K][L][3] per-frame sum of rho' A^T r
+  double* lm_Li;                               // [L][9] L^-1 of (H_ll + mu E) (6) and z = L^-1 g_l (3)
   double* lm_gn;                               // [L][3] Gauss-Newton step of the current linearisation
   double* lm_scale;                            // [L][3] Jacobi scale (fixed after the first linearisation)
   double* quality;                             // [L]
   // kernel A -> kernel S partial sums, one record per chunk
-  double* partA;                               // [n_chunks][partA_stride]
-  int partA_stride;                            // 4 + 27*K + dcp*dcp
+  double* partA;                               // [n_chunks][dcp*dcp] Schur accumulator per chunk (k_schur)
+  int partA_stride;                            // dcp*dcp
+  double* partH;                               // [ceil(L/128)][K][32] pose-block sums, cost, step norm (k_linearize)
   // dense part
   double* Hd;                                  // [d][d] J^T J restricted to dense blocks (speculative)
   double* gd[2];                               // [d]

@@ -8,23 +8,16 @@
 //       traditional dogleg step, candidate state.
 // plus k_quality (post-solve landmark quality, Estimator.cpp:880-894) and small utility kernels.
 #pragma once
+#include "okb_chol.cuh"
 #include "okb_estimator.cuh"
+#include "okb_kernels_lm.cuh"
 
 namespace okb {
 
-constexpr int A_WARPS = 12;
-constexpr int A_THREADS = A_WARPS * 32;
 constexpr int S_THREADS = 512;
 constexpr int S_WARPS = S_THREADS / 32;
 constexpr int kImuScratch = 3 * 225 + 450 + 450 + 16;   // doubles of shared scratch per IMU warp
 constexpr int kImuOut = 932;     // doubles per IMU term produced by k_imu: H30 | g30 | cost | pad
-
-struct SlotCtx {
-  SlotXf xf;
-  CamIntr cam;
-  int frame;
-  int valid;
-};
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -62,317 +55,6 @@ __device__ __forceinline__ double block_max(double v, double* red) {
   double s = red[0];
   for (int i = 1; i < nw; ++i) s = fmax(s, red[i]);
   return s;
-}
-
-// shared-memory footprint of kernel A for a window shape
-__host__ __device__ inline size_t smemA_bytes(int NSP, int K, int dcp) {
-  size_t b = 0;
-  b += (size_t)NSP * sizeof(SlotCtx);
-  b = (b + 15) & ~(size_t)15;
-  b += (size_t)K * 4 * sizeof(double);                    // frame translations (+pad)
-  b += (size_t)A_WARPS * 27 * K * sizeof(double);         // per-warp H_pp / g_p accumulators
-  b += (size_t)A_WARPS * K * 9 * sizeof(double);          // per-warp stash of M_f, m_f
-  b += (size_t)3 * A_WARPS * dcp * sizeof(double);        // Y tile, k-major
-  b += 64 * sizeof(double);                               // reduction scratch
-  return b;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Kernel A
-// ------------------------------------------------------------------------------------------------
-template <int TPT>
-__global__ void __launch_bounds__(A_THREADS, 1) k_landmarks(const WinDev* __restrict__ wins, int win_first) {
-  const WinDev& W = wins[win_first + blockIdx.y];
-  SolverState* st = W.st;
-  if (st->done) return;
-  const int chunk = blockIdx.x;
-  if (chunk >= W.n_chunks) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = W.K, NSP = W.NSP, CP = W.CP, NG = W.NG, dc = W.dc, dcp = W.dcp, L = W.L;
-
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  size_t off = 0;
-  SlotCtx* slots = reinterpret_cast<SlotCtx*>(smem_raw);
-  off += (size_t)NSP * sizeof(SlotCtx);
-  off = (off + 15) & ~(size_t)15;
-  double* tws = reinterpret_cast<double*>(smem_raw + off); off += (size_t)K * 4 * sizeof(double);
-  double* hpp = reinterpret_cast<double*>(smem_raw + off); off += (size_t)A_WARPS * 27 * K * sizeof(double);
-  double* stash = reinterpret_cast<double*>(smem_raw + off); off += (size_t)A_WARPS * K * 9 * sizeof(double);
-  double* Yt = reinterpret_cast<double*>(smem_raw + off); off += (size_t)3 * A_WARPS * dcp * sizeof(double);
-  double* red = reinterpret_cast<double*>(smem_raw + off);
-
-  const int mode = st->mode;
-  const int cur = st->cur;
-  const double step_a = st->a, step_b = st->b;
-  const double mu = (mode == MODE_STEP) ? fmax(kMinMu, 2.0 * st->mu / kMuIncrease) : st->mu;
-  const bool cauchy = W.use_cauchy != 0;
-
-  // ---- prologue: slot transforms at the candidate poses
-  for (int s = tid; s < NSP; s += A_THREADS) {
-    const SlotInfo si = W.slots[s];
-    SlotCtx& sc = slots[s];
-    sc.valid = si.valid;
-    sc.frame = si.valid ? si.pose_idx : 0;
-    if (si.valid) {
-      make_slot_xf(W.pose_c + 7 * si.pose_idx, W.ext + 7 * si.ext_idx, sc.xf);
-      cam_load(W.cams[si.cam_idx], sc.cam);
-    }
-  }
-  for (int f = tid; f < K; f += A_THREADS) {
-    tws[4 * f + 0] = W.pose_c[7 * f + 0]; tws[4 * f + 1] = W.pose_c[7 * f + 1]; tws[4 * f + 2] = W.pose_c[7 * f + 2];
-  }
-  for (int i = tid; i < A_WARPS * 27 * K; i += A_THREADS) hpp[i] = 0.0;
-  __syncthreads();
-
-  // ---- SYRK thread mapping: 4x4 micro-tiles of the lower triangle of the (dcp x dcp) matrix.
-  // TPT = 1: one micro-tile per thread, the tile's columns split KS ways; TPT = 2: two micro-tiles.
-  const int NT = dcp >> 2;
-  const int NTT = NT * (NT + 1) / 2;
-  int KS = 1;
-  if (TPT == 1) { KS = A_THREADS / NTT; if (KS < 1) KS = 1; }
-  const int ks = (TPT == 1) ? tid / NTT : 0;
-  int ti[TPT], tj[TPT];
-  bool syrk_on[TPT];
-  double acc[TPT][16];
-#pragma unroll
-  for (int m = 0; m < TPT; ++m) {
-    const int tt = (TPT == 1) ? tid % NTT : tid + m * A_THREADS;
-    syrk_on[m] = (TPT == 1) ? (ks < KS) : (tt < NTT);
-    const int tq = syrk_on[m] ? tt : 0;
-    int a = (int)((sqrt(8.0 * tq + 1.0) - 1.0) * 0.5);
-    while (a * (a + 1) / 2 > tq) --a;
-    while ((a + 1) * (a + 2) / 2 <= tq) ++a;
-    ti[m] = a;
-    tj[m] = tq - a * (a + 1) / 2;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[m][i] = 0.0;
-  }
-
-  const int lm_begin = chunk * W.lm_per_chunk;
-  const int lm_end = min(L, lm_begin + W.lm_per_chunk);
-  const int ntiles = (lm_end - lm_begin + A_WARPS - 1) / A_WARPS;
-  double cost_acc = 0.0, stepn2 = 0.0;
-  double* my_hpp = hpp + (size_t)warp * 27 * K;
-  double* my_stash = stash + (size_t)warp * K * 9;
-  double* my_Y = Yt + (size_t)3 * warp * dcp;
-  const double* gcur = W.lm_g[cur];
-  const double* Ecur = W.lm_E[cur];
-  double* gspec = W.lm_g[cur ^ 1];
-  double* Espec = W.lm_E[cur ^ 1];
-
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int l = lm_begin + tile * A_WARPS + warp;
-    for (int i = lane; i < 3 * dcp; i += 32) my_Y[i] = 0.0;
-    for (int i = lane; i < 9 * K; i += 32) my_stash[i] = 0.0;
-    __syncwarp();
-    if (l < lm_end) {
-      // candidate landmark
-      double X[4];
-      {
-        const double4 x4 = *reinterpret_cast<const double4*>(W.lm + 4 * (size_t)l);
-        X[0] = x4.x; X[1] = x4.y; X[2] = x4.z; X[3] = x4.w;
-      }
-      if (mode == MODE_STEP) {
-        double dn = 0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const double dlt = step_a * gcur[3 * (size_t)l + c] / Ecur[3 * (size_t)l + c] + step_b * W.lm_gn[3 * (size_t)l + c];
-          X[c] += dlt;
-          dn += dlt * dlt;
-        }
-        if (lane == 0) stepn2 += dn;
-      }
-      if (lane == 0) *reinterpret_cast<double4*>(W.lm_c + 4 * (size_t)l) = make_double4(X[0], X[1], X[2], X[3]);
-
-      // ---- phase 1: lane = slot
-      for (int g = 0; g < NG; ++g) {
-        const int slot = g * 32 + lane;
-        const SlotCtx& sc = slots[slot];
-        const double2 z = W.obs_z[(size_t)l * NSP + slot];
-        const double wobs = W.obs_w[(size_t)l * NSP + slot];
-        double M[6] = {0, 0, 0, 0, 0, 0}, m[3] = {0, 0, 0};
-        if (wobs > 0.0 && sc.valid) {
-          double r[2], A[6];
-          reproj_slot<true>(sc.xf, sc.cam, X, z.x, z.y, wobs, r, A);
-          const double sq = r[0] * r[0] + r[1] * r[1];
-          double rho1 = 1.0;
-          if (cauchy) { rho1 = 1.0 / (1.0 + sq); cost_acc += 0.5 * log(1.0 + sq); }
-          else cost_acc += 0.5 * sq;
-          M[0] = rho1 * (A[0] * A[0] + A[3] * A[3]);
-          M[1] = rho1 * (A[0] * A[1] + A[3] * A[4]);
-          M[2] = rho1 * (A[0] * A[2] + A[3] * A[5]);
-          M[3] = rho1 * (A[1] * A[1] + A[4] * A[4]);
-          M[4] = rho1 * (A[1] * A[2] + A[4] * A[5]);
-          M[5] = rho1 * (A[2] * A[2] + A[5] * A[5]);
-          m[0] = rho1 * (A[0] * r[0] + A[3] * r[1]);
-          m[1] = rho1 * (A[1] * r[0] + A[4] * r[1]);
-          m[2] = rho1 * (A[2] * r[0] + A[5] * r[1]);
-        }
-        for (int o = 1; o < CP; o <<= 1) {
-#pragma unroll
-          for (int i = 0; i < 6; ++i) M[i] += __shfl_xor_sync(0xffffffffu, M[i], o);
-#pragma unroll
-          for (int i = 0; i < 3; ++i) m[i] += __shfl_xor_sync(0xffffffffu, m[i], o);
-        }
-        if ((lane & (CP - 1)) == 0 && sc.valid) {
-          double* sp = my_stash + 9 * sc.frame;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) sp[i] = M[i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) sp[6 + i] = m[i];
-        }
-      }
-      __syncwarp();
-      // ---- landmark block (replicated on all lanes, fixed summation order)
-      double H[6] = {0, 0, 0, 0, 0, 0}, gl[3] = {0, 0, 0};
-      for (int f = 0; f < K; ++f) {
-        const double* sp = my_stash + 9 * f;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) H[i] += sp[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) gl[i] -= sp[6 + i];
-      }
-      double sc3[3], E[3];
-      const double hd[3] = {H[0], H[3], H[5]};
-      if (mode == MODE_INIT) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sc3[c] = 1.0 / (1.0 + sqrt(hd[c]));
-        if (lane == 0) { W.lm_scale[3 * (size_t)l] = sc3[0]; W.lm_scale[3 * (size_t)l + 1] = sc3[1]; W.lm_scale[3 * (size_t)l + 2] = sc3[2]; }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sc3[c] = W.lm_scale[3 * (size_t)l + c];
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double s2 = sc3[c] * sc3[c];
-        E[c] = fmin(fmax(s2 * hd[c], kMinDiag), kMaxDiag) / s2;
-      }
-      double R[6] = {H[0] + mu * E[0], H[1], H[2], H[3] + mu * E[1], H[4], H[5] + mu * E[2]};
-      double Lc[6], Li[6];
-      const bool pd = chol3(R, Lc);
-      if (pd) linv3(Lc, Li);
-      else {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Li[i] = 0.0;
-        if (lane == 0) st->numeric_fail = 1;
-      }
-      if (lane == 0) {
-        // Rinv = Li^T Li
-        double* Ro = W.lm_Rinv + 6 * (size_t)l;
-        Ro[0] = Li[0] * Li[0] + Li[1] * Li[1] + Li[3] * Li[3];
-        Ro[1] = Li[1] * Li[2] + Li[3] * Li[4];
-        Ro[2] = Li[3] * Li[5];
-        Ro[3] = Li[2] * Li[2] + Li[4] * Li[4];
-        Ro[4] = Li[4] * Li[5];
-        Ro[5] = Li[5] * Li[5];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { gspec[3 * (size_t)l + c] = gl[c]; Espec[3 * (size_t)l + c] = E[c]; }
-        // z = L^-1 g_l  -> augmented row dc of the Y tile
-        my_Y[0 * dcp + dc] = Li[0] * gl[0];
-        my_Y[1 * dcp + dc] = Li[1] * gl[0] + Li[2] * gl[1];
-        my_Y[2 * dcp + dc] = Li[3] * gl[0] + Li[4] * gl[1] + Li[5] * gl[2];
-      }
-      // ---- phase 2: lane = frame
-      const uint32_t vis = W.lm_vis[l];
-      for (int f = lane; f < K; f += 32) {
-        if (!((vis >> f) & 1u)) continue;
-        const double* sp = my_stash + 9 * f;
-        const double M0 = sp[0], M1 = sp[1], M2 = sp[2], M3 = sp[3], M4 = sp[4], M5 = sp[5];
-        const double m0 = sp[6], m1 = sp[7], m2 = sp[8];
-        double* Mo = W.lm_M + ((size_t)f * L + l) * 6;
-        Mo[0] = M0; Mo[1] = M1; Mo[2] = M2; Mo[3] = M3; Mo[4] = M4; Mo[5] = M5;
-        const double w = X[3];
-        const double p0 = X[0] - tws[4 * f] * w, p1 = X[1] - tws[4 * f + 1] * w, p2 = X[2] - tws[4 * f + 2] * w;
-        // Q = M [p]x  (3x3): columns of [p]x are (0,p2,-p1), (-p2,0,p0), (p1,-p0,0)
-        const double Q00 = M1 * p2 - M2 * p1, Q01 = -M0 * p2 + M2 * p0, Q02 = M0 * p1 - M1 * p0;
-        const double Q10 = M3 * p2 - M4 * p1, Q11 = -M1 * p2 + M4 * p0, Q12 = M1 * p1 - M3 * p0;
-        const double Q20 = M4 * p2 - M5 * p1, Q21 = -M2 * p2 + M5 * p0, Q22 = M2 * p1 - M4 * p0;
-        // H_rr = [p]x^T Q = -[p]x Q : rows of -[p]x are (0,p2,-p1), (-p2,0,p0), (p1,-p0,0)
-        double* hp = my_hpp + f;
-        const double w2 = w * w;
-        hp[0 * K] += w2 * M0; hp[1 * K] += w2 * M1; hp[2 * K] += w2 * M2;
-        hp[3 * K] += w2 * M3; hp[4 * K] += w2 * M4; hp[5 * K] += w2 * M5;
-        // H_tr = -w Q (3x3 row-major)
-        hp[6 * K] -= w * Q00; hp[7 * K] -= w * Q01; hp[8 * K] -= w * Q02;
-        hp[9 * K] -= w * Q10; hp[10 * K] -= w * Q11; hp[11 * K] -= w * Q12;
-        hp[12 * K] -= w * Q20; hp[13 * K] -= w * Q21; hp[14 * K] -= w * Q22;
-        // H_rr (symmetric packed)
-        hp[15 * K] += p2 * Q10 - p1 * Q20;
-        hp[16 * K] += p2 * Q11 - p1 * Q21;
-        hp[17 * K] += p2 * Q12 - p1 * Q22;
-        hp[18 * K] += -p2 * Q01 + p0 * Q21;
-        hp[19 * K] += -p2 * Q02 + p0 * Q22;
-        hp[20 * K] += p1 * Q02 - p0 * Q12;
-        // g_p = [w m ; p x m]
-        hp[21 * K] += w * m0; hp[22 * K] += w * m1; hp[23 * K] += w * m2;
-        hp[24 * K] += p1 * m2 - p2 * m1; hp[25 * K] += p2 * m0 - p0 * m2; hp[26 * K] += p0 * m1 - p1 * m0;
-        // N = M L^-T : column j of L^-T is row j of L^-1 ... N[:,j] = sum_k M[:,k] Li[j][k]
-        const double N00 = M0 * Li[0], N01 = M0 * Li[1] + M1 * Li[2], N02 = M0 * Li[3] + M1 * Li[4] + M2 * Li[5];
-        const double N10 = M1 * Li[0], N11 = M1 * Li[1] + M3 * Li[2], N12 = M1 * Li[3] + M3 * Li[4] + M4 * Li[5];
-        const double N20 = M2 * Li[0], N21 = M2 * Li[1] + M4 * Li[2], N22 = M2 * Li[3] + M4 * Li[4] + M5 * Li[5];
-        // Y_f = W L^-T = -[w N ; [p]x N]
-        double* y0 = my_Y + 0 * dcp + 6 * f;
-        double* y1 = my_Y + 1 * dcp + 6 * f;
-        double* y2 = my_Y + 2 * dcp + 6 * f;
-        y0[0] = -w * N00; y0[1] = -w * N10; y0[2] = -w * N20;
-        y1[0] = -w * N01; y1[1] = -w * N11; y1[2] = -w * N21;
-        y2[0] = -w * N02; y2[1] = -w * N12; y2[2] = -w * N22;
-        // [p]x N column j = p x N[:,j]
-        y0[3] = -(p1 * N20 - p2 * N10); y0[4] = -(p2 * N00 - p0 * N20); y0[5] = -(p0 * N10 - p1 * N00);
-        y1[3] = -(p1 * N21 - p2 * N11); y1[4] = -(p2 * N01 - p0 * N21); y1[5] = -(p0 * N11 - p1 * N01);
-        y2[3] = -(p1 * N22 - p2 * N12); y2[4] = -(p2 * N02 - p0 * N22); y2[5] = -(p0 * N12 - p1 * N02);
-      }
-    }
-    __syncthreads();
-    // ---- SYRK over the tile: acc(ti,tj) += Y[4ti..][k] * Y[4tj..][k]
-#pragma unroll
-    for (int m = 0; m < TPT; ++m) {
-      if (syrk_on[m]) {
-        const int ncols = 3 * A_WARPS;
-        for (int k = ks; k < ncols; k += KS) {
-          const double* row = Yt + (size_t)k * dcp;
-          const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * ti[m]);
-          const double2 a23 = *reinterpret_cast<const double2*>(row + 4 * ti[m] + 2);
-          const double2 b01 = *reinterpret_cast<const double2*>(row + 4 * tj[m]);
-          const double2 b23 = *reinterpret_cast<const double2*>(row + 4 * tj[m] + 2);
-          const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-          const double b[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[m][i * 4 + j] += a[i] * b[j];
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- epilogue: chunk partials
-  double* part = W.partA + (size_t)chunk * W.partA_stride;
-  const double csum = block_sum(cost_acc, red);
-  const double ssum = block_sum(stepn2, red);
-  if (tid == 0) { part[0] = csum; part[1] = ssum; part[2] = 0.0; part[3] = 0.0; }
-  for (int i = tid; i < 27 * K; i += A_THREADS) {
-    double s = 0;
-    for (int w8 = 0; w8 < A_WARPS; ++w8) s += hpp[(size_t)w8 * 27 * K + i];
-    part[4 + i] = s;
-  }
-  double* Sp = part + 4 + 27 * K;
-  for (int s = 0; s < KS; ++s) {
-#pragma unroll
-    for (int m = 0; m < TPT; ++m) {
-      if (syrk_on[m] && ks == s) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            double* p = Sp + (size_t)(4 * ti[m] + i) * dcp + 4 * tj[m] + j;
-            *p = (s == 0) ? acc[m][i * 4 + j] : (*p + acc[m][i * 4 + j]);
-          }
-      }
-    }
-    __syncthreads();
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,7 +105,7 @@ struct SShared {
   double red[64];
   // broadcast scalars
   double cand_cost, cost_lm, stepn2_lm, cost_dense;
-  int adopt, terminate, commit_only, fail, spec;
+  int adopt, terminate, commit_only, fail, spec, chol_flag;
 };
 
 // r = S e etc. are tiny; one warp handles all priors.
@@ -483,9 +165,9 @@ __host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_im
   b += (size_t)8 * d * sizeof(double);                     // gd, Ed, ud, rhs, vd, tmp, delta, colk
   b += (size_t)K * 4 * sizeof(double);                     // committed frame translations
   b += (size_t)3 * (n_marg > 0 ? n_marg : 1) * sizeof(double);   // marg: dchi, e, Jte
-  size_t imu = 1024;
-  size_t ch = chol_in_smem ? (size_t)d * d * sizeof(double) : 0;
-  b += imu > ch ? imu : ch;
+  b = (b + 31) & ~(size_t)31;
+  b += (size_t)CH_NB * ((d + 3) & ~3) * sizeof(double);      // Cholesky panel (k-major)
+  b += chol_in_smem ? (size_t)d * d * sizeof(double) : 16;   // the reduced system itself
   return b;
 }
 
@@ -514,7 +196,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   double* s_dchi = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
   double* s_me = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
   double* s_mJte = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
-  double* s_big = reinterpret_cast<double*>(smem_raw + off);   // IMU scratch, later the Cholesky matrix
+  const int ld_p = (d + 3) & ~3;
+  off = (off + 31) & ~(size_t)31;
+  double* s_panel = reinterpret_cast<double*>(smem_raw + off); off += (size_t)CH_NB * ld_p * 8;
+  double* s_big = reinterpret_cast<double*>(smem_raw + off);   // the reduced system (when it fits)
 
   unsigned long long t_ph = globaltimer_ns();
 #define PHASE_MARK(i) do { if (tid == 0) { const unsigned long long n_ = globaltimer_ns(); st->phase_ns[i] += n_ - t_ph; t_ph = n_; } } while (0)
@@ -633,17 +318,18 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   const double cost_dense = block_sum(cost_dense_local, sh->red);
 
   PHASE_MARK(0);
-  // ================= phase 2: gather kernel-A partials =================
+  // ================= phase 2: gather the landmark-kernel partials =================
   double cost_lm = 0.0, stepn2_lm = 0.0;
-  for (int c = 0; c < W.n_chunks; ++c) {   // fixed order, replicated in all threads (tiny)
-    cost_lm += W.partA[(size_t)c * W.partA_stride + 0];
-    stepn2_lm += W.partA[(size_t)c * W.partA_stride + 1];
+  const int n_cx = (L + L1_THREADS - 1) / L1_THREADS;
+  for (int i = 0; i < n_cx * K; ++i) {   // fixed order, replicated in all threads (small)
+    cost_lm += W.partH[(size_t)i * kPartH + 27];
+    stepn2_lm += W.partH[(size_t)i * kPartH + 28];
   }
   // H_pp / g_p block contributions
   for (int i = tid; i < 27 * K; i += S_THREADS) {
-    double s = 0;
-    for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + 4 + i];
     const int e = i / K, f = i % K, o = 6 * f;
+    double s = 0;
+    for (int c = 0; c < n_cx; ++c) s += W.partH[((size_t)c * K + f) * kPartH + e];
     if (e < 6) {          // H_tt symmetric packed
       const int a = (e < 3) ? 0 : (e < 5) ? 1 : 2;
       const int b = (e < 3) ? e : (e < 5) ? e - 2 : 2;
@@ -664,7 +350,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     }
   }
   __syncthreads();
-
   PHASE_MARK(1);
   // ================= phase 3: judge =================
   if (tid == 0) {
@@ -767,7 +452,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       if (r0 < dc && c0 < dc) {
         const int rr = r0 >= c0 ? r0 : c0, cc = r0 >= c0 ? c0 : r0;
         double s = 0;
-        for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + 4 + 27 * K + (size_t)rr * dcp + cc];
+        for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + (size_t)rr * dcp + cc];
         v -= s;
       }
       Mx[i] = v;
@@ -776,54 +461,21 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       double v = s_g[i];
       if (i < dc) {
         double s = 0;
-        for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + 4 + 27 * K + (size_t)dc * dcp + i];
+        for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + (size_t)dc * dcp + i];
         v -= s;
       }
       s_rhs[i] = v;
     }
     __syncthreads();
     PHASE_MARK(2);
-    // ---- dense Cholesky (lower), right-looking
+    // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh)
     int chol_fail = sh->fail;
-    if (!chol_fail) {
-      const int ty = tid >> 5, tx = tid & 31;
-      for (int k = 0; k < d; ++k) {
-        const double piv = Mx[(size_t)k * d + k];
-        if (!(piv > 0.0)) { chol_fail = 1; break; }   // uniform: every thread reads the same value
-        const double inv = 1.0 / sqrt(piv);
-        __syncthreads();
-        for (int i = k + tid; i < d; i += S_THREADS) {
-          const double v = (i == k) ? sqrt(piv) : Mx[(size_t)i * d + k] * inv;
-          Mx[(size_t)i * d + k] = v;
-          s_col[i] = v;
-        }
-        __syncthreads();
-        for (int i = k + 1 + ty; i < d; i += S_WARPS) {
-          const double lik = s_col[i];
-          for (int j = k + 1 + tx; j <= i; j += 32) Mx[(size_t)i * d + j] -= lik * s_col[j];
-        }
-        __syncthreads();
-      }
-    }
+    if (!chol_fail) chol_fail = block_cholesky(Mx, d, s_panel, ld_p, &sh->chol_flag);
     PHASE_MARK(3);
     if (!chol_fail) {
-      // forward / backward substitution (column oriented)
       for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = s_rhs[i];
       __syncthreads();
-      for (int k = 0; k < d; ++k) {
-        if (tid == 0) s_tmp[k] = s_tmp[k] / Mx[(size_t)k * d + k];
-        __syncthreads();
-        const double zk = s_tmp[k];
-        for (int i = k + 1 + tid; i < d; i += S_THREADS) s_tmp[i] -= Mx[(size_t)i * d + k] * zk;
-        __syncthreads();
-      }
-      for (int k = d - 1; k >= 0; --k) {
-        if (tid == 0) s_tmp[k] = s_tmp[k] / Mx[(size_t)k * d + k];
-        __syncthreads();
-        const double uk = s_tmp[k];
-        for (int i = tid; i < k; i += S_THREADS) s_tmp[i] -= Mx[(size_t)k * d + i] * uk;
-        __syncthreads();
-      }
+      block_cholesky_solve(Mx, d, s_tmp);
       for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
       __syncthreads();
     }
@@ -1018,50 +670,6 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   }
   PHASE_MARK(6);
 #undef PHASE_MARK
-}
-
-// ------------------------------------------------------------------------------------------------
-// Post-solve landmark quality: H = sum J_lm^T J_lm (sqrt-information weighted, no robust weight)
-// at the final estimate; quality = sqrt(lambda_min)/sqrt(lambda_max), 0 if lambda_min < 1e-12.
-// Warp per landmark, lane per slot.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_quality(const WinDev* __restrict__ wins, int win_first) {
-  const WinDev& W = wins[win_first + blockIdx.y];
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SlotCtx* slots = reinterpret_cast<SlotCtx*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int s = tid; s < W.NSP; s += blockDim.x) {
-    const SlotInfo si = W.slots[s];
-    SlotCtx& sc = slots[s];
-    sc.valid = si.valid; sc.frame = si.valid ? si.pose_idx : 0;
-    if (si.valid) { make_slot_xf(W.pose + 7 * si.pose_idx, W.ext + 7 * si.ext_idx, sc.xf); cam_load(W.cams[si.cam_idx], sc.cam); }
-  }
-  __syncthreads();
-  const int nw = blockDim.x >> 5;
-  for (int l = blockIdx.x * nw + warp; l < W.L; l += gridDim.x * nw) {
-    const double4 x4 = *reinterpret_cast<const double4*>(W.lm + 4 * (size_t)l);
-    const double X[4] = {x4.x, x4.y, x4.z, x4.w};
-    double H[6] = {0, 0, 0, 0, 0, 0};
-    for (int g = 0; g < W.NG; ++g) {
-      const int slot = g * 32 + lane;
-      const SlotCtx& sc = slots[slot];
-      const double2 z = W.obs_z[(size_t)l * W.NSP + slot];
-      const double wobs = W.obs_w[(size_t)l * W.NSP + slot];
-      if (wobs > 0.0 && sc.valid) {
-        double r[2], A[6];
-        reproj_slot<true>(sc.xf, sc.cam, X, z.x, z.y, wobs, r, A);
-        H[0] += A[0] * A[0] + A[3] * A[3]; H[1] += A[0] * A[1] + A[3] * A[4]; H[2] += A[0] * A[2] + A[3] * A[5];
-        H[3] += A[1] * A[1] + A[4] * A[4]; H[4] += A[1] * A[2] + A[4] * A[5]; H[5] += A[2] * A[2] + A[5] * A[5];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) H[i] = warp_sum(H[i]);
-    if (lane == 0) {
-      double ev[3];
-      eig3sym_closed(H, ev);
-      W.quality[l] = (ev[0] < 1.0e-12) ? 0.0 : sqrt(ev[0]) / sqrt(ev[2]);
-    }
-  }
 }
 
 // resets the solver state (and optionally the parameter state) of a range of windows
