@@ -15,7 +15,7 @@ constexpr int CH_NB = 16;
 // In-place lower Cholesky of the d x d row-major matrix M (only the lower triangle is referenced
 // and written).  `panel` is shared scratch of CH_NB * ld_p doubles (ld_p >= d rounded up to 4),
 // `flag` a shared int.  Returns 0 on success, 1 on a non-positive pivot (uniform over the CTA).
-__device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, int* flag) {
+__device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, double* rdiag, int* flag) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *flag = 0;
   __syncthreads();
@@ -32,9 +32,10 @@ __device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, 
       for (int j = 0; j < CH_NB; ++j) {
         const double piv = __shfl_sync(0xffffffffu, row[j], j);
         if (!(piv > 0.0)) bad = true;
-        const double ljj = sqrt(piv);
-        const double lij = (lane == j) ? ljj : row[j] / ljj;
+        const double rs = rsqrt(piv);            // one slow operation per column instead of sqrt + divide
+        const double lij = (lane == j) ? piv * rs : row[j] * rs;
         row[j] = lij;
+        if (lane == j && j < nb) rdiag[kb + j] = rs;
 #pragma unroll
         for (int c = j + 1; c < CH_NB; ++c) {
           const double lcj = __shfl_sync(0xffffffffu, lij, c);
@@ -65,7 +66,7 @@ __device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, 
           double s = x[j];
 #pragma unroll
           for (int c = 0; c < CH_NB; ++c) if (c < j) s -= x[c] * lrow[c];
-          x[j] = s / lrow[j];
+          x[j] = s * rdiag[kb + j];
         }
       }
 #pragma unroll
@@ -117,7 +118,7 @@ __device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, 
 }
 
 // Solves L L^T x = b in place in `x` (shared memory vector of length d, initialised with b).
-__device__ inline void block_cholesky_solve(const double* M, int d, double* x) {
+__device__ inline void block_cholesky_solve(const double* M, int d, const double* rdiag, double* x) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   // forward: L z = b
   for (int kb = 0; kb < d; kb += CH_NB) {
@@ -125,7 +126,7 @@ __device__ inline void block_cholesky_solve(const double* M, int d, double* x) {
     if (warp == 0) {
       double t = (lane < nb) ? x[kb + lane] : 0.0;
       for (int j = 0; j < nb; ++j) {
-        const double zj = __shfl_sync(0xffffffffu, t, j) / M[(size_t)(kb + j) * d + kb + j];
+        const double zj = __shfl_sync(0xffffffffu, t, j) * rdiag[kb + j];
         if (lane == j) t = zj;
         else if (lane > j && lane < nb) t -= M[(size_t)(kb + lane) * d + kb + j] * zj;
       }
@@ -148,7 +149,7 @@ __device__ inline void block_cholesky_solve(const double* M, int d, double* x) {
     if (warp == 0) {
       double t = (lane < nb) ? x[kb + lane] : 0.0;
       for (int j = nb - 1; j >= 0; --j) {
-        const double uj = __shfl_sync(0xffffffffu, t, j) / M[(size_t)(kb + j) * d + kb + j];
+        const double uj = __shfl_sync(0xffffffffu, t, j) * rdiag[kb + j];
         if (lane == j) t = uj;
         else if (lane < j) t -= M[(size_t)(kb + j) * d + kb + lane] * uj;
       }

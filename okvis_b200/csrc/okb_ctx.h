@@ -14,6 +14,7 @@ struct WinStore {
   size_t staging_bytes = 0;
   size_t h2d_bytes = 0;
   bool uploaded = false;
+  cudaEvent_t copied = nullptr;       // recorded after the H2D copy of `staging`; the next upload of the slot waits on it
 };
 
 struct okb_frontend_state;

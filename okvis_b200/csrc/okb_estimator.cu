@@ -85,6 +85,7 @@ extern "C" void okb_ctx_destroy(okb_ctx* c) {
   for (auto& w : c->wins) {
     if (w.arena) cudaFree(w.arena);
     if (w.staging) cudaFreeHost(w.staging);
+    if (w.copied) cudaEventDestroy(w.copied);
   }
   okb_frontend_release(c);
   if (c->d_wins) cudaFree(c->d_wins);
@@ -217,6 +218,8 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
     OKB_CUDA(c, cudaMallocHost(&S.staging, input_bytes));
     S.staging_bytes = input_bytes;
   }
+  if (!S.copied) OKB_CUDA(c, cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
+  else OKB_CUDA(c, cudaEventSynchronize(S.copied));
   unsigned char* H = S.staging;
   std::memset(H, 0, input_bytes);
   std::memcpy(H + o_pose, D->poses, sizeof(double) * 7 * K);
@@ -325,8 +328,9 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   S.uploaded = true;
   S.h2d_bytes = input_bytes;
   OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + win, &c->host[win], sizeof(WinDev), cudaMemcpyHostToDevice, c->stream));
-  // the staging buffer is reused by the next upload of this slot: wait for the copy
-  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  // No stream synchronisation here: uploads of different slots pipeline behind each other.  The staging
+  // buffer belongs to this slot; its next upload waits on `copied` before touching it.
+  OKB_CUDA(c, cudaEventRecord(S.copied, c->stream));
   return OKB_OK;
 }
 
@@ -549,7 +553,7 @@ __global__ void k_hook_imu(okb_imu_params prm, const okb_imu_sample* s, int n, i
                            const double* sb_ref, int have_ref, ImuCache* cache, double* out /* r15 | SF 450 | sqrt 225 | redo */) {
   __shared__ double buf[3 * 225 + 450 + 450 + 16];
   WarpCtx cx;
-  ImuWork wk{buf, buf + 225, buf + 450};
+  ImuWork wk{buf, buf + 225, buf + 450, buf + 1125};
   double* F01 = buf + 675; double* SF = buf + 1125; double* r15 = buf + 1575;
   if (threadIdx.x == 0) { cache->valid = 0; cache->redo_count = 0; for (int k = 0; k < 9; ++k) cache->sb_ref[k] = 0; }
   __syncwarp();
@@ -564,9 +568,9 @@ __global__ void k_hook_imu(okb_imu_params prm, const okb_imu_sample* s, int n, i
 }
 __global__ void k_hook_propagate(okb_imu_params prm, const okb_imu_sample* s, int n, int64_t t0, int64_t t1, double* io /*16*/,
                                  double* cov, double* jac, int want_cov, int want_jac, int* n_used) {
-  __shared__ double buf[3 * 225];
+  __shared__ double buf[4 * 225];
   WarpCtx cx;
-  ImuWork wk{buf, buf + 225, buf + 450};
+  ImuWork wk{buf, buf + 225, buf + 450, buf + 675};
   const int steps = imu_propagate(cx, s, n, prm, t0, t1, io, io + 7, want_cov ? cov : nullptr, want_jac ? jac : nullptr, wk);
   if (threadIdx.x == 0) *n_used = steps;
 }

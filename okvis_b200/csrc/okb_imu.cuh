@@ -53,9 +53,10 @@ OKB_HD double ns_to_sec(int64_t ns) {
 
 // Workspace for the cooperative 15x15 products: 3 matrices of 225 doubles (shared memory on the device).
 struct ImuWork {
-  double* P;    // covariance
-  double* F;    // transition
-  double* T;    // temp
+  double* P;    // covariance (result)
+  double* F;    // scratch (rows of N; later general 15x15 scratch)
+  double* T;    // scratch (U = N P; later general 15x15 scratch)
+  double* P2;   // second covariance buffer for the ping-pong update
 };
 
 // Integrates the samples over [t0,t1].  PREINT selects the redoPreintegration variant
@@ -73,6 +74,9 @@ OKB_HD int imu_integrate(const Ctx& cx, const okb_imu_sample* s, int n, const ok
   }
   for (int k = 0; k < 3; ++k) st.acc_integral[k] = st.acc_doubleintegral[k] = 0;
   st.Delta_t = 0;
+  // covariance ping-pong buffers: Pc (current) / Pn (next); wk.F holds N's rows, wk.T holds U = N P
+  double* Pc = wk.P;
+  double* Pn = wk.P2;
   if (WANT_COV) {
     for (int e = cx.lane(); e < 225; e += cx.lanes()) wk.P[e] = 0.0;
     cx.sync();
@@ -163,36 +167,41 @@ OKB_HD int imu_integrate(const Ctx& cx, const okb_imu_sample* s, int n, const ok
       st.dp_db_g[k] += F09[k];
     }
     if (WANT_COV) {
-      // F = I + N, N = {(0,3):-[add]x, (0,6): dt I, (0,9): F09, (0,12): F012, (3,9): -dt C1,
-      //                 (6,3): -[0.5 CCa dt]x, (6,9): 0.5 dt sumA, (6,12): -0.5 CC dt}
+      // P <- F P F^T + Q with F = I + N, N nonzero only in rows 0..8:
+      //   N = {(0,3):-[add]x, (0,6): dt I, (0,9): F09, (0,12): F012, (3,9): -dt C1,
+      //        (6,3): -[0.5 CCa dt]x, (6,9): 0.5 dt sumA, (6,12): -0.5 CC dt}
+      // so P' = P + U + U^T + U N^T with U = N P (9 x 15): ~4x fewer multiply-adds than the dense products.
       double X03[9], X63[9];
       crossMx(add, X03);
       const double v63[3] = {0.5 * CCa[0] * dt, 0.5 * CCa[1] * dt, 0.5 * CCa[2] * dt};
       crossMx(v63, X63);
-      for (int e = cx.lane(); e < 225; e += cx.lanes()) {
+      double* Nr = wk.F;          // rows 0..8 of N, dense [9][15]
+      double* U = wk.T;           // U = N P, [9][15]
+      for (int e = cx.lane(); e < 135; e += cx.lanes()) {
         const int rr = e / 15, cc = e % 15;
-        const int br = rr / 3, bc = cc / 3, a = rr % 3, b = cc % 3;
-        double v = (rr == cc) ? 1.0 : 0.0;
+        const int br = rr / 3, bc = cc / 3, a3 = rr % 3, b3 = cc % 3;
+        double v = 0.0;
         if (br == 0) {
-          if (bc == 1) v = -X03[a * 3 + b];
-          else if (bc == 2) v = (a == b) ? dt : 0.0;
-          else if (bc == 3) v = F09[a * 3 + b];
-          else if (bc == 4) v = F012[a * 3 + b];
+          if (bc == 1) v = -X03[a3 * 3 + b3];
+          else if (bc == 2) v = (a3 == b3) ? dt : 0.0;
+          else if (bc == 3) v = F09[a3 * 3 + b3];
+          else if (bc == 4) v = F012[a3 * 3 + b3];
         } else if (br == 1) {
-          if (bc == 3) v = -dt * C1[a * 3 + b];
-        } else if (br == 2) {
-          if (bc == 1) v = -X63[a * 3 + b];
-          else if (bc == 3) v = 0.5 * dt * sumA[a * 3 + b];
-          else if (bc == 4) v = -0.5 * CC[a * 3 + b] * dt;
+          if (bc == 3) v = -dt * C1[a3 * 3 + b3];
+        } else {
+          if (bc == 1) v = -X63[a3 * 3 + b3];
+          else if (bc == 3) v = 0.5 * dt * sumA[a3 * 3 + b3];
+          else if (bc == 4) v = -0.5 * CC[a3 * 3 + b3] * dt;
         }
-        wk.F[e] = v;
+        Nr[e] = v;
       }
       cx.sync();
-      for (int e = cx.lane(); e < 225; e += cx.lanes()) {  // T = F P
+      for (int e = cx.lane(); e < 135; e += cx.lanes()) {   // U = N P (columns 3..14 of N only)
         const int rr = e / 15, cc = e % 15;
         double sacc = 0;
-        for (int k = 0; k < 15; ++k) sacc += wk.F[rr * 15 + k] * wk.P[k * 15 + cc];
-        wk.T[e] = sacc;
+#pragma unroll
+        for (int k = 3; k < 15; ++k) sacc += Nr[rr * 15 + k] * Pc[k * 15 + cc];
+        U[e] = sacc;
       }
       cx.sync();
       const double s2_dalpha = dt * sigma_g_c * sigma_g_c;
@@ -200,17 +209,25 @@ OKB_HD int imu_integrate(const Ctx& cx, const okb_imu_sample* s, int n, const ok
       const double s2_p = 0.5 * dt * dt * s2_v;
       const double s2_bg = dt * prm.sigma_gw_c * prm.sigma_gw_c;
       const double s2_ba = dt * prm.sigma_aw_c * prm.sigma_aw_c;
-      for (int e = cx.lane(); e < 225; e += cx.lanes()) {  // P = T F^T + Q
+      for (int e = cx.lane(); e < 225; e += cx.lanes()) {
         const int rr = e / 15, cc = e % 15;
-        double sacc = 0;
-        for (int k = 0; k < 15; ++k) sacc += wk.T[rr * 15 + k] * wk.F[cc * 15 + k];
-        if (rr == cc) {
-          const int b = rr / 3;
-          sacc += (b == 0) ? s2_p : (b == 1) ? s2_dalpha : (b == 2) ? s2_v : (b == 3) ? s2_bg : s2_ba;
+        double v = Pc[e];
+        if (rr < 9) v += U[rr * 15 + cc];
+        if (cc < 9) v += U[cc * 15 + rr];
+        if (rr < 9 && cc < 9) {
+          double sacc = 0;
+#pragma unroll
+          for (int k = 3; k < 15; ++k) sacc += U[rr * 15 + k] * Nr[cc * 15 + k];
+          v += sacc;
         }
-        wk.P[e] = sacc;
+        if (rr == cc) {
+          const int bq = rr / 3;
+          v += (bq == 0) ? s2_p : (bq == 1) ? s2_dalpha : (bq == 2) ? s2_v : (bq == 3) ? s2_bg : s2_ba;
+        }
+        Pn[e] = v;
       }
       cx.sync();
+      double* tsw = Pc; Pc = Pn; Pn = tsw;
     }
     for (int k = 0; k < 4; ++k) st.Delta_q[k] = q1[k];
     for (int k = 0; k < 9; ++k) { st.C_integral[k] = Ci1[k]; st.cross[k] = cross1[k]; st.dv_db_g[k] = dv1[k]; }
@@ -218,6 +235,10 @@ OKB_HD int imu_integrate(const Ctx& cx, const okb_imu_sample* s, int n, const ok
     time = nexttime;
     ++i;
     if (nexttime == t1) break;
+  }
+  if (WANT_COV && Pc != wk.P) {   // leave the result in wk.P
+    for (int e = cx.lane(); e < 225; e += cx.lanes()) wk.P[e] = Pc[e];
+    cx.sync();
   }
   return i;
 }

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(32) k_imu(const WinDev* __restrict__ wins, int
   if (t >= W.n_imu) return;
   __shared__ double buf[kImuScratch];
   WarpCtx cx;
-  ImuWork wk{buf, buf + 225, buf + 450};
+  ImuWork wk{buf, buf + 225, buf + 450, buf + 675 + 450};   // P2 aliases the SF buffer (unused while preintegrating)
   double* F01 = buf + 675;
   double* SF = buf + 675 + 450;
   double* r15 = buf + 675 + 900;
@@ -470,12 +470,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     PHASE_MARK(2);
     // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh)
     int chol_fail = sh->fail;
-    if (!chol_fail) chol_fail = block_cholesky(Mx, d, s_panel, ld_p, &sh->chol_flag);
+    if (!chol_fail) chol_fail = block_cholesky(Mx, d, s_panel, ld_p, s_col, &sh->chol_flag);
     PHASE_MARK(3);
     if (!chol_fail) {
       for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = s_rhs[i];
       __syncthreads();
-      block_cholesky_solve(Mx, d, s_tmp);
+      block_cholesky_solve(Mx, d, s_col, s_tmp);
       for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
       __syncthreads();
     }
@@ -495,10 +495,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       const double v0 = g0 / E0, v1 = g1 / E1, v2 = g2 / E2;
       double q0 = 0, q1 = 0, q2 = 0;        // sum_f M_f (G_f u_f)
       double hv = 0;                        // sum_f v^T M_f (v - 2 G_f v_f)
-      uint32_t vis = W.lm_vis[l];
-      while (vis) {
-        const int f = __ffs(vis) - 1;
-        vis &= vis - 1;
+      // every frame: M blocks of unobserved (landmark, frame) pairs are zero in memory, so no branch is
+      // needed and the loads of several frames are in flight together
+#pragma unroll 5
+      for (int f = 0; f < K; ++f) {
         const double* Mo = W.lm_M + ((size_t)f * L + l) * 6;
         const double M0 = Mo[0], M1 = Mo[1], M2 = Mo[2], M3 = Mo[3], M4 = Mo[4], M5 = Mo[5];
         const double p0 = X.x - s_tws[4 * f] * X.w, p1 = X.y - s_tws[4 * f + 1] * X.w, p2 = X.z - s_tws[4 * f + 2] * X.w;

@@ -55,9 +55,8 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
   const int mode = st->mode, cur = st->cur;
   const bool cauchy = W.use_cauchy != 0;
   const int l = cx * L1_THREADS + tid;
-  double v[kPartH];
 #pragma unroll
-  for (int i = 0; i < kPartH; ++i) v[i] = 0.0;
+  for (int i = 0; i < 29; ++i) sred[i][tid] = 0.0;   // contributions go straight to shared memory (no live registers)
 
   if (l < L) {
     const bool vis = (W.lm_vis[l] >> f) & 1u;
@@ -79,17 +78,23 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
           X[c] += dlt;
           dn += dlt * dlt;
         }
-        if (f == 0) v[28] = dn;
+        if (f == 0) sred[28][tid] = dn;
       }
       if (f == 0) *reinterpret_cast<double4*>(W.lm_c + 4 * (size_t)l) = make_double4(X[0], X[1], X[2], X[3]);
       if (vis) {
         double M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0, m0 = 0, m1 = 0, m2 = 0, cost = 0;
+        // the first two cameras' observations are fetched up front so that their latency overlaps
+        double pw[2] = {0.0, 0.0};
+        double2 pz[2] = {make_double2(0, 0), make_double2(0, 0)};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          if (c < CP) { const size_t gi = (size_t)(f * CP + c) * L + l; pw[c] = W.obs_w[gi]; pz[c] = W.obs_z[gi]; }
         for (int c = 0; c < CP; ++c) {
           const SlotCtx& sc = slots[c];
           const size_t gi = (size_t)(f * CP + c) * L + l;
-          const double wobs = W.obs_w[gi];
+          const double wobs = (c < 2) ? pw[c & 1] : W.obs_w[gi];
           if (wobs > 0.0 && sc.valid) {
-            const double2 z = W.obs_z[gi];
+            const double2 z = (c < 2) ? pz[c & 1] : W.obs_z[gi];
             double r[2], A[6];
             reproj_slot<true>(sc.xf, sc.cam, X, z.x, z.y, wobs, r, A);
             const double sq = r[0] * r[0] + r[1] * r[1];
@@ -118,22 +123,20 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
         const double Q10 = M3 * p2 - M4 * p1, Q11 = -M1 * p2 + M4 * p0, Q12 = M1 * p1 - M3 * p0;
         const double Q20 = M4 * p2 - M5 * p1, Q21 = -M2 * p2 + M5 * p0, Q22 = M2 * p1 - M4 * p0;
         const double w2 = w * w;
-        v[0] = w2 * M0; v[1] = w2 * M1; v[2] = w2 * M2; v[3] = w2 * M3; v[4] = w2 * M4; v[5] = w2 * M5;
-        v[6] = -w * Q00; v[7] = -w * Q01; v[8] = -w * Q02;
-        v[9] = -w * Q10; v[10] = -w * Q11; v[11] = -w * Q12;
-        v[12] = -w * Q20; v[13] = -w * Q21; v[14] = -w * Q22;
-        v[15] = p2 * Q10 - p1 * Q20; v[16] = p2 * Q11 - p1 * Q21; v[17] = p2 * Q12 - p1 * Q22;
-        v[18] = -p2 * Q01 + p0 * Q21; v[19] = -p2 * Q02 + p0 * Q22;
-        v[20] = p1 * Q02 - p0 * Q12;
-        v[21] = w * m0; v[22] = w * m1; v[23] = w * m2;
-        v[24] = p1 * m2 - p2 * m1; v[25] = p2 * m0 - p0 * m2; v[26] = p0 * m1 - p1 * m0;
-        v[27] = cost;
+        sred[0][tid] = w2 * M0; sred[1][tid] = w2 * M1; sred[2][tid] = w2 * M2; sred[3][tid] = w2 * M3; sred[4][tid] = w2 * M4; sred[5][tid] = w2 * M5;
+        sred[6][tid] = -w * Q00; sred[7][tid] = -w * Q01; sred[8][tid] = -w * Q02;
+        sred[9][tid] = -w * Q10; sred[10][tid] = -w * Q11; sred[11][tid] = -w * Q12;
+        sred[12][tid] = -w * Q20; sred[13][tid] = -w * Q21; sred[14][tid] = -w * Q22;
+        sred[15][tid] = p2 * Q10 - p1 * Q20; sred[16][tid] = p2 * Q11 - p1 * Q21; sred[17][tid] = p2 * Q12 - p1 * Q22;
+        sred[18][tid] = -p2 * Q01 + p0 * Q21; sred[19][tid] = -p2 * Q02 + p0 * Q22;
+        sred[20][tid] = p1 * Q02 - p0 * Q12;
+        sred[21][tid] = w * m0; sred[22][tid] = w * m1; sred[23][tid] = w * m2;
+        sred[24][tid] = p1 * m2 - p2 * m1; sred[25][tid] = p2 * m0 - p0 * m2; sred[26][tid] = p0 * m1 - p1 * m0;
+        sred[27][tid] = cost;
       }
     }
   }
   // ---- CTA reduction of the 29 used values (fixed order -> deterministic)
-#pragma unroll
-  for (int i = 0; i < 29; ++i) sred[i][tid] = v[i];
   __syncthreads();
   for (int e = warp; e < 29; e += L1_THREADS / 32) {
     double s = sred[e][lane] + sred[e][lane + 32] + sred[e][lane + 64] + sred[e][lane + 96];
@@ -212,15 +215,25 @@ __global__ void __launch_bounds__(128) k_lmblock(const WinDev* __restrict__ wins
 // ------------------------------------------------------------------------------------------------
 // A2
 // ------------------------------------------------------------------------------------------------
+constexpr int kMStride = 7;   // doubles per (landmark, frame) M block in shared memory (6 + 1 pad: 2-way bank conflicts at most)
+constexpr int kLiStride = 10;  // L^-1 (6) | z (3) | pad
+
 __host__ __device__ inline size_t smemA2_bytes(int K, int dcp) {
   size_t b = 0;
-  b += (size_t)3 * A2_TILE * dcp * sizeof(double);          // Y tile, k-major
-  b += (size_t)K * A2_TILE * 6 * sizeof(double);            // M tile
-  b += (size_t)A2_TILE * 8 * sizeof(double);                // Linv (6) + pad
-  b += (size_t)A2_TILE * 4 * sizeof(double);                // X
-  b += (size_t)K * 4 * sizeof(double);                      // frame translations
+  b += (size_t)3 * A2_TILE * dcp * sizeof(double);                 // Y tile, k-major
+  b += (size_t)2 * K * A2_TILE * kMStride * sizeof(double);        // M tiles (double buffered)
+  b += (size_t)2 * A2_TILE * kLiStride * sizeof(double);           // L^-1 | z
+  b += (size_t)2 * A2_TILE * 4 * sizeof(double);                   // X
+  b += (size_t)K * 4 * sizeof(double);                             // frame translations
   return b;
 }
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int TPT>
 __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restrict__ wins, int win_first) {
@@ -234,10 +247,10 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Yt = reinterpret_cast<double*>(smem_raw);
-  double* sM = Yt + (size_t)3 * A2_TILE * dcp;
-  double* sLi = sM + (size_t)K * A2_TILE * 6;
-  double* sX = sLi + A2_TILE * 8;
-  double* tws = sX + A2_TILE * 4;
+  double* sMb = Yt + (size_t)3 * A2_TILE * dcp;
+  double* sLib = sMb + (size_t)2 * K * A2_TILE * kMStride;
+  double* sXb = sLib + 2 * A2_TILE * kLiStride;
+  double* tws = sXb + 2 * A2_TILE * 4;
 
   for (int f = tid; f < K; f += A2_THREADS) {
     tws[4 * f] = W.pose_c[7 * f]; tws[4 * f + 1] = W.pose_c[7 * f + 1]; tws[4 * f + 2] = W.pose_c[7 * f + 2];
@@ -268,47 +281,62 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
 
   const int lm_begin = chunk * W.lm_per_chunk;
   const int lm_end = min(L, lm_begin + W.lm_per_chunk);
-  __syncthreads();
 
-  for (int base = lm_begin; base < lm_end; base += A2_TILE) {
+  // asynchronous staging of one tile (cp.async, 8-byte elements, no registers held):
+  //   M  [f][l][6] (global, zero where unobserved) -> [ll][f][kMStride]
+  //   Li [l][9] -> [ll][kLiStride],  X = lm_c [l][4] -> [ll][4]
+  auto stage = [&](int base, int buf) {
+    double* sM = sMb + (size_t)buf * K * A2_TILE * kMStride;
+    double* sLi = sLib + buf * A2_TILE * kLiStride;
+    double* sX = sXb + buf * A2_TILE * 4;
     const int nl = min(A2_TILE, lm_end - base);
-    // ---- (a) stage the tile's M blocks: for every frame 32 landmarks x 6 doubles are contiguous
     for (int i = tid; i < K * A2_TILE * 6; i += A2_THREADS) {
       const int f = i / (A2_TILE * 6), r = i % (A2_TILE * 6);
-      const int ll = r / 6;
-      double val = 0.0;
-      if (ll < nl && ((W.lm_vis[base + ll] >> f) & 1u)) val = W.lm_M[((size_t)f * L + base) * 6 + r];
-      sM[i] = val;
+      const int ll = r / 6, e = r % 6;
+      if (ll < nl) cp_async8(sM + ((size_t)ll * K + f) * kMStride + e, W.lm_M + ((size_t)f * L + base) * 6 + r);
     }
-    __syncthreads();
-    // ---- (b) per-landmark data of the tile: L^-1, candidate X, augmented row z
+    for (int i = tid; i < A2_TILE * 9; i += A2_THREADS) {
+      const int ll = i / 9, e = i % 9;
+      if (ll < nl) cp_async8(sLi + ll * kLiStride + e, W.lm_Li + 9 * (size_t)base + i);
+    }
+    for (int i = tid; i < A2_TILE * 4; i += A2_THREADS) {
+      const int ll = i / 4;
+      if (ll < nl) cp_async8(sX + i, W.lm_c + 4 * (size_t)base + i);
+    }
+    cp_async_commit();
+  };
+
+  int buf = 0;
+  if (lm_begin < lm_end) stage(lm_begin, 0);
+  for (int base = lm_begin; base < lm_end; base += A2_TILE) {
+    const int nl = min(A2_TILE, lm_end - base);
+    const double* sM = sMb + (size_t)buf * K * A2_TILE * kMStride;
+    const double* sLi = sLib + buf * A2_TILE * kLiStride;
+    const double* sX = sXb + buf * A2_TILE * 4;
+    cp_async_wait_all();
+    __syncthreads();                       // tile `buf` is complete; the previous SYRK has finished
+    if (base + A2_TILE < lm_end) stage(base + A2_TILE, buf ^ 1);   // overlaps with this tile's math
+    // ---- augmented row z and the padding rows of the Y tile
     if (tid < A2_TILE) {
       const int ll = tid;
       double* yz = Yt + (size_t)(3 * ll) * dcp + dc;
-      if (ll < nl) {
-        const int l = base + ll;
-        const double* Lo = W.lm_Li + 9 * (size_t)l;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) sLi[ll * 8 + i] = Lo[i];
-        const double4 x4 = *reinterpret_cast<const double4*>(W.lm_c + 4 * (size_t)l);
-        sX[ll * 4] = x4.x; sX[ll * 4 + 1] = x4.y; sX[ll * 4 + 2] = x4.z; sX[ll * 4 + 3] = x4.w;
-        yz[0] = Lo[6]; yz[dcp] = Lo[7]; yz[2 * dcp] = Lo[8];
-      } else {
-        yz[0] = 0.0; yz[dcp] = 0.0; yz[2 * dcp] = 0.0;
-      }
+      if (ll < nl) { yz[0] = sLi[ll * kLiStride + 6]; yz[dcp] = sLi[ll * kLiStride + 7]; yz[2 * dcp] = sLi[ll * kLiStride + 8]; }
+      else { yz[0] = 0.0; yz[dcp] = 0.0; yz[2 * dcp] = 0.0; }
       for (int r = dc + 1; r < dcp; ++r) { Yt[(size_t)(3 * ll) * dcp + r] = 0.0; Yt[(size_t)(3 * ll + 1) * dcp + r] = 0.0; Yt[(size_t)(3 * ll + 2) * dcp + r] = 0.0; }
     }
-    __syncthreads();
-    // ---- (c) Y_f = W_f L^-T for every (landmark, frame) pair of the tile
+    // ---- Y_f = W_f L^-T for every (landmark, frame) pair of the tile
     for (int pidx = tid; pidx < A2_TILE * K; pidx += A2_THREADS) {
       const int ll = pidx / K, f = pidx % K;
       double* y0 = Yt + (size_t)(3 * ll) * dcp + 6 * f;
       double* y1 = y0 + dcp;
       double* y2 = y1 + dcp;
-      const double* sp = sM + ((size_t)f * A2_TILE + ll) * 6;
-      const double M0 = sp[0], M1 = sp[1], M2 = sp[2], M3 = sp[3], M4 = sp[4], M5 = sp[5];
-      if (ll < nl && (M0 != 0.0 || M3 != 0.0 || M5 != 0.0)) {
-        const double* Li = sLi + ll * 8;
+      double M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0;
+      if (ll < nl) {
+        const double* sp = sM + ((size_t)ll * K + f) * kMStride;
+        M0 = sp[0]; M1 = sp[1]; M2 = sp[2]; M3 = sp[3]; M4 = sp[4]; M5 = sp[5];
+      }
+      if (M0 != 0.0 || M3 != 0.0 || M5 != 0.0) {
+        const double* Li = sLi + ll * kLiStride;
         const double w = sX[ll * 4 + 3];
         const double p0 = sX[ll * 4] - tws[4 * f] * w, p1 = sX[ll * 4 + 1] - tws[4 * f + 1] * w, p2 = sX[ll * 4 + 2] - tws[4 * f + 2] * w;
         const double N00 = M0 * Li[0], N01 = M0 * Li[1] + M1 * Li[2], N02 = M0 * Li[3] + M1 * Li[4] + M2 * Li[5];
@@ -326,11 +354,12 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
       }
     }
     __syncthreads();
-    // ---- (d) SYRK over the tile
+    // ---- SYRK over the tile
 #pragma unroll
     for (int m = 0; m < TPT; ++m) {
       if (syrk_on[m]) {
         const int ncols = 3 * A2_TILE;
+#pragma unroll 2
         for (int k = ks; k < ncols; k += KS) {
           const double* row = Yt + (size_t)k * dcp;
           const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * ti[m]);
@@ -346,8 +375,9 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
         }
       }
     }
-    __syncthreads();
+    buf ^= 1;
   }
+  __syncthreads();
 
   // ---- epilogue: chunk partial of the Schur accumulator (deterministic k-split order)
   double* Sp = W.partA + (size_t)chunk * W.partA_stride;
