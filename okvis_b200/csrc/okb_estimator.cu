@@ -434,6 +434,7 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
     k_lmblock<<<dim3(max_cx, count), 128, 0, c->stream>>>(c->d_wins, first);
     if (tpt == 1) k_schur<1><<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first);
     else k_schur<2><<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first);
+    if (max_chunks > 1) { k_reduce_partials<<<dim3(8, count), 256, 0, c->stream>>>(c->d_wins, first); c->launches += 1; }
     prof_end(c);
     c->launches += 2;
     if (max_imu > 0) cudaStreamWaitEvent(c->stream, c->ev_imu, 0);
@@ -551,9 +552,9 @@ __global__ void k_hook_reproj(int n, okb_camera cam, const double* pose, const d
 // one warp
 __global__ void k_hook_imu(okb_imu_params prm, const okb_imu_sample* s, int n, int64_t t0, int64_t t1, const double* in /*32*/,
                            const double* sb_ref, int have_ref, ImuCache* cache, double* out /* r15 | SF 450 | sqrt 225 | redo */) {
-  __shared__ double buf[3 * 225 + 450 + 450 + 16];
+  __shared__ double buf[3 * 225 + 450 + 450 + 16 + 32 * kImuPre];
   WarpCtx cx;
-  ImuWork wk{buf, buf + 225, buf + 450, buf + 1125};
+  ImuWork wk{buf, buf + 225, buf + 450, buf + 1125, buf + 1591};
   double* F01 = buf + 675; double* SF = buf + 1125; double* r15 = buf + 1575;
   if (threadIdx.x == 0) { cache->valid = 0; cache->redo_count = 0; for (int k = 0; k < 9; ++k) cache->sb_ref[k] = 0; }
   __syncwarp();
@@ -568,9 +569,9 @@ __global__ void k_hook_imu(okb_imu_params prm, const okb_imu_sample* s, int n, i
 }
 __global__ void k_hook_propagate(okb_imu_params prm, const okb_imu_sample* s, int n, int64_t t0, int64_t t1, double* io /*16*/,
                                  double* cov, double* jac, int want_cov, int want_jac, int* n_used) {
-  __shared__ double buf[4 * 225];
+  __shared__ double buf[4 * 225 + 32 * kImuPre];
   WarpCtx cx;
-  ImuWork wk{buf, buf + 225, buf + 450, buf + 675};
+  ImuWork wk{buf, buf + 225, buf + 450, buf + 675, buf + 900};
   const int steps = imu_propagate(cx, s, n, prm, t0, t1, io, io + 7, want_cov ? cov : nullptr, want_jac ? jac : nullptr, wk);
   if (threadIdx.x == 0) *n_used = steps;
 }

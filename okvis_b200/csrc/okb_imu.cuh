@@ -51,12 +51,15 @@ OKB_HD double ns_to_sec(int64_t ns) {
   return (double)sec + 1e-9 * (double)nsec;
 }
 
+constexpr int kImuPre = 30;   // doubles per precomputed sample: valid, dt, sigma_g, sigma_a, ac(3), dq(4), Jr(9), R(dq^-1)(9), last
+
 // Workspace for the cooperative 15x15 products: 3 matrices of 225 doubles (shared memory on the device).
 struct ImuWork {
   double* P;    // covariance (result)
   double* F;    // scratch (rows of N; later general 15x15 scratch)
   double* T;    // scratch (U = N P; later general 15x15 scratch)
   double* P2;   // second covariance buffer for the ping-pong update
+  double* S;    // per-sample precompute buffer: 32 x kImuPre doubles
 };
 
 // Integrates the samples over [t0,t1].  PREINT selects the redoPreintegration variant
@@ -81,160 +84,184 @@ OKB_HD int imu_integrate(const Ctx& cx, const okb_imu_sample* s, int n, const ok
     for (int e = cx.lane(); e < 225; e += cx.lanes()) wk.P[e] = 0.0;
     cx.sync();
   }
-  int64_t time = t0;
-  bool hasStarted = false;
+  // The per-sample quantities that do not depend on the running state (interpolated rates, dt, the
+  // rotation increment dq with its sinc/cos, the right Jacobian, R(dq^-1), saturation flags) are computed
+  // for 32 samples at a time with one sample per lane; the sequential recursion below then only chains
+  // small matrix products.  Same formulas, same order of operations per sample as the reference loop.
   int i = 0;
-  for (int it = 0; it < n; ++it) {
-    const bool last = (it + 1 == n);
-    double w0[3], a0[3], w1[3], a1[3];
-    for (int k = 0; k < 3; ++k) {
-      w0[k] = s[it].gyro[k]; a0[k] = s[it].acc[k];
-      w1[k] = s[last ? it : it + 1].gyro[k]; a1[k] = s[last ? it : it + 1].acc[k];
+  bool finished = false;
+  for (int base = 0; base < n && !finished; base += 32) {
+    for (int j = cx.lane(); j < 32; j += cx.lanes()) {
+      const int it = base + j;
+      double* o = wk.S + j * kImuPre;
+      o[0] = 0.0;
+      if (it >= n) continue;
+      const bool last = (it + 1 == n);
+      double w0[3], a0[3], w1[3], a1[3];
+      for (int k = 0; k < 3; ++k) {
+        w0[k] = s[it].gyro[k]; a0[k] = s[it].acc[k];
+        w1[k] = s[last ? it : it + 1].gyro[k]; a1[k] = s[last ? it : it + 1].acc[k];
+      }
+      // `time` of the reference loop: t0 for the first integrated interval, the sample's own stamp afterwards
+      const int64_t start = (s[it].t_ns > t0) ? s[it].t_ns : t0;
+      int64_t nexttime = last ? t1 : s[it + 1].t_ns;
+      double dt = ns_to_sec(nexttime - start);
+      if (t1 < nexttime) {
+        const double interval = ns_to_sec(nexttime - s[it].t_ns);
+        nexttime = t1;
+        dt = ns_to_sec(nexttime - start);
+        const double r = dt / interval;
+        for (int k = 0; k < 3; ++k) { w1[k] = (1.0 - r) * w0[k] + r * w1[k]; a1[k] = (1.0 - r) * a0[k] + r * a1[k]; }
+      }
+      if (dt <= 0.0) continue;
+      if (s[it].t_ns <= t0) {   // first integrated interval (hasStarted == false in the reference)
+        const double r = dt / ns_to_sec(nexttime - s[it].t_ns);
+        for (int k = 0; k < 3; ++k) { w0[k] = r * w0[k] + (1.0 - r) * w1[k]; a0[k] = r * a0[k] + (1.0 - r) * a1[k]; }
+      }
+      double sigma_g_c = prm.sigma_g_c, sigma_a_c = prm.sigma_a_c;
+      bool gsat = false, asat = false;
+      for (int k = 0; k < 3; ++k) {
+        if (fabs(w0[k]) > prm.g_max || fabs(w1[k]) > prm.g_max) gsat = true;
+        if (fabs(a0[k]) > prm.a_max || fabs(a1[k]) > prm.a_max) asat = true;
+      }
+      if (gsat) sigma_g_c *= 100;
+      if (asat) sigma_a_c *= 100;
+      double om[3];
+      for (int k = 0; k < 3; ++k) { om[k] = 0.5 * (w0[k] + w1[k]) - sb[3 + k]; o[4 + k] = 0.5 * (a0[k] + a1[k]) - sb[6 + k]; }
+      const double th = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]) * 0.5 * dt;
+      const double sc = sinc(th) * 0.5 * dt;
+      const double dq[4] = {sc * om[0], sc * om[1], sc * om[2], cos(th)};
+      const double wdt[3] = {om[0] * dt, om[1] * dt, om[2] * dt};
+      double Jr[9], dqi[4], Rdqi[9];
+      rightJacobian(wdt, Jr);
+      qinv(dq, dqi);
+      q2R(dqi, Rdqi);
+      o[1] = dt; o[2] = sigma_g_c; o[3] = sigma_a_c;
+      for (int k = 0; k < 4; ++k) o[7 + k] = dq[k];
+      for (int k = 0; k < 9; ++k) { o[11 + k] = Jr[k]; o[20 + k] = Rdqi[k]; }
+      o[29] = (nexttime == t1) ? 1.0 : 0.0;
+      o[0] = 1.0;
     }
-    int64_t nexttime = last ? t1 : s[it + 1].t_ns;
-    double dt = ns_to_sec(nexttime - time);
-    if (t1 < nexttime) {
-      const double interval = ns_to_sec(nexttime - s[it].t_ns);
-      nexttime = t1;
-      dt = ns_to_sec(nexttime - time);
-      const double r = dt / interval;
-      for (int k = 0; k < 3; ++k) { w1[k] = (1.0 - r) * w0[k] + r * w1[k]; a1[k] = (1.0 - r) * a0[k] + r * a1[k]; }
-    }
-    if (dt <= 0.0) continue;
-    st.Delta_t += dt;
-    if (!hasStarted) {
-      hasStarted = true;
-      const double r = dt / ns_to_sec(nexttime - s[it].t_ns);
-      for (int k = 0; k < 3; ++k) { w0[k] = r * w0[k] + (1.0 - r) * w1[k]; a0[k] = r * a0[k] + (1.0 - r) * a1[k]; }
-    }
-    double sigma_g_c = prm.sigma_g_c, sigma_a_c = prm.sigma_a_c;
-    bool gsat = false, asat = false;
-    for (int k = 0; k < 3; ++k) {
-      if (fabs(w0[k]) > prm.g_max || fabs(w1[k]) > prm.g_max) gsat = true;
-      if (fabs(a0[k]) > prm.a_max || fabs(a1[k]) > prm.a_max) asat = true;
-    }
-    if (gsat) sigma_g_c *= 100;
-    if (asat) sigma_a_c *= 100;
-
-    double om[3], ac[3];
-    for (int k = 0; k < 3; ++k) { om[k] = 0.5 * (w0[k] + w1[k]) - sb[3 + k]; ac[k] = 0.5 * (a0[k] + a1[k]) - sb[6 + k]; }
-    const double th = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]) * 0.5 * dt;
-    const double sc = sinc(th) * 0.5 * dt;
-    const double dq[4] = {sc * om[0], sc * om[1], sc * om[2], cos(th)};
-    double q1[4];
-    qmul(st.Delta_q, dq, q1);
-    double C[9], C1[9], CC[9], CCa[3];
-    q2R(st.Delta_q, C);
-    q2R(q1, C1);
-    for (int k = 0; k < 9; ++k) CC[k] = C[k] + C1[k];
-    mat3vec(CC, ac, CCa);
-    double Ci1[9], ai1[3], add[3];
-    for (int k = 0; k < 9; ++k) Ci1[k] = st.C_integral[k] + 0.5 * CC[k] * dt;
-    for (int k = 0; k < 3; ++k) ai1[k] = st.acc_integral[k] + 0.5 * CCa[k] * dt;
-    double F012[9];
-    for (int k = 0; k < 9; ++k) {
-      F012[k] = -st.C_integral[k] * dt + 0.25 * CC[k] * dt * dt;
-      st.C_doubleintegral[k] += st.C_integral[k] * dt + 0.25 * CC[k] * dt * dt;
-    }
-    for (int k = 0; k < 3; ++k) {
-      add[k] = st.acc_integral[k] * dt + 0.25 * CCa[k] * dt * dt;
-      st.acc_doubleintegral[k] += add[k];
-    }
-    const double wdt[3] = {om[0] * dt, om[1] * dt, om[2] * dt};
-    double Jr[9];
-    rightJacobian(wdt, Jr);
-    if (PREINT) {
-      double CJ[9];
-      mat3mul(C1, Jr, CJ);
-      for (int k = 0; k < 9; ++k) st.dalpha_db_g[k] += CJ[k] * dt;
-    } else {
-      for (int k = 0; k < 9; ++k) st.dalpha_db_g[k] += dt * C1[k];
-    }
-    double dqi[4], Rdqi[9], cross1[9];
-    qinv(dq, dqi);
-    q2R(dqi, Rdqi);
-    mat3mul(Rdqi, st.cross, cross1);
-    for (int k = 0; k < 9; ++k) cross1[k] += Jr[k] * dt;
-    double ax[9], t1m[9], t2m[9], A1[9], A2[9], sumA[9];
-    crossMx(ac, ax);
-    mat3mul(C, ax, t1m); mat3mul(t1m, st.cross, A1);
-    mat3mul(C1, ax, t2m); mat3mul(t2m, cross1, A2);
-    for (int k = 0; k < 9; ++k) sumA[k] = A1[k] + A2[k];
-    double dv1[9], F09[9];
-    for (int k = 0; k < 9; ++k) {
-      dv1[k] = st.dv_db_g[k] + 0.5 * dt * sumA[k];
-      F09[k] = dt * st.dv_db_g[k] + 0.25 * dt * dt * sumA[k];
-      st.dp_db_g[k] += F09[k];
-    }
-    if (WANT_COV) {
-      // P <- F P F^T + Q with F = I + N, N nonzero only in rows 0..8:
-      //   N = {(0,3):-[add]x, (0,6): dt I, (0,9): F09, (0,12): F012, (3,9): -dt C1,
-      //        (6,3): -[0.5 CCa dt]x, (6,9): 0.5 dt sumA, (6,12): -0.5 CC dt}
-      // so P' = P + U + U^T + U N^T with U = N P (9 x 15): ~4x fewer multiply-adds than the dense products.
-      double X03[9], X63[9];
-      crossMx(add, X03);
-      const double v63[3] = {0.5 * CCa[0] * dt, 0.5 * CCa[1] * dt, 0.5 * CCa[2] * dt};
-      crossMx(v63, X63);
-      double* Nr = wk.F;          // rows 0..8 of N, dense [9][15]
-      double* U = wk.T;           // U = N P, [9][15]
-      for (int e = cx.lane(); e < 135; e += cx.lanes()) {
-        const int rr = e / 15, cc = e % 15;
-        const int br = rr / 3, bc = cc / 3, a3 = rr % 3, b3 = cc % 3;
-        double v = 0.0;
-        if (br == 0) {
-          if (bc == 1) v = -X03[a3 * 3 + b3];
-          else if (bc == 2) v = (a3 == b3) ? dt : 0.0;
-          else if (bc == 3) v = F09[a3 * 3 + b3];
-          else if (bc == 4) v = F012[a3 * 3 + b3];
-        } else if (br == 1) {
-          if (bc == 3) v = -dt * C1[a3 * 3 + b3];
-        } else {
-          if (bc == 1) v = -X63[a3 * 3 + b3];
-          else if (bc == 3) v = 0.5 * dt * sumA[a3 * 3 + b3];
-          else if (bc == 4) v = -0.5 * CC[a3 * 3 + b3] * dt;
+    cx.sync();
+    for (int j = 0; j < 32 && base + j < n; ++j) {
+      const double* o = wk.S + j * kImuPre;
+      if (o[0] == 0.0) continue;
+      const double dt = o[1], sigma_g_c = o[2], sigma_a_c = o[3];
+      const double ac[3] = {o[4], o[5], o[6]};
+      const double dq[4] = {o[7], o[8], o[9], o[10]};
+      const double* Jr = o + 11;
+      const double* Rdqi = o + 20;
+      st.Delta_t += dt;
+      double q1[4];
+      qmul(st.Delta_q, dq, q1);
+      double C[9], C1[9], CC[9], CCa[3];
+      q2R(st.Delta_q, C);
+      q2R(q1, C1);
+      for (int k = 0; k < 9; ++k) CC[k] = C[k] + C1[k];
+      mat3vec(CC, ac, CCa);
+      double Ci1[9], ai1[3], add[3];
+      for (int k = 0; k < 9; ++k) Ci1[k] = st.C_integral[k] + 0.5 * CC[k] * dt;
+      for (int k = 0; k < 3; ++k) ai1[k] = st.acc_integral[k] + 0.5 * CCa[k] * dt;
+      double F012[9];
+      for (int k = 0; k < 9; ++k) {
+        F012[k] = -st.C_integral[k] * dt + 0.25 * CC[k] * dt * dt;
+        st.C_doubleintegral[k] += st.C_integral[k] * dt + 0.25 * CC[k] * dt * dt;
+      }
+      for (int k = 0; k < 3; ++k) {
+        add[k] = st.acc_integral[k] * dt + 0.25 * CCa[k] * dt * dt;
+        st.acc_doubleintegral[k] += add[k];
+      }
+      if (PREINT) {
+        double CJ[9];
+        mat3mul(C1, Jr, CJ);
+        for (int k = 0; k < 9; ++k) st.dalpha_db_g[k] += CJ[k] * dt;
+      } else {
+        for (int k = 0; k < 9; ++k) st.dalpha_db_g[k] += dt * C1[k];
+      }
+      double cross1[9];
+      mat3mul(Rdqi, st.cross, cross1);
+      for (int k = 0; k < 9; ++k) cross1[k] += Jr[k] * dt;
+      double ax[9], t1m[9], t2m[9], A1[9], A2[9], sumA[9];
+      crossMx(ac, ax);
+      mat3mul(C, ax, t1m); mat3mul(t1m, st.cross, A1);
+      mat3mul(C1, ax, t2m); mat3mul(t2m, cross1, A2);
+      for (int k = 0; k < 9; ++k) sumA[k] = A1[k] + A2[k];
+      double dv1[9], F09[9];
+      for (int k = 0; k < 9; ++k) {
+        dv1[k] = st.dv_db_g[k] + 0.5 * dt * sumA[k];
+        F09[k] = dt * st.dv_db_g[k] + 0.25 * dt * dt * sumA[k];
+        st.dp_db_g[k] += F09[k];
+      }
+      if (WANT_COV) {
+        // P <- F P F^T + Q with F = I + N, N nonzero only in rows 0..8:
+        //   N = {(0,3):-[add]x, (0,6): dt I, (0,9): F09, (0,12): F012, (3,9): -dt C1,
+        //        (6,3): -[0.5 CCa dt]x, (6,9): 0.5 dt sumA, (6,12): -0.5 CC dt}
+        // so P' = P + U + U^T + U N^T with U = N P (9 x 15): ~4x fewer multiply-adds than the dense products.
+        double X03[9], X63[9];
+        crossMx(add, X03);
+        const double v63[3] = {0.5 * CCa[0] * dt, 0.5 * CCa[1] * dt, 0.5 * CCa[2] * dt};
+        crossMx(v63, X63);
+        double* Nr = wk.F;          // rows 0..8 of N, dense [9][15]
+        double* U = wk.T;           // U = N P, [9][15]
+        for (int e = cx.lane(); e < 135; e += cx.lanes()) {
+          const int rr = e / 15, cc = e % 15;
+          const int br = rr / 3, bc = cc / 3, a3 = rr % 3, b3 = cc % 3;
+          double v = 0.0;
+          if (br == 0) {
+            if (bc == 1) v = -X03[a3 * 3 + b3];
+            else if (bc == 2) v = (a3 == b3) ? dt : 0.0;
+            else if (bc == 3) v = F09[a3 * 3 + b3];
+            else if (bc == 4) v = F012[a3 * 3 + b3];
+          } else if (br == 1) {
+            if (bc == 3) v = -dt * C1[a3 * 3 + b3];
+          } else {
+            if (bc == 1) v = -X63[a3 * 3 + b3];
+            else if (bc == 3) v = 0.5 * dt * sumA[a3 * 3 + b3];
+            else if (bc == 4) v = -0.5 * CC[a3 * 3 + b3] * dt;
+          }
+          Nr[e] = v;
         }
-        Nr[e] = v;
-      }
-      cx.sync();
-      for (int e = cx.lane(); e < 135; e += cx.lanes()) {   // U = N P (columns 3..14 of N only)
-        const int rr = e / 15, cc = e % 15;
-        double sacc = 0;
-#pragma unroll
-        for (int k = 3; k < 15; ++k) sacc += Nr[rr * 15 + k] * Pc[k * 15 + cc];
-        U[e] = sacc;
-      }
-      cx.sync();
-      const double s2_dalpha = dt * sigma_g_c * sigma_g_c;
-      const double s2_v = PREINT ? dt * sigma_a_c * sigma_a_c : dt * sigma_a_c * prm.sigma_a_c;
-      const double s2_p = 0.5 * dt * dt * s2_v;
-      const double s2_bg = dt * prm.sigma_gw_c * prm.sigma_gw_c;
-      const double s2_ba = dt * prm.sigma_aw_c * prm.sigma_aw_c;
-      for (int e = cx.lane(); e < 225; e += cx.lanes()) {
-        const int rr = e / 15, cc = e % 15;
-        double v = Pc[e];
-        if (rr < 9) v += U[rr * 15 + cc];
-        if (cc < 9) v += U[cc * 15 + rr];
-        if (rr < 9 && cc < 9) {
+        cx.sync();
+        for (int e = cx.lane(); e < 135; e += cx.lanes()) {   // U = N P (columns 3..14 of N only)
+          const int rr = e / 15, cc = e % 15;
           double sacc = 0;
 #pragma unroll
-          for (int k = 3; k < 15; ++k) sacc += U[rr * 15 + k] * Nr[cc * 15 + k];
-          v += sacc;
+          for (int k = 3; k < 15; ++k) sacc += Nr[rr * 15 + k] * Pc[k * 15 + cc];
+          U[e] = sacc;
         }
-        if (rr == cc) {
-          const int bq = rr / 3;
-          v += (bq == 0) ? s2_p : (bq == 1) ? s2_dalpha : (bq == 2) ? s2_v : (bq == 3) ? s2_bg : s2_ba;
+        cx.sync();
+        const double s2_dalpha = dt * sigma_g_c * sigma_g_c;
+        const double s2_v = PREINT ? dt * sigma_a_c * sigma_a_c : dt * sigma_a_c * prm.sigma_a_c;
+        const double s2_p = 0.5 * dt * dt * s2_v;
+        const double s2_bg = dt * prm.sigma_gw_c * prm.sigma_gw_c;
+        const double s2_ba = dt * prm.sigma_aw_c * prm.sigma_aw_c;
+        for (int e = cx.lane(); e < 225; e += cx.lanes()) {
+          const int rr = e / 15, cc = e % 15;
+          double v = Pc[e];
+          if (rr < 9) v += U[rr * 15 + cc];
+          if (cc < 9) v += U[cc * 15 + rr];
+          if (rr < 9 && cc < 9) {
+            double sacc = 0;
+#pragma unroll
+            for (int k = 3; k < 15; ++k) sacc += U[rr * 15 + k] * Nr[cc * 15 + k];
+            v += sacc;
+          }
+          if (rr == cc) {
+            const int bq = rr / 3;
+            v += (bq == 0) ? s2_p : (bq == 1) ? s2_dalpha : (bq == 2) ? s2_v : (bq == 3) ? s2_bg : s2_ba;
+          }
+          Pn[e] = v;
         }
-        Pn[e] = v;
+        cx.sync();
+        double* tsw = Pc; Pc = Pn; Pn = tsw;
       }
-      cx.sync();
-      double* tsw = Pc; Pc = Pn; Pn = tsw;
+      for (int k = 0; k < 4; ++k) st.Delta_q[k] = q1[k];
+      for (int k = 0; k < 9; ++k) { st.C_integral[k] = Ci1[k]; st.cross[k] = cross1[k]; st.dv_db_g[k] = dv1[k]; }
+      for (int k = 0; k < 3; ++k) st.acc_integral[k] = ai1[k];
+      ++i;
+      if (o[29] != 0.0) { finished = true; break; }
     }
-    for (int k = 0; k < 4; ++k) st.Delta_q[k] = q1[k];
-    for (int k = 0; k < 9; ++k) { st.C_integral[k] = Ci1[k]; st.cross[k] = cross1[k]; st.dv_db_g[k] = dv1[k]; }
-    for (int k = 0; k < 3; ++k) st.acc_integral[k] = ai1[k];
-    time = nexttime;
-    ++i;
-    if (nexttime == t1) break;
+    cx.sync();   // the per-sample buffer is rewritten by the next batch
   }
   if (WANT_COV && Pc != wk.P) {   // leave the result in wk.P
     for (int e = cx.lane(); e < 225; e += cx.lanes()) wk.P[e] = Pc[e];

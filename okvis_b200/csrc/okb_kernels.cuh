@@ -16,7 +16,7 @@ namespace okb {
 
 constexpr int S_THREADS = 512;
 constexpr int S_WARPS = S_THREADS / 32;
-constexpr int kImuScratch = 3 * 225 + 450 + 450 + 16;   // doubles of shared scratch per IMU warp
+constexpr int kImuScratch = 3 * 225 + 450 + 450 + 16 + 32 * kImuPre;   // doubles of shared scratch per IMU warp
 constexpr int kImuOut = 932;     // doubles per IMU term produced by k_imu: H30 | g30 | cost | pad
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(32) k_imu(const WinDev* __restrict__ wins, int
   if (t >= W.n_imu) return;
   __shared__ double buf[kImuScratch];
   WarpCtx cx;
-  ImuWork wk{buf, buf + 225, buf + 450, buf + 675 + 450};   // P2 aliases the SF buffer (unused while preintegrating)
+  ImuWork wk{buf, buf + 225, buf + 450, buf + 675 + 450, buf + 675 + 900 + 16};   // P2 aliases the SF buffer (unused while preintegrating)
   double* F01 = buf + 675;
   double* SF = buf + 675 + 450;
   double* r15 = buf + 675 + 900;
@@ -451,18 +451,14 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       if (r0 == c0) v += mu * s_E[r0];
       if (r0 < dc && c0 < dc) {
         const int rr = r0 >= c0 ? r0 : c0, cc = r0 >= c0 ? c0 : r0;
-        double s = 0;
-        for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + (size_t)rr * dcp + cc];
-        v -= s;
+        v -= W.partA[(size_t)rr * dcp + cc];     // chunk partials were summed by k_reduce_partials
       }
       Mx[i] = v;
     }
     for (int i = tid; i < d; i += S_THREADS) {
       double v = s_g[i];
       if (i < dc) {
-        double s = 0;
-        for (int c = 0; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + (size_t)dc * dcp + i];
-        v -= s;
+        v -= W.partA[(size_t)dc * dcp + i];
       }
       s_rhs[i] = v;
     }

@@ -398,6 +398,19 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   }
 }
 
+// Sums the per-chunk Schur accumulators of a window into chunk 0 (fixed order => deterministic), in
+// parallel over the matrix elements, so that k_solve reads one partial regardless of the chunk count.
+__global__ void __launch_bounds__(256) k_reduce_partials(const WinDev* __restrict__ wins, int win_first) {
+  const WinDev& W = wins[win_first + blockIdx.y];
+  if (W.st->done || W.n_chunks <= 1) return;
+  const int n = W.dcp * W.dcp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double s = W.partA[i];
+    for (int c = 1; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + i];
+    W.partA[i] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Post-solve landmark quality: H = sum J_lm^T J_lm (sqrt-information weighted, no robust weight)
 // at the final estimate; quality = sqrt(lambda_min)/sqrt(lambda_max), 0 if lambda_min < 1e-12.

@@ -23,8 +23,8 @@ int hc_imu_eval(const okb_imu_params* prm, const okb_imu_sample* s, int n, int64
   SeqCtx cx;
   static ImuCache cache;
   std::memset(&cache, 0, sizeof cache);
-  double P[225], F[225], T[225], P2[225], F01[450], SF[450], e[15];
-  ImuWork wk{P, F, T, P2};
+  double P[225], F[225], T[225], P2[225], Sb[32 * kImuPre], F01[450], SF[450], e[15];
+  ImuWork wk{P, F, T, P2, Sb};
   if (sb_ref) imu_preintegrate(cx, s, n, *prm, t0, t1, sb_ref, &cache, wk);
   const int before = cache.redo_count;
   imu_evaluate(cx, s, n, *prm, t0, t1, pose0, sb0, pose1, sb1, &cache, wk, F01, e, r, SF);
@@ -38,8 +38,8 @@ int hc_imu_eval(const okb_imu_params* prm, const okb_imu_sample* s, int n, int64
 int hc_imu_propagate(const okb_imu_params* prm, const okb_imu_sample* s, int n, int64_t t0, int64_t t1, double* pose,
                      double* sb, double* cov, double* jac) {
   SeqCtx cx;
-  double P[225], F[225], T[225], P2[225];
-  ImuWork wk{P, F, T, P2};
+  double P[225], F[225], T[225], P2[225], Sb[32 * kImuPre];
+  ImuWork wk{P, F, T, P2, Sb};
   return imu_propagate(cx, s, n, *prm, t0, t1, pose, sb, cov, jac, wk);
 }
 }

@@ -135,3 +135,10 @@ def test_unsupported_inputs_fail_loudly(ctx, okb):
     with pytest.raises(okb.OkbError) as e:
         ctx.upload(0, w)
     assert e.value.code == -3
+
+
+def test_four_camera_twenty_frame_window(ctx, oracle):
+    """cfg-5 shape (20 keyframes, 4 cameras; fewer landmarks): exercises 3 slot groups, the two-tile
+    SYRK mapping and the global-memory Cholesky (d = 300)."""
+    cfg = dataclasses.replace(synthetic.CONFIGS[5], n_landmarks=600)
+    compare(ctx, oracle, synthetic.make_window(5, 0, cfg=cfg), max_iterations=6)

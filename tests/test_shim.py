@@ -37,7 +37,9 @@ def test_shim_estimator_cycle_converges():
     assert out.returncode == 0, out.stderr
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["frames"] == 5 and r["landmarks"] > 50
-    assert r["final_cost"] < 1e-3 * r["initial_cost"] or r["final_cost"] < 1e-6
+    # exact measurements: what remains is the first-frame speed prior (v = 0, sigma = 1) against the true
+    # 0.5 m/s: 0.5 * 0.5^2 = 0.125
+    assert r["final_cost"] < 0.2, r
     assert r["pos_err"] < 2e-3            # exact measurements: the estimate returns to the true trajectory
     assert abs(r["vy"] - 0.5) < 2e-2      # velocity recovered although the first-frame prior says 0
     assert 0.0 < r["lm_quality"] <= 1.0
