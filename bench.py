@@ -174,39 +174,49 @@ def run_b200(args):
     launches = ctx.kernel_launches - launches0
     clocks = sampler.result() if rank == 0 else None
 
-    # ---- e2e through the C-ABI with host buffers (upload + optimize + download every step)
-    Be = min(B, args.e2e_batch)
-    e2e_steps = max(1, args.steps // 2)
-    h2d = d2h = 0
+    # ---- e2e through the C-ABI with HOST buffers: every step uploads its windows (host -> device), optimizes
+    # and downloads the estimates (device -> host).  Two window ranges are used alternately so that the host
+    # packing / copies of step i+1 overlap the device work of step i (what a streaming caller does); uploads
+    # and downloads of different windows run on a few host threads (the C calls release the GIL).
+    from concurrent.futures import ThreadPoolExecutor
+    Be = min(B // 2, args.e2e_batch)
+    e2e_steps = max(2, args.steps)
+    pool = ThreadPoolExecutor(max_workers=args.host_threads)
 
-    def e2e_step():
-        nonlocal h2d, d2h
+    def upload_range(base):
+        def up(i):
+            ctx.upload(base + i, windows[i % len(windows)])
+            return ctx.h2d_bytes(base + i)
+        return sum(pool.map(up, range(Be)))
+
+    def download_range(base):
+        def down(i):
+            out = ctx.download(base + i)
+            return sum(v.nbytes for v in out.values())
+        return sum(pool.map(down, range(Be))) + Be * 48
+
+    def e2e_run(n_steps):
+        it = 0
         h2d = d2h = 0
-        for i in range(Be):
-            w = windows[i % len(windows)]
-            ctx.upload(i, w)
-            h2d += ctx.h2d_bytes(i)
-        ss = ctx.optimize(0, Be, max_iterations=ITERS)
-        for i in range(Be):
-            out = ctx.download(i)
-            d2h += sum(v.nbytes for v in out.values())
-        d2h += Be * 48
-        return sum(s["iterations"] for s in ss)
+        h2d += upload_range(0)
+        for st in range(n_steps):
+            base = (st % 2) * Be
+            ctx.optimize_async(base, Be, max_iterations=ITERS)
+            if st + 1 < n_steps:
+                h2d += upload_range(((st + 1) % 2) * Be)       # overlaps the optimize of this step
+            ss = ctx.optimize_finish(base, Be)
+            d2h += download_range(base)
+            it += sum(x["iterations"] for x in ss)
+        return it, h2d / n_steps, d2h / n_steps
 
-    e2e_step()
+    e2e_run(2)
     barrier()
-    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_iters = 0
     t_host = time.perf_counter()
-    with torch.cuda.stream(stream):
-        ee0.record(stream)
-        for _ in range(e2e_steps):
-            e_iters += e2e_step()
-        ee1.record(stream)
+    e_iters, h2d, d2h = e2e_run(e2e_steps)
     torch.cuda.synchronize(dev)
     e2e_wall = time.perf_counter() - t_host     # host packing is part of the end-to-end path
+    pool.shutdown()
     barrier()
-    # restore the resident batch for any later use
     (elapsed_ms, e2e_ms), (iters_all, e_iters_all, launches_all) = sharding.reduce_measurement(
         dist, dev, [elapsed_ms, e2e_wall * 1e3], [iters, e_iters, launches])
     launches_all = int(launches_all)
@@ -234,7 +244,7 @@ def run_b200(args):
             p.close()
             return s["iterations"]
 
-        n_cpu = cores
+        n_cpu = 1 if args.skip_cpu else cores
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=cores) as ex:
             cpu_iters = sum(ex.map(solve_one, range(n_cpu)))
@@ -248,7 +258,8 @@ def run_b200(args):
                        "parallelism": "independent windows, %d per GPU, no collective" % B,
                        "l2": "inputs larger than L2 (%.0f MB resident per GPU)" % (B * 3.0)},
             "e2e": {"value": e_iters_all / (e2e_ms * 1e-3), "unit": "iterations/s", "h2d_bytes_per_step": int(h2d) * world,
-                    "d2h_bytes_per_step": int(d2h) * world, "windows_per_gpu": Be, "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(d2h) * world, "windows_per_gpu": Be, "steps": e2e_steps,
+                    "note": "upload+optimize+download per step; step i+1 uploads overlap step i compute; %d host threads" % args.host_threads},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_landmarks (residuals + Jacobian factors + J^T J + Schur SYRK)",
@@ -274,6 +285,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=592, help="resident windows per GPU (4 per SM)")
     ap.add_argument("--e2e-batch", type=int, default=148)
+    ap.add_argument("--skip-cpu", action="store_true", help="tuning runs only: shrink the cpu_baseline sample to one window")
+    ap.add_argument("--host-threads", type=int, default=8, help="host threads packing/uploading windows in the e2e leg")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic windows per rank (replicated to fill the batch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

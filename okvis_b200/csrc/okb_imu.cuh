@@ -62,6 +62,31 @@ struct ImuWork {
   double* S;    // per-sample precompute buffer: 32 x kImuPre doubles
 };
 
+// y = F x for the 15-vector x with F = I + N (N as listed in imu_integrate): rows 0..8 only.
+OKB_HD void imu_apply_F(const double* x, double* y, double dt, const double* X03, const double* F09,
+                               const double* F012, const double* C1, const double* X63, const double* sumA,
+                               const double* CC) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    double r0 = x[a] + dt * x[6 + a], r1 = 0.0, r2 = x[6 + a], r2b = 0.0, r2c = 0.0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      r0 -= X03[a * 3 + b] * x[3 + b];
+      r0 += F09[a * 3 + b] * x[9 + b];
+      r0 += F012[a * 3 + b] * x[12 + b];
+      r1 += C1[a * 3 + b] * x[9 + b];
+      r2 -= X63[a * 3 + b] * x[3 + b];
+      r2b += sumA[a * 3 + b] * x[9 + b];
+      r2c += CC[a * 3 + b] * x[12 + b];
+    }
+    y[a] = r0;
+    y[3 + a] = x[3 + a] - dt * r1;
+    y[6 + a] = r2 + 0.5 * dt * (r2b - r2c);
+  }
+#pragma unroll
+  for (int k = 9; k < 15; ++k) y[k] = x[k];
+}
+
 // Integrates the samples over [t0,t1].  PREINT selects the redoPreintegration variant
 // (dalpha_db_g uses the right Jacobian; sigma2_v = dt*sigma_a_c^2), otherwise the propagation variant.
 // Returns the number of steps (-1 if the samples do not reach t1).  With WANT_COV the covariance is
@@ -77,9 +102,7 @@ OKB_HD int imu_integrate(const Ctx& cx, const okb_imu_sample* s, int n, const ok
   }
   for (int k = 0; k < 3; ++k) st.acc_integral[k] = st.acc_doubleintegral[k] = 0;
   st.Delta_t = 0;
-  // covariance ping-pong buffers: Pc (current) / Pn (next); wk.F holds N's rows, wk.T holds U = N P
-  double* Pc = wk.P;
-  double* Pn = wk.P2;
+  double* Pc = wk.P;   // covariance, updated in place (wk.T holds the intermediate F P)
   if (WANT_COV) {
     for (int e = cx.lane(); e < 225; e += cx.lanes()) wk.P[e] = 0.0;
     cx.sync();
@@ -196,64 +219,38 @@ OKB_HD int imu_integrate(const Ctx& cx, const okb_imu_sample* s, int n, const ok
         // P <- F P F^T + Q with F = I + N, N nonzero only in rows 0..8:
         //   N = {(0,3):-[add]x, (0,6): dt I, (0,9): F09, (0,12): F012, (3,9): -dt C1,
         //        (6,3): -[0.5 CCa dt]x, (6,9): 0.5 dt sumA, (6,12): -0.5 CC dt}
-        // so P' = P + U + U^T + U N^T with U = N P (9 x 15): ~4x fewer multiply-adds than the dense products.
+        // One lane per column: T(:,c) = F P(:,c), then one lane per row: P'(l,:) = F T(l,:)^T.  The blocks of
+        // N stay in registers (constant indexing), each lane does 2 x 66 multiply-adds per sample.
         double X03[9], X63[9];
         crossMx(add, X03);
         const double v63[3] = {0.5 * CCa[0] * dt, 0.5 * CCa[1] * dt, 0.5 * CCa[2] * dt};
         crossMx(v63, X63);
-        double* Nr = wk.F;          // rows 0..8 of N, dense [9][15]
-        double* U = wk.T;           // U = N P, [9][15]
-        for (int e = cx.lane(); e < 135; e += cx.lanes()) {
-          const int rr = e / 15, cc = e % 15;
-          const int br = rr / 3, bc = cc / 3, a3 = rr % 3, b3 = cc % 3;
-          double v = 0.0;
-          if (br == 0) {
-            if (bc == 1) v = -X03[a3 * 3 + b3];
-            else if (bc == 2) v = (a3 == b3) ? dt : 0.0;
-            else if (bc == 3) v = F09[a3 * 3 + b3];
-            else if (bc == 4) v = F012[a3 * 3 + b3];
-          } else if (br == 1) {
-            if (bc == 3) v = -dt * C1[a3 * 3 + b3];
-          } else {
-            if (bc == 1) v = -X63[a3 * 3 + b3];
-            else if (bc == 3) v = 0.5 * dt * sumA[a3 * 3 + b3];
-            else if (bc == 4) v = -0.5 * CC[a3 * 3 + b3] * dt;
-          }
-          Nr[e] = v;
-        }
-        cx.sync();
-        for (int e = cx.lane(); e < 135; e += cx.lanes()) {   // U = N P (columns 3..14 of N only)
-          const int rr = e / 15, cc = e % 15;
-          double sacc = 0;
-#pragma unroll
-          for (int k = 3; k < 15; ++k) sacc += Nr[rr * 15 + k] * Pc[k * 15 + cc];
-          U[e] = sacc;
-        }
-        cx.sync();
         const double s2_dalpha = dt * sigma_g_c * sigma_g_c;
         const double s2_v = PREINT ? dt * sigma_a_c * sigma_a_c : dt * sigma_a_c * prm.sigma_a_c;
         const double s2_p = 0.5 * dt * dt * s2_v;
         const double s2_bg = dt * prm.sigma_gw_c * prm.sigma_gw_c;
         const double s2_ba = dt * prm.sigma_aw_c * prm.sigma_aw_c;
-        for (int e = cx.lane(); e < 225; e += cx.lanes()) {
-          const int rr = e / 15, cc = e % 15;
-          double v = Pc[e];
-          if (rr < 9) v += U[rr * 15 + cc];
-          if (cc < 9) v += U[cc * 15 + rr];
-          if (rr < 9 && cc < 9) {
-            double sacc = 0;
+        double* Tm = wk.T;
+        for (int c = cx.lane(); c < 15; c += cx.lanes()) {
+          double x[15], y[15];
 #pragma unroll
-            for (int k = 3; k < 15; ++k) sacc += U[rr * 15 + k] * Nr[cc * 15 + k];
-            v += sacc;
-          }
-          if (rr == cc) {
-            const int bq = rr / 3;
-            v += (bq == 0) ? s2_p : (bq == 1) ? s2_dalpha : (bq == 2) ? s2_v : (bq == 3) ? s2_bg : s2_ba;
-          }
-          Pn[e] = v;
+          for (int k = 0; k < 15; ++k) x[k] = Pc[k * 15 + c];
+          imu_apply_F(x, y, dt, X03, F09, F012, C1, X63, sumA, CC);
+#pragma unroll
+          for (int k = 0; k < 15; ++k) Tm[k * 15 + c] = y[k];
         }
         cx.sync();
-        double* tsw = Pc; Pc = Pn; Pn = tsw;
+        for (int l = cx.lane(); l < 15; l += cx.lanes()) {
+          double x[15], y[15];
+#pragma unroll
+          for (int k = 0; k < 15; ++k) x[k] = Tm[l * 15 + k];
+          imu_apply_F(x, y, dt, X03, F09, F012, C1, X63, sumA, CC);
+          const int bq = l / 3;
+          const double qd = (bq == 0) ? s2_p : (bq == 1) ? s2_dalpha : (bq == 2) ? s2_v : (bq == 3) ? s2_bg : s2_ba;
+#pragma unroll
+          for (int k = 0; k < 15; ++k) Pc[l * 15 + k] = y[k] + ((k == l) ? qd : 0.0);
+        }
+        cx.sync();
       }
       for (int k = 0; k < 4; ++k) st.Delta_q[k] = q1[k];
       for (int k = 0; k < 9; ++k) { st.C_integral[k] = Ci1[k]; st.cross[k] = cross1[k]; st.dv_db_g[k] = dv1[k]; }
@@ -262,10 +259,6 @@ OKB_HD int imu_integrate(const Ctx& cx, const okb_imu_sample* s, int n, const ok
       if (o[29] != 0.0) { finished = true; break; }
     }
     cx.sync();   // the per-sample buffer is rewritten by the next batch
-  }
-  if (WANT_COV && Pc != wk.P) {   // leave the result in wk.P
-    for (int e = cx.lane(); e < 225; e += cx.lanes()) wk.P[e] = Pc[e];
-    cx.sync();
   }
   return i;
 }
