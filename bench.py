@@ -178,35 +178,43 @@ def run_b200(args):
     # and downloads the estimates (device -> host).  Two window ranges are used alternately so that the host
     # packing / copies of step i+1 overlap the device work of step i (what a streaming caller does); uploads
     # and downloads of different windows run on a few host threads (the C calls release the GIL).
-    from concurrent.futures import ThreadPoolExecutor
     Be = min(B // 2, args.e2e_batch)
     e2e_steps = max(2, args.steps)
-    pool = ThreadPoolExecutor(max_workers=args.host_threads)
+    range_windows = [windows[i % len(windows)] for i in range(Be)]
+    descs = ctx.make_descs(range_windows)              # descriptors only point at the host arrays
+    for base in (0, Be):
+        ctx.upload_batch(base, range_windows, args.host_threads, descs)
+    host_out = {base: ctx.alloc_outputs(base, Be) for base in (0, Be)}   # host result buffers, reused every step
+
+    h2d_range = sum(ctx.h2d_bytes(i) for i in range(Be))                # counted by the library per upload
+    d2h_range = sum(v.nbytes for o in host_out[0][0] for v in o.values()) + Be * 48   # estimates + summaries
 
     def upload_range(base):
-        def up(i):
-            ctx.upload(base + i, windows[i % len(windows)])
-            return ctx.h2d_bytes(base + i)
-        return sum(pool.map(up, range(Be)))
+        ctx.upload_batch(base, range_windows, args.host_threads, descs)
+        return h2d_range
 
     def download_range(base):
-        def down(i):
-            out = ctx.download(base + i)
-            return sum(v.nbytes for v in out.values())
-        return sum(pool.map(down, range(Be))) + Be * 48
+        ctx.download_batch(base, Be, host_out[base])
+        return d2h_range
 
     def e2e_run(n_steps):
+        # software pipeline over two window ranges: while the device optimizes range `cur`, the host downloads
+        # the estimates of the previous step and uploads the next step's windows (transfer stream)
         it = 0
         h2d = d2h = 0
         h2d += upload_range(0)
+        pending = None
         for st in range(n_steps):
             base = (st % 2) * Be
             ctx.optimize_async(base, Be, max_iterations=ITERS)
+            if pending is not None:
+                d2h += download_range(pending)
             if st + 1 < n_steps:
-                h2d += upload_range(((st + 1) % 2) * Be)       # overlaps the optimize of this step
+                h2d += upload_range(((st + 1) % 2) * Be)
             ss = ctx.optimize_finish(base, Be)
-            d2h += download_range(base)
             it += sum(x["iterations"] for x in ss)
+            pending = base
+        d2h += download_range(pending)
         return it, h2d / n_steps, d2h / n_steps
 
     e2e_run(2)
@@ -215,7 +223,6 @@ def run_b200(args):
     e_iters, h2d, d2h = e2e_run(e2e_steps)
     torch.cuda.synchronize(dev)
     e2e_wall = time.perf_counter() - t_host     # host packing is part of the end-to-end path
-    pool.shutdown()
     barrier()
     (elapsed_ms, e2e_ms), (iters_all, e_iters_all, launches_all) = sharding.reduce_measurement(
         dist, dev, [elapsed_ms, e2e_wall * 1e3], [iters, e_iters, launches])
@@ -284,7 +291,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=592, help="resident windows per GPU (4 per SM)")
-    ap.add_argument("--e2e-batch", type=int, default=148)
+    ap.add_argument("--e2e-batch", type=int, default=296)
     ap.add_argument("--skip-cpu", action="store_true", help="tuning runs only: shrink the cpu_baseline sample to one window")
     ap.add_argument("--host-threads", type=int, default=8, help="host threads packing/uploading windows in the e2e leg")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic windows per rank (replicated to fill the batch)")

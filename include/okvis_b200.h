@@ -198,6 +198,12 @@ void* okb_stream(const okb_ctx* ctx);
 
 /* Packs and uploads one window into slot `win` (0 <= win < max_windows). */
 int okb_window_upload(okb_ctx* ctx, int win, const okb_window_desc* desc);
+/* Uploads `count` windows into slots [win_first, win_first+count); descs[i] describes slot win_first+i.
+ * The packing of different slots is spread over up to `host_threads` host threads (<= 0: library default).
+ * Uploads run on the context's transfer stream: they overlap solver work already launched on OTHER
+ * slots, and every later okb_optimize* / okb_window_reset is ordered after them.  Uploads of different slots
+ * may also be issued concurrently from several caller threads. */
+int okb_window_upload_batch(okb_ctx* ctx, int win_first, int count, const okb_window_desc* descs, int host_threads);
 /* Bytes the last okb_window_upload of this slot copied host -> device (0 if the slot is empty). */
 int64_t okb_window_h2d_bytes(const okb_ctx* ctx, int win);
 /* Restores the uploaded initial state of the slot on the device (no host traffic); used to
@@ -215,6 +221,11 @@ int okb_optimize_finish(okb_ctx* ctx, int win_first, int win_count, okb_summary*
  * of the landmark's 3x3 Hessian block as in Estimator.cpp:880-894 (0 if lambda_min < 1e-12). */
 int okb_window_download(okb_ctx* ctx, int win, double* poses, double* speed_bias,
                         double* landmarks, double* quality);
+/* Downloads the estimates of `count` slots with one synchronisation.  Each argument is an array of `count`
+ * host pointers (or NULL to skip that quantity; individual entries may be NULL too).  Like the uploads this
+ * runs on the transfer stream: it waits only for solver work launched on these slots, not for other slots. */
+int okb_window_download_batch(okb_ctx* ctx, int win_first, int count, double* const* poses,
+                              double* const* speed_bias, double* const* landmarks, double* const* quality);
 
 /* Optional per-kernel device timing: CUDA events on the context stream around every solver kernel
  * launch.  okb_profile_enable(ctx,1) clears the counters; okb_profile_read synchronises and returns

@@ -123,6 +123,39 @@ class Context:
         self._check(lib().okb_window_download(self._h, int(win), _p(poses), _p(sb), _p(lms), _p(q)))
         return dict(poses=poses, speed_bias=sb, landmarks=lms, quality=q)
 
+    def upload_batch(self, first, windows, host_threads=0, descs=None):
+        """okb_window_upload_batch; `descs` (from make_descs) may be cached by the caller while the host arrays live."""
+        if descs is None:
+            descs = self.make_descs(windows)
+        self._check(lib().okb_window_upload_batch(self._h, int(first), len(windows), descs, int(host_threads)))
+        for i, w in enumerate(windows):
+            self._windows[first + i] = w
+
+    @staticmethod
+    def make_descs(windows):
+        arr = (abi.WindowDesc * len(windows))()
+        for i, w in enumerate(windows):
+            arr[i] = w.desc()
+        arr._keep = list(windows)
+        return arr
+
+    def alloc_outputs(self, first, count):
+        """Host buffers for download_batch plus the pointer tables over them."""
+        outs = []
+        for i in range(first, first + count):
+            w = self._windows[i]
+            outs.append(dict(poses=np.zeros_like(w.poses), speed_bias=np.zeros_like(w.speed_bias),
+                             landmarks=np.zeros_like(w.landmarks), quality=np.zeros(len(w.landmarks))))
+        PP = C.POINTER(C.c_double) * count
+        tables = [PP(*[o[k].ctypes.data_as(C.POINTER(C.c_double)) for o in outs])
+                  for k in ("poses", "speed_bias", "landmarks", "quality")]
+        return outs, tables
+
+    def download_batch(self, first, count, out=None):
+        outs, tables = out if out is not None else self.alloc_outputs(first, count)
+        self._check(lib().okb_window_download_batch(self._h, int(first), int(count), *tables))
+        return outs
+
     # ---------------------------------------------------------------- single-block hooks
     def eval_reprojection(self, cam, pose, lm, ext, z, sqrt_info):
         pose, lm, ext, z, sqrt_info = map(_f64, (pose, lm, ext, z, sqrt_info))

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -15,6 +16,10 @@ struct WinStore {
   size_t h2d_bytes = 0;
   bool uploaded = false;
   cudaEvent_t copied = nullptr;       // recorded after the H2D copy of `staging`; the next upload of the slot waits on it
+  unsigned char* out_staging = nullptr;  // pinned host buffer the estimates are downloaded into
+  size_t out_bytes = 0;
+  cudaEvent_t down = nullptr;         // recorded after the D2H copies of a download
+  int done_idx = -1;                  // index into okb_ctx::done_ring of the last solver work launched on this slot
 };
 
 struct okb_frontend_state;
@@ -28,6 +33,15 @@ struct okb_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream_imu = nullptr;     // k_imu runs beside the landmark kernels
   cudaEvent_t ev_round = nullptr, ev_imu = nullptr;
+  // Transfers (window uploads / estimate downloads) run on their own stream so that they overlap solver
+  // kernels of other windows.  ev_join orders the solver stream after all uploads issued so far;
+  // done_ring[k] is recorded on the solver stream after each optimize / reset and transfers of the
+  // windows it touched wait on it.
+  cudaStream_t stream_xfer = nullptr;
+  cudaEvent_t ev_join = nullptr;
+  static constexpr int kDoneRing = 8;
+  cudaEvent_t done_ring[kDoneRing] = {};
+  int done_next = 0;
   std::vector<WinStore> wins;
   std::vector<okb::WinDev> host;      // host mirror of d_wins
   okb::WinDev* d_wins = nullptr;
@@ -43,7 +57,8 @@ struct okb_ctx {
   std::vector<int> prof_kind;             // kernel id per pair
   size_t prof_used = 0;
   std::string error;
-  void set_error(const std::string& e) { error = e; }
+  std::mutex error_mu;                    // uploads of different slots may run on several host threads
+  void set_error(const std::string& e) { std::lock_guard<std::mutex> g(error_mu); error = e; }
 };
 
 void okb_frontend_release(okb_ctx* c);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "okb_ctx.h"
@@ -49,11 +50,14 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
   }
   if (cudaStreamCreateWithFlags(&c->stream_imu, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_round, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_imu, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&c->ev_imu, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream_xfer, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     g_create_error = "cudaStreamCreate / cudaEventCreate failed";
     delete c;
     return OKB_ERR_CUDA;
   }
+  for (int k = 0; k < okb_ctx::kDoneRing; ++k) cudaEventCreateWithFlags(&c->done_ring[k], cudaEventDisableTiming);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device_id);
   c->sm_count = prop.multiProcessorCount;
@@ -82,11 +86,17 @@ extern "C" void okb_ctx_destroy(okb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->stream_xfer) cudaStreamSynchronize(c->stream_xfer);
   for (auto& w : c->wins) {
     if (w.arena) cudaFree(w.arena);
     if (w.staging) cudaFreeHost(w.staging);
+    if (w.out_staging) cudaFreeHost(w.out_staging);
     if (w.copied) cudaEventDestroy(w.copied);
+    if (w.down) cudaEventDestroy(w.down);
   }
+  for (int k = 0; k < okb_ctx::kDoneRing; ++k) if (c->done_ring[k]) cudaEventDestroy(c->done_ring[k]);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream_xfer) cudaStreamDestroy(c->stream_xfer);
   okb_frontend_release(c);
   if (c->d_wins) cudaFree(c->d_wins);
   if (c->d_states) cudaFree(c->d_states);
@@ -116,6 +126,18 @@ struct ArenaPlan {
     return o;
   }
 };
+// Orders the solver stream after every transfer issued so far.
+int join_transfers(okb_ctx* c) {
+  if (cudaEventRecord(c->ev_join, c->stream_xfer) != cudaSuccess) return 1;
+  return cudaStreamWaitEvent(c->stream, c->ev_join, 0) != cudaSuccess;
+}
+// Marks solver-stream work on windows [first, first+count): later transfers of these windows wait for it.
+void mark_work(okb_ctx* c, int first, int count) {
+  const int k = c->done_next;
+  c->done_next = (k + 1) % okb_ctx::kDoneRing;
+  cudaEventRecord(c->done_ring[k], c->stream);
+  for (int i = first; i < first + count; ++i) c->wins[i].done_idx = k;
+}
 }  // namespace
 
 extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) {
@@ -163,9 +185,8 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   const size_t o_lm = P.take(sizeof(double) * 4 * L);
   const size_t o_slots = P.take(sizeof(SlotInfo) * NSP);
   const size_t o_cams = P.take(sizeof(okb_camera) * NC);
-  const size_t o_obsz = P.take(sizeof(double2) * (size_t)L * NS);
-  const size_t o_obsw = P.take(sizeof(double) * (size_t)L * NS);
   const size_t o_vis = P.take(sizeof(uint32_t) * L);
+  const size_t o_obsl = P.take(sizeof(okb_observation) * std::max(D->n_obs, 1));
   const size_t o_imut = P.take(sizeof(okb_imu_term) * std::max(W.n_imu, 1));
   const size_t o_samp = P.take(sizeof(okb_imu_sample) * std::max(W.n_samples, 1));
   const size_t o_pp = P.take(sizeof(okb_pose_prior) * std::max(W.n_pp, 1));
@@ -187,12 +208,10 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   size_t o_lmg[2], o_lmE[2], o_gd[2], o_Ed[2];
   for (int b = 0; b < 2; ++b) { o_lmg[b] = P.take(sizeof(double) * 3 * L); o_lmE[b] = P.take(sizeof(double) * 3 * L); }
   const size_t o_Rinv = P.take(sizeof(double) * 6 * L);
-  const size_t o_M = P.take(sizeof(double) * 6 * (size_t)L * K);
   const size_t o_mf = P.take(sizeof(double) * 3 * (size_t)L * K);
   const size_t o_gn = P.take(sizeof(double) * 3 * L);
   const size_t o_Li = P.take(sizeof(double) * 9 * L);
   const size_t o_scale = P.take(sizeof(double) * 3 * L);
-  const size_t o_quality = P.take(sizeof(double) * L);
   const int pstride = dcp * dcp;
   const int n_cx = (L + L1_THREADS - 1) / L1_THREADS;
   const size_t o_partH = P.take(sizeof(double) * (size_t)n_cx * K * kPartH);
@@ -201,8 +220,15 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   for (int b = 0; b < 2; ++b) { o_gd[b] = P.take(sizeof(double) * d); o_Ed[b] = P.take(sizeof(double) * d); }
   const size_t o_ud = P.take(sizeof(double) * d), o_scd = P.take(sizeof(double) * d);
   const size_t o_chol = P.take(sizeof(double) * (size_t)d * d);
+  // one contiguous region zeroed by a single memset per upload
+  const size_t o_zero = P.total;
+  const size_t o_obsz = P.take(sizeof(double2) * (size_t)L * NS);
+  const size_t o_obsw = P.take(sizeof(double) * (size_t)L * NS);
+  const size_t o_M = P.take(sizeof(double) * 6 * (size_t)L * K);
+  const size_t o_quality = P.take(sizeof(double) * L);
   const size_t o_cache = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
   const size_t o_cache_i = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
+  const size_t zero_bytes = P.total - o_zero;
   const size_t o_imu_out = P.take(sizeof(double) * kImuOut * std::max(W.n_imu, 1));
 
   WinStore& S = c->wins[win];
@@ -218,10 +244,17 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
     OKB_CUDA(c, cudaMallocHost(&S.staging, input_bytes));
     S.staging_bytes = input_bytes;
   }
+  const size_t out_bytes = (o_lm + sizeof(double) * 4 * L - o_pose) + sizeof(double) * L;
+  if (S.out_bytes < out_bytes) {
+    if (S.out_staging) cudaFreeHost(S.out_staging);
+    S.out_staging = nullptr; S.out_bytes = 0;
+    OKB_CUDA(c, cudaMallocHost(&S.out_staging, out_bytes));
+    S.out_bytes = out_bytes;
+  }
+  if (!S.down) OKB_CUDA(c, cudaEventCreateWithFlags(&S.down, cudaEventDisableTiming));
   if (!S.copied) OKB_CUDA(c, cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
   else OKB_CUDA(c, cudaEventSynchronize(S.copied));
   unsigned char* H = S.staging;
-  std::memset(H, 0, input_bytes);
   std::memcpy(H + o_pose, D->poses, sizeof(double) * 7 * K);
   if (NSB) std::memcpy(H + o_sb, D->speed_bias, sizeof(double) * 9 * NSB);
   std::memcpy(H + o_ext, D->extrinsics, sizeof(double) * 7 * NE);
@@ -231,12 +264,14 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   if (W.n_samples) std::memcpy(H + o_samp, D->imu_samples, sizeof(okb_imu_sample) * W.n_samples);
   if (W.n_pp) std::memcpy(H + o_pp, D->pose_priors, sizeof(okb_pose_prior) * W.n_pp);
   if (W.n_sbp) std::memcpy(H + o_sbp, D->sb_priors, sizeof(okb_sb_prior) * W.n_sbp);
-  // slots + observation grid
+  // Observations travel as the compact list; the device scatters them into the slot-major grid
+  // (k_prepare).  The host pass validates indices, finds the (frame,camera) slots, rejects duplicates with a
+  // bitmap over the grid cells and builds the per-landmark frame-visibility masks.
   SlotInfo* slots = reinterpret_cast<SlotInfo*>(H + o_slots);
   for (int s = 0; s < NSP; ++s) slots[s] = SlotInfo{0, 0, 0, 0};
-  double2* oz = reinterpret_cast<double2*>(H + o_obsz);
-  double* ow = reinterpret_cast<double*>(H + o_obsw);
   uint32_t* vis = reinterpret_cast<uint32_t*>(H + o_vis);
+  std::memset(vis, 0, sizeof(uint32_t) * L);
+  std::vector<uint64_t> seen(((size_t)NS * L + 63) / 64, 0);
   for (int i = 0; i < D->n_obs; ++i) {
     const okb_observation& ob = D->obs[i];
     if ((int)ob.pose_idx >= K || (int)ob.lm_idx >= L || (int)ob.ext_idx >= NE || (int)ob.cam_idx >= NC) {
@@ -248,12 +283,14 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
     if (!si.valid) si = SlotInfo{(int)ob.pose_idx, (int)ob.ext_idx, (int)ob.cam_idx, 1};
     else if (si.ext_idx != (int)ob.ext_idx) { c->set_error("inconsistent extrinsics block for a (frame,camera) slot"); return OKB_ERR_INVALID_ARG; }
     const size_t g = (size_t)s * L + ob.lm_idx;
-    if (ow[g] != 0.0) { c->set_error("duplicate observation of a landmark in one (frame,camera)"); return OKB_ERR_UNSUPPORTED; }
+    uint64_t& word = seen[g >> 6];
+    const uint64_t bit = 1ull << (g & 63);
+    if (word & bit) { c->set_error("duplicate observation of a landmark in one (frame,camera)"); return OKB_ERR_UNSUPPORTED; }
+    word |= bit;
     if (!(ob.sqrt_info > 0.0)) { c->set_error("observation with non-positive sqrt information"); return OKB_ERR_INVALID_ARG; }
-    oz[g] = make_double2(ob.z[0], ob.z[1]);
-    ow[g] = ob.sqrt_info;
     vis[ob.lm_idx] |= (1u << ob.pose_idx);
   }
+  if (D->n_obs) std::memcpy(H + o_obsl, D->obs, sizeof(okb_observation) * D->n_obs);
   for (int t = 0; t < W.n_imu; ++t) {
     const okb_imu_term& T = D->imu_terms[t];
     if ((int)T.pose0 >= K || (int)T.pose1 >= K || (int)T.sb0 >= NSB || (int)T.sb1 >= NSB ||
@@ -289,14 +326,12 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
       }
   }
   unsigned char* A = S.arena;
-  OKB_CUDA(c, cudaMemcpyAsync(A, H, input_bytes, cudaMemcpyHostToDevice, c->stream));
-  // initial-state copies + zeroed caches
-  OKB_CUDA(c, cudaMemcpyAsync(A + o_pose_i, A + o_pose, sizeof(double) * 7 * K, cudaMemcpyDeviceToDevice, c->stream));
-  if (NSB) OKB_CUDA(c, cudaMemcpyAsync(A + o_sb_i, A + o_sb, sizeof(double) * 9 * NSB, cudaMemcpyDeviceToDevice, c->stream));
-  OKB_CUDA(c, cudaMemcpyAsync(A + o_lm_i, A + o_lm, sizeof(double) * 4 * L, cudaMemcpyDeviceToDevice, c->stream));
-  OKB_CUDA(c, cudaMemsetAsync(A + o_cache, 0, sizeof(ImuCache) * std::max(W.n_imu, 1) * 2, c->stream));
-  OKB_CUDA(c, cudaMemsetAsync(A + o_M, 0, sizeof(double) * 6 * (size_t)L * K, c->stream));
-  OKB_CUDA(c, cudaMemsetAsync(A + o_quality, 0, sizeof(double) * L, c->stream));
+  cudaStream_t xs = c->stream_xfer;
+  // solver work launched earlier on this slot must have finished before its arena is overwritten
+  if (S.done_idx >= 0) OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
+  OKB_CUDA(c, cudaMemcpyAsync(A, H, input_bytes, cudaMemcpyHostToDevice, xs));
+  OKB_CUDA(c, cudaEventRecord(S.copied, xs));
+  OKB_CUDA(c, cudaMemsetAsync(A + o_zero, 0, zero_bytes, xs));
 
   auto dp = [&](size_t o) { return reinterpret_cast<double*>(A + o); };
   W.pose = dp(o_pose); W.sb = dp(o_sb); W.ext = dp(o_ext); W.lm = dp(o_lm);
@@ -307,6 +342,8 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   W.obs_z = reinterpret_cast<double2*>(A + o_obsz);
   W.obs_w = dp(o_obsw);
   W.lm_vis = reinterpret_cast<uint32_t*>(A + o_vis);
+  W.obs_list = reinterpret_cast<const okb_observation*>(A + o_obsl);
+  W.n_obs = D->n_obs;
   for (int b = 0; b < 2; ++b) { W.lm_g[b] = dp(o_lmg[b]); W.lm_E[b] = dp(o_lmE[b]); W.gd[b] = dp(o_gd[b]); W.Ed[b] = dp(o_Ed[b]); }
   W.lm_Rinv = dp(o_Rinv); W.lm_M = dp(o_M); W.lm_mf = dp(o_mf); W.partH = dp(o_partH); W.lm_gn = dp(o_gn); W.lm_Li = dp(o_Li); W.lm_scale = dp(o_scale); W.quality = dp(o_quality);
   W.partA = dp(o_part); W.partA_stride = pstride;
@@ -327,10 +364,43 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   c->host[win] = W;
   S.uploaded = true;
   S.h2d_bytes = input_bytes;
-  OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + win, &c->host[win], sizeof(WinDev), cudaMemcpyHostToDevice, c->stream));
-  // No stream synchronisation here: uploads of different slots pipeline behind each other.  The staging
-  // buffer belongs to this slot; its next upload waits on `copied` before touching it.
-  OKB_CUDA(c, cudaEventRecord(S.copied, c->stream));
+  OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + win, &c->host[win], sizeof(WinDev), cudaMemcpyHostToDevice, xs));
+  {
+    const int work = std::max(std::max(D->n_obs, 4 * L), std::max(7 * K, 9 * NSB));
+    k_prepare<<<(work + 255) / 256, 256, 0, xs>>>(c->d_wins, win);
+    OKB_CUDA(c, cudaGetLastError());
+  }
+  // No synchronisation here: uploads of different slots pipeline behind each other on the transfer stream
+  // and overlap solver kernels of other windows.  The staging buffer belongs to this slot; its next upload
+  // waits on `copied` before touching it.  okb_optimize* / okb_window_reset order themselves after all
+  // uploads issued before them (join_transfers).
+  return OKB_OK;
+}
+
+extern "C" int okb_window_upload_batch(okb_ctx* c, int first, int count, const okb_window_desc* descs, int host_threads) {
+  if (!c || !descs || count < 1 || first < 0 || first + count > c->max_windows) return OKB_ERR_INVALID_ARG;
+  int T = host_threads > 0 ? host_threads : 8;
+  T = std::max(1, std::min(T, count));
+  if (T == 1) {
+    for (int i = 0; i < count; ++i) {
+      const int rc = okb_window_upload(c, first + i, descs + i);
+      if (rc) return rc;
+    }
+    return OKB_OK;
+  }
+  std::vector<int> rcs(T, OKB_OK);
+  std::vector<std::thread> th;
+  th.reserve(T);
+  for (int t = 0; t < T; ++t)
+    th.emplace_back([=, &rcs]() {
+      for (int i = t; i < count; i += T) {
+        const int rc = okb_window_upload(c, first + i, descs + i);
+        if (rc) { rcs[t] = rc; return; }
+      }
+    });
+  for (auto& x : th) x.join();
+  for (int t = 0; t < T; ++t)
+    if (rcs[t]) return rcs[t];
   return OKB_OK;
 }
 
@@ -391,9 +461,11 @@ extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
   int rc = check_range(c, first, count);
   if (rc) return rc;
   cudaSetDevice(c->device);
+  if (join_transfers(c)) { c->set_error("stream ordering failed"); return OKB_ERR_CUDA; }
   k_reset<<<count, 128, 0, c->stream>>>(c->d_wins, first, 1);
   c->launches += 1;
   OKB_CUDA(c, cudaGetLastError());
+  mark_work(c, first, count);
   return OKB_OK;
 }
 
@@ -447,6 +519,23 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
   return OKB_OK;
 }
 
+// post-solve landmark quality (Estimator.cpp:880-894)
+static int launch_quality(okb_ctx* c, int first, int count) {
+  size_t smQ = 0;
+  int maxL = 1;
+  for (int i = first; i < first + count; ++i) {
+    smQ = std::max(smQ, (size_t)c->host[i].NS * sizeof(SlotCtx));
+    maxL = std::max(maxL, c->host[i].L);
+  }
+  const int gx = std::max(1, std::min((maxL + 127) / 128, (4 * c->sm_count + count - 1) / count));
+  prof_begin(c, 2);
+  k_quality<<<dim3(gx, count), 128, smQ, c->stream>>>(c->d_wins, first);
+  prof_end(c);
+  c->launches += 1;
+  OKB_CUDA(c, cudaGetLastError());
+  return OKB_OK;
+}
+
 extern "C" int okb_optimize_async(okb_ctx* c, int first, int count, const okb_solve_options* opt) {
   int rc = check_range(c, first, count);
   if (rc) return rc;
@@ -462,43 +551,38 @@ extern "C" int okb_optimize_async(okb_ctx* c, int first, int count, const okb_so
     W.lm_per_chunk = (W.L + chunks - 1) / chunks;
     W.use_cauchy = opt->use_cauchy_loss ? 1 : 0;
   }
+  if (join_transfers(c)) { c->set_error("stream ordering failed"); return OKB_ERR_CUDA; }
   OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + first, &c->host[first], sizeof(WinDev) * count, cudaMemcpyHostToDevice, c->stream));
   k_reset<<<count, 128, 0, c->stream>>>(c->d_wins, first, 0);
   c->launches += 1;
   c->last_opt = *opt;
   // round 0 linearises at the initial state; each later round judges one step and proposes the next
-  return launch_rounds(c, first, count, *opt, opt->max_iterations + 1);
+  rc = launch_rounds(c, first, count, *opt, opt->max_iterations + 1);
+  if (rc) return rc;
+  rc = launch_quality(c, first, count);
+  OKB_CUDA(c, cudaMemcpyAsync(c->h_states + first, c->d_states + first, sizeof(SolverState) * count, cudaMemcpyDeviceToHost, c->stream));
+  mark_work(c, first, count);
+  return rc;
 }
 
 extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary* out) {
   int rc = check_range(c, first, count);
   if (rc) return rc;
   cudaSetDevice(c->device);
-  // Rebuild rounds (linear-solver failures) consume rounds without advancing the iteration count:
-  // keep launching until every window reports done (bounded).
+  // optimize_async already queued the landmark-quality pass and the copy of the solver states.  Rebuild
+  // rounds (linear-solver failures) consume rounds without advancing the iteration count: keep launching
+  // until every window reports done (bounded).
   for (int guard = 0; guard < 64; ++guard) {
-    OKB_CUDA(c, cudaMemcpyAsync(c->h_states + first, c->d_states + first, sizeof(SolverState) * count, cudaMemcpyDeviceToHost, c->stream));
     OKB_CUDA(c, cudaStreamSynchronize(c->stream));
     bool all_done = true;
     for (int i = first; i < first + count; ++i) all_done = all_done && c->h_states[i].done;
     if (all_done) break;
     rc = launch_rounds(c, first, count, c->last_opt, 2);
     if (rc) return rc;
-  }
-  // post-solve landmark quality (Estimator.cpp:880-894)
-  {
-    size_t smQ = 0;
-    int maxL = 1;
-    for (int i = first; i < first + count; ++i) {
-      smQ = std::max(smQ, (size_t)c->host[i].NS * sizeof(SlotCtx));
-      maxL = std::max(maxL, c->host[i].L);
-    }
-    const int gx = std::max(1, std::min((maxL + 127) / 128, (4 * c->sm_count + count - 1) / count));
-    prof_begin(c, 2);
-    k_quality<<<dim3(gx, count), 128, smQ, c->stream>>>(c->d_wins, first);
-    prof_end(c);
-    c->launches += 1;
-    OKB_CUDA(c, cudaGetLastError());
+    rc = launch_quality(c, first, count);
+    if (rc) return rc;
+    OKB_CUDA(c, cudaMemcpyAsync(c->h_states + first, c->d_states + first, sizeof(SolverState) * count, cudaMemcpyDeviceToHost, c->stream));
+    mark_work(c, first, count);
   }
   if (out) {
     for (int i = 0; i < count; ++i) {
@@ -509,7 +593,6 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
       o.imu_redo_count = s.imu_redo_final; o.final_radius = s.radius; o.solve_time_s = s.solve_time_s;
     }
   }
-  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
   return OKB_OK;
 }
 
@@ -531,11 +614,66 @@ extern "C" int okb_window_download(okb_ctx* c, int win, double* poses, double* s
   if (rc) return rc;
   cudaSetDevice(c->device);
   const WinDev& W = c->host[win];
-  if (poses) OKB_CUDA(c, cudaMemcpyAsync(poses, W.pose, sizeof(double) * 7 * W.K, cudaMemcpyDeviceToHost, c->stream));
-  if (speed_bias && W.NSB) OKB_CUDA(c, cudaMemcpyAsync(speed_bias, W.sb, sizeof(double) * 9 * W.NSB, cudaMemcpyDeviceToHost, c->stream));
-  if (landmarks) OKB_CUDA(c, cudaMemcpyAsync(landmarks, W.lm, sizeof(double) * 4 * W.L, cudaMemcpyDeviceToHost, c->stream));
-  if (quality) OKB_CUDA(c, cudaMemcpyAsync(quality, W.quality, sizeof(double) * W.L, cudaMemcpyDeviceToHost, c->stream));
-  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  WinStore& S = c->wins[win];
+  if (!S.uploaded) { c->set_error("window not uploaded"); return OKB_ERR_INVALID_ARG; }
+  // Estimates live contiguously in the arena ([poses | speed/bias | extrinsics | landmarks]); they and the
+  // quality vector are copied into the slot's pinned buffer on the transfer stream, after the solver work
+  // last launched on this slot.
+  cudaStream_t xs = c->stream_xfer;
+  if (S.done_idx >= 0) OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(W.pose);
+  const size_t span = (reinterpret_cast<const unsigned char*>(W.lm) - base) + sizeof(double) * 4 * W.L;
+  OKB_CUDA(c, cudaMemcpyAsync(S.out_staging, base, span, cudaMemcpyDeviceToHost, xs));
+  if (quality) OKB_CUDA(c, cudaMemcpyAsync(S.out_staging + span, W.quality, sizeof(double) * W.L, cudaMemcpyDeviceToHost, xs));
+  OKB_CUDA(c, cudaEventRecord(S.down, xs));
+  OKB_CUDA(c, cudaEventSynchronize(S.down));
+  if (poses) std::memcpy(poses, S.out_staging, sizeof(double) * 7 * W.K);
+  if (speed_bias && W.NSB) std::memcpy(speed_bias, S.out_staging + (reinterpret_cast<const unsigned char*>(W.sb) - base), sizeof(double) * 9 * W.NSB);
+  if (landmarks) std::memcpy(landmarks, S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base), sizeof(double) * 4 * W.L);
+  if (quality) std::memcpy(quality, S.out_staging + span, sizeof(double) * W.L);
+  return OKB_OK;
+}
+
+extern "C" int okb_window_download_batch(okb_ctx* c, int first, int count, double* const* poses, double* const* speed_bias,
+                                         double* const* landmarks, double* const* quality) {
+  int rc = check_range(c, first, count);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  cudaStream_t xs = c->stream_xfer;
+  bool waited[okb_ctx::kDoneRing] = {};
+  for (int i = first; i < first + count; ++i) {
+    WinStore& S = c->wins[i];
+    if (!S.uploaded) { c->set_error("window not uploaded"); return OKB_ERR_INVALID_ARG; }
+    if (S.done_idx >= 0 && !waited[S.done_idx]) {
+      OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
+      waited[S.done_idx] = true;
+    }
+  }
+  for (int i = first; i < first + count; ++i) {
+    const WinDev& W = c->host[i];
+    WinStore& S = c->wins[i];
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(W.pose);
+    const size_t span = (reinterpret_cast<const unsigned char*>(W.lm) - base) + sizeof(double) * 4 * W.L;
+    OKB_CUDA(c, cudaMemcpyAsync(S.out_staging, base, span, cudaMemcpyDeviceToHost, xs));
+    if (quality && quality[i - first])
+      OKB_CUDA(c, cudaMemcpyAsync(S.out_staging + span, W.quality, sizeof(double) * W.L, cudaMemcpyDeviceToHost, xs));
+  }
+  WinStore& S0 = c->wins[first];
+  OKB_CUDA(c, cudaEventRecord(S0.down, xs));
+  OKB_CUDA(c, cudaEventSynchronize(S0.down));
+  for (int i = first; i < first + count; ++i) {
+    const WinDev& W = c->host[i];
+    const WinStore& S = c->wins[i];
+    const int k = i - first;
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(W.pose);
+    const size_t span = (reinterpret_cast<const unsigned char*>(W.lm) - base) + sizeof(double) * 4 * W.L;
+    if (poses && poses[k]) std::memcpy(poses[k], S.out_staging, sizeof(double) * 7 * W.K);
+    if (speed_bias && speed_bias[k] && W.NSB)
+      std::memcpy(speed_bias[k], S.out_staging + (reinterpret_cast<const unsigned char*>(W.sb) - base), sizeof(double) * 9 * W.NSB);
+    if (landmarks && landmarks[k])
+      std::memcpy(landmarks[k], S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base), sizeof(double) * 4 * W.L);
+    if (quality && quality[k]) std::memcpy(quality[k], S.out_staging + span, sizeof(double) * W.L);
+  }
   return OKB_OK;
 }
 

@@ -79,6 +79,8 @@ struct WinDev {
   double2* obs_z;                              // [NS][L]  slot-major: coalesced for thread-per-landmark kernels
   double* obs_w;                               // [NS][L] sqrt information, 0 = no observation
   uint32_t* lm_vis;                            // [L] bit f set = observed in frame f
+  const okb_observation* obs_list;             // [n_obs] as uploaded; k_prepare scatters it into the grid
+  int n_obs;
   // per-landmark solver data
   double* lm_g[2];                             // [L][3] gradient block (double buffered: cur / speculative)
   double* lm_E[2];                             // [L][3] metric (Ceres diagonal^2 / scale^2)

@@ -669,6 +669,22 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
 }
 
 // resets the solver state (and optionally the parameter state) of a range of windows
+// Runs once per upload (transfer stream): scatters the compact observation list into the slot-major
+// grid (zeroed by a memset just before) and keeps the uploaded state for okb_window_reset.
+__global__ void k_prepare(const WinDev* __restrict__ wins, int win) {
+  const WinDev& W = wins[win];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W.n_obs) {
+    const okb_observation ob = W.obs_list[i];
+    const size_t g = (size_t)((int)ob.pose_idx * W.CP + (int)ob.cam_idx) * W.L + ob.lm_idx;
+    W.obs_z[g] = make_double2(ob.z[0], ob.z[1]);
+    W.obs_w[g] = ob.sqrt_info;
+  }
+  if (i < 7 * W.K) W.pose_init[i] = W.pose[i];
+  if (i < 9 * W.NSB) W.sb_init[i] = W.sb[i];
+  if (i < 4 * W.L) W.lm_init[i] = W.lm[i];
+}
+
 __global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int restore_params) {
   const WinDev& W = wins[win_first + blockIdx.x];
   const int tid = threadIdx.x;

@@ -151,15 +151,16 @@ class Window:
             arr = getattr(self, name)
             setattr(d, name, arr.ctypes.data if len(arr) else None)
         d.imu_params = self.imu_params
-        self._marg_c = None
         if self.marg is not None:
-            m = abi.MargPrior()
-            mk = self.marg
-            m.n, m.n_blocks = int(mk["J"].shape[0]), len(mk["block_kind"])
-            m.block_kind = mk["block_kind"].ctypes.data_as(C.POINTER(C.c_int32))
-            m.block_idx = mk["block_idx"].ctypes.data_as(C.POINTER(C.c_uint32))
-            m.x0, m.J, m.e0 = abi.dptr(mk["x0"]), abi.dptr(mk["J"]), abi.dptr(mk["e0"])
-            self._marg_c = m
+            m = getattr(self, "_marg_c", None)
+            if m is None:       # built once: descriptors copied elsewhere keep pointing at this struct
+                m = abi.MargPrior()
+                mk = self.marg
+                m.n, m.n_blocks = int(mk["J"].shape[0]), len(mk["block_kind"])
+                m.block_kind = mk["block_kind"].ctypes.data_as(C.POINTER(C.c_int32))
+                m.block_idx = mk["block_idx"].ctypes.data_as(C.POINTER(C.c_uint32))
+                m.x0, m.J, m.e0 = abi.dptr(mk["x0"]), abi.dptr(mk["J"]), abi.dptr(mk["e0"])
+                self._marg_c = m
             d.marg = C.pointer(m)
         return d
 

@@ -142,3 +142,25 @@ def test_four_camera_twenty_frame_window(ctx, oracle):
     SYRK mapping and the global-memory Cholesky (d = 300)."""
     cfg = dataclasses.replace(synthetic.CONFIGS[5], n_landmarks=600)
     compare(ctx, oracle, synthetic.make_window(5, 0, cfg=cfg), max_iterations=6)
+
+
+def test_batch_transfer_api_matches_single_calls(ctx):
+    """okb_window_upload_batch / okb_window_download_batch (transfer stream, threaded packing) give the same
+    bits as the one-window calls, also when a download overlaps an optimize of other slots."""
+    ws = [synthetic.make_window(1, i) for i in range(3)] + [synthetic.make_window(2, 1)]
+    single = []
+    for i, w in enumerate(ws):
+        ctx.upload(i, w)
+        ctx.optimize(i, 1, max_iterations=6)
+        single.append(ctx.download(i))
+    ctx.upload_batch(4, ws, host_threads=3)
+    ctx.optimize_async(4, 4, max_iterations=6)
+    ctx.optimize_finish(4, 4)
+    ctx.upload_batch(0, ws, host_threads=2)          # other slots: overlaps nothing it depends on
+    ctx.optimize_async(0, 4, max_iterations=6)       # in flight while slots 4..7 are downloaded
+    outs = ctx.download_batch(4, 4)
+    ctx.optimize_finish(0, 4)
+    again = ctx.download_batch(0, 4)
+    for a, b, c in zip(single, outs, again):
+        for k in ("poses", "speed_bias", "landmarks", "quality"):
+            assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
