@@ -235,7 +235,7 @@ int okb_profile_enable(okb_ctx* ctx, int on);
 int okb_profile_read(okb_ctx* ctx, double out[6]);
 /* Diagnostics: nanoseconds the reduced-solve kernel spent per internal phase during the last optimize of
  * `win` (dense terms, partial gather, assembly, Cholesky, substitution, back-substitution, dogleg). */
-int okb_debug_phase_ns(okb_ctx* ctx, int win, double out[8]);
+int okb_debug_phase_ns(okb_ctx* ctx, int win, double out[16]);
 
 /* ------------------------------------------------- single-block test hooks
  * Mirror ErrorInterface::EvaluateWithMinimalJacobians (okvis_ceres/include/okvis/ceres/ErrorInterface.hpp:93-95).

@@ -80,9 +80,10 @@ class Context:
         self._windows[win] = window
 
     def debug_phase_us(self, win):
-        out = np.zeros(8)
+        out = np.zeros(16)
         self._check(lib().okb_debug_phase_ns(self._h, int(win), _p(out)))
-        names = ["dense_terms", "gather", "assemble", "cholesky", "substitution", "backsub", "dogleg", "_"]
+        names = ["dense_terms", "gather", "assemble", "cholesky", "substitution", "backsub", "dogleg", "_",
+                 "schur_wait_top", "schur_stage_flush", "schur_Y", "schur_wait_Y", "schur_syrk", "schur_epilogue", "_a", "_b"]
         return {n: v * 1e-3 for n, v in zip(names, out)}
 
     def h2d_bytes(self, win):

@@ -19,6 +19,7 @@ struct WinStore {
   unsigned char* out_staging = nullptr;  // pinned host buffer the estimates are downloaded into
   size_t out_bytes = 0;
   cudaEvent_t down = nullptr;         // recorded after the D2H copies of a download
+  std::vector<uint32_t> perm;         // internal (sorted) landmark index -> caller's index
   int done_idx = -1;                  // index into okb_ctx::done_ring of the last solver work launched on this slot
 };
 
@@ -29,6 +30,7 @@ struct okb_ctx {
   int max_windows = 0;
   int sm_count = 148;
   int smem_optin = 0;
+  int smem_per_sm = 0;
   int chunk_cap = 1;
   cudaStream_t stream = nullptr;
   cudaStream_t stream_imu = nullptr;     // k_imu runs beside the landmark kernels

@@ -62,6 +62,7 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
   cudaGetDeviceProperties(&prop, device_id);
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   c->wins.resize(max_windows);
   c->host.assign(max_windows, WinDev());
   std::memset(c->host.data(), 0, sizeof(WinDev) * max_windows);
@@ -74,8 +75,7 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
     return OKB_ERR_CUDA;
   }
   cudaMemset(c->d_states, 0, sizeof(SolverState) * max_windows);
-  cudaFuncSetAttribute(k_schur<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-  cudaFuncSetAttribute(k_schur<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   cudaFuncSetAttribute(k_quality, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   *out = c;
@@ -126,6 +126,15 @@ struct ArenaPlan {
     return o;
   }
 };
+// Landmark estimates / qualities come back in the internal (sorted) order: scatter to the caller's order.
+void unpermute_landmarks(const WinStore& S, int L, const double* lm_sorted, const double* q_sorted, double* landmarks, double* quality) {
+  for (int j = 0; j < L; ++j) {
+    const uint32_t l = S.perm[j];
+    if (landmarks) std::memcpy(landmarks + 4 * (size_t)l, lm_sorted + 4 * (size_t)j, sizeof(double) * 4);
+    if (quality) quality[l] = q_sorted[j];
+  }
+}
+
 // Orders the solver stream after every transfer issued so far.
 int join_transfers(okb_ctx* c) {
   if (cudaEventRecord(c->ev_join, c->stream_xfer) != cudaSuccess) return 1;
@@ -158,15 +167,13 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   const int NS = K * CP, NG = (NS + 31) / 32, NSP = NG * 32;
   const int dc = 6 * K, d = dc + 9 * NSB, dcp = 4 * ((dc + 1 + 3) / 4);
   if (d > kMaxDense) { c->set_error("reduced system too large"); return OKB_ERR_CAPACITY; }
-  const int NT = dcp / 4, NTT = NT * (NT + 1) / 2;
-  if (NTT > 2 * A2_THREADS) { c->set_error("too many frames for the Schur tile kernel"); return OKB_ERR_CAPACITY; }
   int marg_n = 0, marg_nb = 0, marg_xdim = 0;
   if (D->marg && D->marg->n > 0) {
     marg_n = D->marg->n; marg_nb = D->marg->n_blocks;
     if (marg_n > kMaxMarg) { c->set_error("marginalisation prior too large"); return OKB_ERR_CAPACITY; }
     for (int b = 0; b < marg_nb; ++b) marg_xdim += (D->marg->block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
   }
-  const size_t smA = smemA2_bytes(K, dcp);
+  const size_t smA = smemA2_bytes(K, dcp, 0);
   if (smA > (size_t)c->smem_optin) { c->set_error("window does not fit kernel A shared memory"); return OKB_ERR_CAPACITY; }
 
   // ---- arena plan: [inputs (copied from the staging buffer)] [scratch]
@@ -186,6 +193,9 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   const size_t o_slots = P.take(sizeof(SlotInfo) * NSP);
   const size_t o_cams = P.take(sizeof(okb_camera) * NC);
   const size_t o_vis = P.take(sizeof(uint32_t) * L);
+  const size_t o_inv = P.take(sizeof(uint32_t) * L);
+  const int n_tiles = (L + 31) / 32;
+  const size_t o_trange = P.take(sizeof(uint32_t) * n_tiles);
   const size_t o_obsl = P.take(sizeof(okb_observation) * std::max(D->n_obs, 1));
   const size_t o_imut = P.take(sizeof(okb_imu_term) * std::max(W.n_imu, 1));
   const size_t o_samp = P.take(sizeof(okb_imu_sample) * std::max(W.n_samples, 1));
@@ -208,6 +218,7 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   size_t o_lmg[2], o_lmE[2], o_gd[2], o_Ed[2];
   for (int b = 0; b < 2; ++b) { o_lmg[b] = P.take(sizeof(double) * 3 * L); o_lmE[b] = P.take(sizeof(double) * 3 * L); }
   const size_t o_Rinv = P.take(sizeof(double) * 6 * L);
+  const size_t o_slotctx = P.take(sizeof(SlotCtx) * NSP);
   const size_t o_mf = P.take(sizeof(double) * 3 * (size_t)L * K);
   const size_t o_gn = P.take(sizeof(double) * 3 * L);
   const size_t o_Li = P.take(sizeof(double) * 9 * L);
@@ -258,7 +269,6 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   std::memcpy(H + o_pose, D->poses, sizeof(double) * 7 * K);
   if (NSB) std::memcpy(H + o_sb, D->speed_bias, sizeof(double) * 9 * NSB);
   std::memcpy(H + o_ext, D->extrinsics, sizeof(double) * 7 * NE);
-  std::memcpy(H + o_lm, D->landmarks, sizeof(double) * 4 * L);
   std::memcpy(H + o_cams, D->cameras, sizeof(okb_camera) * NC);
   if (W.n_imu) std::memcpy(H + o_imut, D->imu_terms, sizeof(okb_imu_term) * W.n_imu);
   if (W.n_samples) std::memcpy(H + o_samp, D->imu_samples, sizeof(okb_imu_sample) * W.n_samples);
@@ -269,8 +279,7 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   // bitmap over the grid cells and builds the per-landmark frame-visibility masks.
   SlotInfo* slots = reinterpret_cast<SlotInfo*>(H + o_slots);
   for (int s = 0; s < NSP; ++s) slots[s] = SlotInfo{0, 0, 0, 0};
-  uint32_t* vis = reinterpret_cast<uint32_t*>(H + o_vis);
-  std::memset(vis, 0, sizeof(uint32_t) * L);
+  std::vector<uint32_t> vis(L, 0u);       // frame-visibility mask per landmark (caller's indexing)
   std::vector<uint64_t> seen(((size_t)NS * L + 63) / 64, 0);
   for (int i = 0; i < D->n_obs; ++i) {
     const okb_observation& ob = D->obs[i];
@@ -289,6 +298,39 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
     word |= bit;
     if (!(ob.sqrt_info > 0.0)) { c->set_error("observation with non-positive sqrt information"); return OKB_ERR_INVALID_ARG; }
     vis[ob.lm_idx] |= (1u << ob.pose_idx);
+  }
+  // Internal landmark order: sorted by (first, last) observing frame, stable (counting sort); landmarks
+  // without observations go last.  The device works in this order only; downloads map back.
+  {
+    S.perm.resize(L);
+    uint32_t* inv = reinterpret_cast<uint32_t*>(H + o_inv);
+    std::vector<uint32_t> count(32 * 32 + 2, 0u);
+    auto key_of = [&](uint32_t m) -> uint32_t {
+      if (!m) return 32u * 32u;
+      return (uint32_t)__builtin_ctz(m) * 32u + (31u - (uint32_t)__builtin_clz(m));
+    };
+    for (int l = 0; l < L; ++l) ++count[key_of(vis[l]) + 1];
+    for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
+    for (int l = 0; l < L; ++l) {
+      const uint32_t j = count[key_of(vis[l])]++;
+      S.perm[j] = (uint32_t)l;
+      inv[l] = j;
+    }
+    uint32_t* vis_s = reinterpret_cast<uint32_t*>(H + o_vis);
+    double* lm_s = reinterpret_cast<double*>(H + o_lm);
+    uint32_t* trange = reinterpret_cast<uint32_t*>(H + o_trange);
+    for (int t = 0; t < n_tiles; ++t) trange[t] = 1u;      // first = 1 > last = 0: nothing observed
+    for (int j = 0; j < L; ++j) {
+      const uint32_t l = S.perm[j], m = vis[l];
+      vis_s[j] = m;
+      std::memcpy(lm_s + 4 * (size_t)j, D->landmarks + 4 * (size_t)l, sizeof(double) * 4);
+      if (m) {
+        const uint32_t fi = (uint32_t)__builtin_ctz(m), la = 31u - (uint32_t)__builtin_clz(m);
+        uint32_t& tr = trange[j >> 5];
+        const uint32_t a = tr & 0xffu, b = tr >> 8;
+        tr = (a > b) ? (fi | (la << 8)) : (std::min(a, fi) | (std::max(b, la) << 8));
+      }
+    }
   }
   if (D->n_obs) std::memcpy(H + o_obsl, D->obs, sizeof(okb_observation) * D->n_obs);
   for (int t = 0; t < W.n_imu; ++t) {
@@ -342,9 +384,12 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   W.obs_z = reinterpret_cast<double2*>(A + o_obsz);
   W.obs_w = dp(o_obsw);
   W.lm_vis = reinterpret_cast<uint32_t*>(A + o_vis);
+  W.lm_inv = reinterpret_cast<const uint32_t*>(A + o_inv);
+  W.tile_range = reinterpret_cast<const uint32_t*>(A + o_trange);
   W.obs_list = reinterpret_cast<const okb_observation*>(A + o_obsl);
   W.n_obs = D->n_obs;
   for (int b = 0; b < 2; ++b) { W.lm_g[b] = dp(o_lmg[b]); W.lm_E[b] = dp(o_lmE[b]); W.gd[b] = dp(o_gd[b]); W.Ed[b] = dp(o_Ed[b]); }
+  W.slot_ctx = reinterpret_cast<SlotCtx*>(A + o_slotctx);
   W.lm_Rinv = dp(o_Rinv); W.lm_M = dp(o_M); W.lm_mf = dp(o_mf); W.partH = dp(o_partH); W.lm_gn = dp(o_gn); W.lm_Li = dp(o_Li); W.lm_scale = dp(o_scale); W.quality = dp(o_quality);
   W.partA = dp(o_part); W.partA_stride = pstride;
   W.Hd = dp(o_Hd); W.ud = dp(o_ud); W.scale_d = dp(o_scd); W.chol = dp(o_chol);
@@ -473,16 +518,22 @@ extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
 // optimize
 // ---------------------------------------------------------------------------------------------
 static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_options& opt, int rounds) {
-  int max_chunks = 1, tpt = 1, max_imu = 0, max_cx = 1, max_K = 1;
+  int max_chunks = 1, max_imu = 0, max_cx = 1, max_K = 1;
   size_t smA = 0, smS = 0;
   bool chol_smem = true;
+  // Schur accumulator in shared memory if two CTAs per SM still fit (else one CTA; else accumulate in global memory)
+  int acc_copies = 1;
+  const size_t sm_two = ((size_t)c->smem_per_sm - 2048) / 2;
+  for (int i = first; i < first + count; ++i)
+    if (smemA2_bytes(c->host[i].K, c->host[i].dcp, 1) > std::min((size_t)c->smem_optin, sm_two) &&
+        smemA2_bytes(c->host[i].K, c->host[i].dcp, 0) <= sm_two) acc_copies = 0;
+  for (int i = first; i < first + count; ++i)
+    if (smemA2_bytes(c->host[i].K, c->host[i].dcp, acc_copies) > (size_t)c->smem_optin) acc_copies = 0;
   for (int i = first; i < first + count; ++i) {
     const WinDev& W = c->host[i];
     max_chunks = std::max(max_chunks, W.n_chunks);
     max_imu = std::max(max_imu, W.n_imu);
-    const int NT = W.dcp / 4;
-    if (NT * (NT + 1) / 2 > A2_THREADS) tpt = 2;
-    smA = std::max(smA, smemA2_bytes(W.K, W.dcp));
+    smA = std::max(smA, smemA2_bytes(W.K, W.dcp, acc_copies));
     max_cx = std::max(max_cx, (W.L + L1_THREADS - 1) / L1_THREADS);
     max_K = std::max(max_K, W.K);
     if (smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, true) > (size_t)c->smem_optin) chol_smem = false;
@@ -504,8 +555,7 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
     prof_begin(c, 0);
     k_linearize<<<dim3(max_cx, max_K, count), L1_THREADS, 0, c->stream>>>(c->d_wins, first);
     k_lmblock<<<dim3(max_cx, count), 128, 0, c->stream>>>(c->d_wins, first);
-    if (tpt == 1) k_schur<1><<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first);
-    else k_schur<2><<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first);
+    k_schur<<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first, acc_copies);
     if (max_chunks > 1) { k_reduce_partials<<<dim3(8, count), 256, 0, c->stream>>>(c->d_wins, first); c->launches += 1; }
     prof_end(c);
     c->launches += 2;
@@ -547,8 +597,8 @@ extern "C" int okb_optimize_async(okb_ctx* c, int first, int count, const okb_so
     int chunks = (2 * c->sm_count + count - 1) / count;
     chunks = std::max(1, std::min(chunks, c->chunk_cap));
     chunks = std::min(chunks, std::max(1, W.L / (2 * A2_TILE)));
-    W.n_chunks = chunks;
-    W.lm_per_chunk = (W.L + chunks - 1) / chunks;
+    W.lm_per_chunk = (((W.L + chunks - 1) / chunks) + A2_TILE - 1) / A2_TILE * A2_TILE;   // whole tiles per chunk
+    W.n_chunks = (W.L + W.lm_per_chunk - 1) / W.lm_per_chunk;
     W.use_cauchy = opt->use_cauchy_loss ? 1 : 0;
   }
   if (join_transfers(c)) { c->set_error("stream ordering failed"); return OKB_ERR_CUDA; }
@@ -597,9 +647,9 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
 }
 
 // diagnostics: accumulated k_solve phase times (ns) of the last optimize of `win`
-extern "C" int okb_debug_phase_ns(okb_ctx* c, int win, double out[8]) {
+extern "C" int okb_debug_phase_ns(okb_ctx* c, int win, double out[16]) {
   if (!c || win < 0 || win >= c->max_windows || !out) return OKB_ERR_INVALID_ARG;
-  for (int i = 0; i < 8; ++i) out[i] = (double)c->h_states[win].phase_ns[i];
+  for (int i = 0; i < 16; ++i) out[i] = (double)c->h_states[win].phase_ns[i];
   return OKB_OK;
 }
 
@@ -629,8 +679,8 @@ extern "C" int okb_window_download(okb_ctx* c, int win, double* poses, double* s
   OKB_CUDA(c, cudaEventSynchronize(S.down));
   if (poses) std::memcpy(poses, S.out_staging, sizeof(double) * 7 * W.K);
   if (speed_bias && W.NSB) std::memcpy(speed_bias, S.out_staging + (reinterpret_cast<const unsigned char*>(W.sb) - base), sizeof(double) * 9 * W.NSB);
-  if (landmarks) std::memcpy(landmarks, S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base), sizeof(double) * 4 * W.L);
-  if (quality) std::memcpy(quality, S.out_staging + span, sizeof(double) * W.L);
+  unpermute_landmarks(S, W.L, reinterpret_cast<const double*>(S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base)),
+                      reinterpret_cast<const double*>(S.out_staging + span), landmarks, quality);
   return OKB_OK;
 }
 
@@ -670,9 +720,9 @@ extern "C" int okb_window_download_batch(okb_ctx* c, int first, int count, doubl
     if (poses && poses[k]) std::memcpy(poses[k], S.out_staging, sizeof(double) * 7 * W.K);
     if (speed_bias && speed_bias[k] && W.NSB)
       std::memcpy(speed_bias[k], S.out_staging + (reinterpret_cast<const unsigned char*>(W.sb) - base), sizeof(double) * 9 * W.NSB);
-    if (landmarks && landmarks[k])
-      std::memcpy(landmarks[k], S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base), sizeof(double) * 4 * W.L);
-    if (quality && quality[k]) std::memcpy(quality[k], S.out_staging + span, sizeof(double) * W.L);
+    unpermute_landmarks(S, W.L, reinterpret_cast<const double*>(S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base)),
+                        reinterpret_cast<const double*>(S.out_staging + span), landmarks ? landmarks[k] : nullptr,
+                        quality ? quality[k] : nullptr);
   }
   return OKB_OK;
 }

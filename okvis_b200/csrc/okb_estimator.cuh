@@ -53,11 +53,13 @@ struct SolverState {
   double grad_max;
   unsigned long long t_start_ns, t_last_iter_ns, t_iter_begin_ns;
   double solve_time_s;
-  unsigned long long phase_ns[8];   // accumulated k_solve phase times (diagnostics)
+  unsigned long long phase_ns[16];  // accumulated phase times (diagnostics): 0..7 k_solve, 8..13 k_schur (chunk 0, thread 0)
 };
 
 // Everything kernels need to know about one window.  All pointers are device pointers into the
 // window's arena.
+struct SlotCtx;   // per (frame, camera) transform + intrinsics at the candidate state (okb_kernels_lm.cuh)
+
 struct WinDev {
   int K, NSB, NE, L, NC;
   int CP;              // cameras per frame padded to a power of two
@@ -81,12 +83,18 @@ struct WinDev {
   uint32_t* lm_vis;                            // [L] bit f set = observed in frame f
   const okb_observation* obs_list;             // [n_obs] as uploaded; k_prepare scatters it into the grid
   int n_obs;
+  // Landmarks are stored sorted by (first, last) observing frame (okb_window_upload): tracks are runs of
+  // consecutive frames, so neighbouring landmarks see nearly the same frames -> warp-coherent visibility
+  // in k_linearize and block-sparse Schur tiles in k_schur.
+  const uint32_t* lm_inv;                      // [L] caller's landmark index -> internal (sorted) index
+  const uint32_t* tile_range;                  // [ceil(L/32)] frames seen by the tile: first | last << 8 (first > last: none)
   // per-landmark solver data
   double* lm_g[2];                             // [L][3] gradient block (double buffered: cur / speculative)
   double* lm_E[2];                             // [L][3] metric (Ceres diagonal^2 / scale^2)
   double* lm_Rinv;                             // [L][6] (H_ll + mu E)^-1, symmetric packed
-  double* lm_M;                                // [K][L][6] per-frame sum of rho' A^T A
-  double* lm_mf;                               // [K][L][3] per-frame sum of rho' A^T r
+  double* lm_M;                                // [K][6][L] per-frame sum of rho' A^T A (element-major: coalesced per landmark)
+  double* lm_mf;                               // [K][3][L] per-frame sum of rho' A^T r
+  SlotCtx* slot_ctx;                           // [NS] built by k_reset / k_solve whenever the candidate poses change
   double* lm_Li;                               // [L][9] L^-1 of (H_ll + mu E) (6) and z = L^-1 g_l (3)
   double* lm_gn;                               // [L][3] Gauss-Newton step of the current linearisation
   double* lm_scale;                            // [L][3] Jacobi scale (fixed after the first linearisation)

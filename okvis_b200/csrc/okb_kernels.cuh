@@ -491,12 +491,13 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       const double v0 = g0 / E0, v1 = g1 / E1, v2 = g2 / E2;
       double q0 = 0, q1 = 0, q2 = 0;        // sum_f M_f (G_f u_f)
       double hv = 0;                        // sum_f v^T M_f (v - 2 G_f v_f)
-      // every frame: M blocks of unobserved (landmark, frame) pairs are zero in memory, so no branch is
-      // needed and the loads of several frames are in flight together
-#pragma unroll 5
+      // landmarks are sorted by observing-frame range, so the visibility test is warp-coherent; M is
+      // element-major ([f][6][l]): every load is coalesced
+      const uint32_t vis = W.lm_vis[l];
       for (int f = 0; f < K; ++f) {
-        const double* Mo = W.lm_M + ((size_t)f * L + l) * 6;
-        const double M0 = Mo[0], M1 = Mo[1], M2 = Mo[2], M3 = Mo[3], M4 = Mo[4], M5 = Mo[5];
+        if (!((vis >> f) & 1u)) continue;
+        const double* Mo = W.lm_M + (size_t)(f * 6) * L + l;
+        const double M0 = Mo[0], M1 = Mo[(size_t)L], M2 = Mo[2 * (size_t)L], M3 = Mo[3 * (size_t)L], M4 = Mo[4 * (size_t)L], M5 = Mo[5 * (size_t)L];
         const double p0 = X.x - s_tws[4 * f] * X.w, p1 = X.y - s_tws[4 * f + 1] * X.w, p2 = X.z - s_tws[4 * f + 2] * X.w;
         const double* uf = s_u + 6 * f;
         const double* vf = s_v + 6 * f;
@@ -663,6 +664,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     }
     sn2 = block_sum(sn2, sh->red);
     if (tid == 0) st->cand_step_norm2_dense = sn2;
+    build_slot_ctx(W, tid, S_THREADS);        // (frame, camera) contexts of the next linearisation
   }
   PHASE_MARK(6);
 #undef PHASE_MARK
@@ -676,7 +678,7 @@ __global__ void k_prepare(const WinDev* __restrict__ wins, int win) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < W.n_obs) {
     const okb_observation ob = W.obs_list[i];
-    const size_t g = (size_t)((int)ob.pose_idx * W.CP + (int)ob.cam_idx) * W.L + ob.lm_idx;
+    const size_t g = (size_t)((int)ob.pose_idx * W.CP + (int)ob.cam_idx) * W.L + W.lm_inv[ob.lm_idx];
     W.obs_z[g] = make_double2(ob.z[0], ob.z[1]);
     W.obs_w[g] = ob.sqrt_info;
   }
@@ -702,6 +704,8 @@ __global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int rest
   __syncthreads();
   for (int i = tid; i < 7 * W.K; i += blockDim.x) W.pose_c[i] = W.pose[i];
   for (int i = tid; i < 9 * W.NSB; i += blockDim.x) W.sb_c[i] = W.sb[i];
+  __syncthreads();
+  build_slot_ctx(W, tid, blockDim.x);
   if (tid == 0) {
     SolverState* st = W.st;
     st->mode = MODE_INIT; st->done = 0; st->cur = 0;
@@ -711,7 +715,7 @@ __global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int rest
     st->cost = 0; st->initial_cost = 0; st->x_norm2 = 0;
     st->G2 = st->VHV = st->GU = st->N2 = 0; st->a = 0; st->b = 0;
     st->model_cost_change = 0; st->dogleg_step_norm = 0; st->cand_step_norm2_dense = 0; st->grad_max = 0;
-    for (int i = 0; i < 8; ++i) st->phase_ns[i] = 0;
+    for (int i = 0; i < 16; ++i) st->phase_ns[i] = 0;
     st->t_start_ns = 0; st->t_last_iter_ns = 0; st->t_iter_begin_ns = 0; st->solve_time_s = 0;
     int redo = 0;
     for (int t = 0; t < W.n_imu; ++t) redo += W.imu_cache[t].redo_count;

@@ -15,7 +15,7 @@
 namespace okb {
 
 constexpr int L1_THREADS = 128;          // k_linearize block = landmarks per CTA (x one frame)
-constexpr int A2_THREADS = 288;          // k_schur block (9 warps: 2 k-splits of 136 micro-tiles at K=10)
+constexpr int A2_THREADS = 192;          // k_schur block (6 warps at 168 registers: two CTAs per SM)
 constexpr int A2_TILE = 32;              // landmarks per Y tile
 constexpr int kPartH = 32;               // doubles per (cx, frame) record: 27 H_pp/g_p + cost + stepnorm2 + pad
 
@@ -25,6 +25,20 @@ struct SlotCtx {
   int frame;
   int valid;
 };
+static_assert(sizeof(SlotCtx) % 8 == 0, "SlotCtx is copied as doubles");
+
+// (frame, camera) contexts at the candidate poses: computed once per round by the kernel that writes the
+// candidate (k_reset / k_solve) instead of by every k_linearize CTA.
+__device__ inline void build_slot_ctx(const WinDev& W, int tid, int nthr) {
+  for (int s = tid; s < W.NS; s += nthr) {
+    const SlotInfo si = W.slots[s];
+    SlotCtx sc;
+    sc.valid = si.valid; sc.frame = s / W.CP;
+    if (si.valid) { make_slot_xf(W.pose_c + 7 * si.pose_idx, W.ext + 7 * si.ext_idx, sc.xf); cam_load(W.cams[si.cam_idx], sc.cam); }
+    else { for (int k = 0; k < 9; ++k) sc.xf.R[k] = 0; for (int k = 0; k < 3; ++k) sc.xf.t[k] = 0; cam_load(W.cams[0], sc.cam); }
+    W.slot_ctx[s] = sc;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // A1
@@ -43,29 +57,50 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
   __shared__ double sred[kPartH][L1_THREADS + 1];
   __shared__ double s_tw[3];
 
-  if (tid < CP) {
-    const SlotInfo si = W.slots[f * CP + tid];
-    SlotCtx& sc = slots[tid];
-    sc.valid = si.valid; sc.frame = f;
-    if (si.valid) { make_slot_xf(W.pose_c + 7 * si.pose_idx, W.ext + 7 * si.ext_idx, sc.xf); cam_load(W.cams[si.cam_idx], sc.cam); }
+  // Landmarks are sorted by observing-frame range: a CTA whose 4 tiles are not seen by frame f has nothing
+  // to do except publishing zeros (frame 0 also carries the candidate landmark update).
+  if (f != 0) {
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < L1_THREADS / 32; ++t) {
+      const int tile = cx * (L1_THREADS / 32) + t;
+      if (tile * 32 < L) {
+        const uint32_t tr = W.tile_range[tile];
+        any = any || ((int)(tr & 0xffu) <= f && f <= (int)(tr >> 8));
+      }
+    }
+    if (!any) {
+      if (tid < 29) W.partH[((size_t)cx * W.K + f) * kPartH + tid] = 0.0;
+      return;
+    }
+  }
+  {
+    const double* src = reinterpret_cast<const double*>(W.slot_ctx + f * CP);
+    double* dst = reinterpret_cast<double*>(slots);
+    const int n = CP * (int)(sizeof(SlotCtx) / sizeof(double));
+    for (int i = tid; i < n; i += L1_THREADS) dst[i] = src[i];
   }
   if (tid < 3) s_tw[tid] = W.pose_c[7 * f + tid];
-  __syncthreads();
-
   const int mode = st->mode, cur = st->cur;
   const bool cauchy = W.use_cauchy != 0;
   const int l = cx * L1_THREADS + tid;
 #pragma unroll
   for (int i = 0; i < 29; ++i) sred[i][tid] = 0.0;   // contributions go straight to shared memory (no live registers)
+  __syncthreads();
 
   if (l < L) {
     const bool vis = (W.lm_vis[l] >> f) & 1u;
     if (vis || f == 0) {
-      double X[4];
-      {
-        const double4 x4 = *reinterpret_cast<const double4*>(W.lm + 4 * (size_t)l);
-        X[0] = x4.x; X[1] = x4.y; X[2] = x4.z; X[3] = x4.w;
+      // all independent global loads first: the landmark, the observations of the first two cameras
+      const double4 x4 = *reinterpret_cast<const double4*>(W.lm + 4 * (size_t)l);
+      const size_t gi0 = (size_t)(f * CP) * L + l;
+      double w0 = 0.0, w1 = 0.0;
+      double2 z0 = make_double2(0, 0), z1 = make_double2(0, 0);
+      if (vis) {
+        w0 = W.obs_w[gi0]; z0 = W.obs_z[gi0];
+        if (CP > 1) { w1 = W.obs_w[gi0 + L]; z1 = W.obs_z[gi0 + L]; }
       }
+      double X[4] = {x4.x, x4.y, x4.z, x4.w};
       if (mode == MODE_STEP) {
         const double a = st->a, b = st->b;
         const double* g = W.lm_g[cur] + 3 * (size_t)l;
@@ -83,18 +118,8 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
       if (f == 0) *reinterpret_cast<double4*>(W.lm_c + 4 * (size_t)l) = make_double4(X[0], X[1], X[2], X[3]);
       if (vis) {
         double M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0, m0 = 0, m1 = 0, m2 = 0, cost = 0;
-        // the first two cameras' observations are fetched up front so that their latency overlaps
-        double pw[2] = {0.0, 0.0};
-        double2 pz[2] = {make_double2(0, 0), make_double2(0, 0)};
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          if (c < CP) { const size_t gi = (size_t)(f * CP + c) * L + l; pw[c] = W.obs_w[gi]; pz[c] = W.obs_z[gi]; }
-        for (int c = 0; c < CP; ++c) {
-          const SlotCtx& sc = slots[c];
-          const size_t gi = (size_t)(f * CP + c) * L + l;
-          const double wobs = (c < 2) ? pw[c & 1] : W.obs_w[gi];
+        auto add_obs = [&](const SlotCtx& sc, double wobs, double2 z) {
           if (wobs > 0.0 && sc.valid) {
-            const double2 z = (c < 2) ? pz[c & 1] : W.obs_z[gi];
             double r[2], A[6];
             reproj_slot<true>(sc.xf, sc.cam, X, z.x, z.y, wobs, r, A);
             const double sq = r[0] * r[0] + r[1] * r[1];
@@ -111,11 +136,17 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
             m1 += rho1 * (A[1] * r[0] + A[4] * r[1]);
             m2 += rho1 * (A[2] * r[0] + A[5] * r[1]);
           }
+        };
+        add_obs(slots[0], w0, z0);
+        if (CP > 1) add_obs(slots[1], w1, z1);
+        for (int c = 2; c < CP; ++c) {
+          const size_t gi = gi0 + (size_t)c * L;
+          add_obs(slots[c], W.obs_w[gi], W.obs_z[gi]);
         }
-        double* Mo = W.lm_M + ((size_t)f * L + l) * 6;
-        Mo[0] = M0; Mo[1] = M1; Mo[2] = M2; Mo[3] = M3; Mo[4] = M4; Mo[5] = M5;
-        double* mo = W.lm_mf + ((size_t)f * L + l) * 3;
-        mo[0] = m0; mo[1] = m1; mo[2] = m2;
+        double* Mo = W.lm_M + (size_t)(f * 6) * L + l;         // [f][e][l]: coalesced stores
+        Mo[0] = M0; Mo[(size_t)L] = M1; Mo[2 * (size_t)L] = M2; Mo[3 * (size_t)L] = M3; Mo[4 * (size_t)L] = M4; Mo[5 * (size_t)L] = M5;
+        double* mo = W.lm_mf + (size_t)(f * 3) * L + l;
+        mo[0] = m0; mo[(size_t)L] = m1; mo[2 * (size_t)L] = m2;
         // pose-block contributions: G = [w I, -[p]x], p = X - t_WS w
         const double w = X[3];
         const double p0 = X[0] - s_tw[0] * w, p1 = X[1] - s_tw[1] * w, p2 = X[2] - s_tw[2] * w;
@@ -164,11 +195,11 @@ __global__ void __launch_bounds__(128) k_lmblock(const WinDev* __restrict__ wins
   uint32_t vis = W.lm_vis[l];
   for (int f = 0; f < K; ++f) {
     if ((vis >> f) & 1u) {
-      const double* Mo = W.lm_M + ((size_t)f * L + l) * 6;
-      const double* mo = W.lm_mf + ((size_t)f * L + l) * 3;
+      const double* Mo = W.lm_M + (size_t)(f * 6) * L + l;
+      const double* mo = W.lm_mf + (size_t)(f * 3) * L + l;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) H[i] += Mo[i];
-      gl[0] -= mo[0]; gl[1] -= mo[1]; gl[2] -= mo[2];
+      for (int i = 0; i < 6; ++i) H[i] += Mo[(size_t)i * L];
+      gl[0] -= mo[0]; gl[1] -= mo[(size_t)L]; gl[2] -= mo[2 * (size_t)L];
     }
   }
   double sc3[3], E[3];
@@ -213,18 +244,35 @@ __global__ void __launch_bounds__(128) k_lmblock(const WinDev* __restrict__ wins
 }
 
 // ------------------------------------------------------------------------------------------------
-// A2
+// A2: Schur complement of the landmark blocks,  S = sum_l Y_l Y_l^T  with  Y_l = W_l L_l^-T  (6K+1 rows: the
+// pose rows of the frames that see landmark l, plus the augmented row z_l = L_l^-1 g_l that yields the
+// reduced right-hand side).
+//
+// Landmarks arrive sorted by (first, last) observing frame, so a tile of 32 consecutive landmarks only
+// touches the frames [a, b] listed in W.tile_range.  The SYRK is therefore done per 6x6 frame block over
+// the u(u+1)/2 block pairs of the tile's range (u = b-a+1) instead of the dense K(K+1)/2: one lane owns one
+// block pair (36 accumulators in registers, 12 operand doubles per 36 multiply-adds) and KS in {1,2,4,8} adjacent lanes split the
+// tile's columns.  The lane -> block-pair map only depends on (a, b); accumulators stay in registers
+// across tiles with the same range and are flushed (shuffle-reduced over the KS lanes, then added to the
+// chunk's partial in global memory by one lane, fixed order => deterministic) when the range changes.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMStride = 7;   // doubles per (landmark, frame) M block in shared memory (6 + 1 pad: 2-way bank conflicts at most)
+constexpr int kMStride = 7;    // doubles per (landmark, frame) M block in shared memory (6 + 1 pad)
 constexpr int kLiStride = 10;  // L^-1 (6) | z (3) | pad
 
-__host__ __device__ inline size_t smemA2_bytes(int K, int dcp) {
+__host__ __device__ inline int schur_ldy(int dcp) { return dcp + 2; }   // Y row stride: rows shift by 16 B across banks
+
+// acc_copies: number of copies of the chunk's Schur accumulator (packed lower triangle of the (dc+1) x (dc+1)
+// matrix) kept in shared memory, one per column split, so that flushes need no ordering between splits;
+// 0: accumulate in the chunk's global partial instead (windows with many frames).
+__host__ __device__ inline size_t schur_acc_doubles(int K) { return (size_t)(6 * K + 1) * (6 * K + 2) / 2; }
+__host__ __device__ inline size_t smemA2_bytes(int K, int dcp, int acc_copies) {
   size_t b = 0;
-  b += (size_t)3 * A2_TILE * dcp * sizeof(double);                 // Y tile, k-major
+  b += ((size_t)3 * A2_TILE * schur_ldy(dcp) + 8) * sizeof(double);   // Y tile, k-major (+ pad: the augmented-row lanes read 6 wide)
   b += (size_t)2 * K * A2_TILE * kMStride * sizeof(double);        // M tiles (double buffered)
   b += (size_t)2 * A2_TILE * kLiStride * sizeof(double);           // L^-1 | z
   b += (size_t)2 * A2_TILE * 4 * sizeof(double);                   // X
   b += (size_t)K * 4 * sizeof(double);                             // frame translations
+  b += (size_t)acc_copies * schur_acc_doubles(K) * sizeof(double);
   return b;
 }
 
@@ -235,8 +283,7 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int TPT>
-__global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restrict__ wins, int win_first) {
+__global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restrict__ wins, int win_first, int acc_copies) {
   const WinDev& W = wins[win_first + blockIdx.y];
   SolverState* st = W.st;
   if (st->done) return;
@@ -244,56 +291,43 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   if (chunk >= W.n_chunks) return;
   const int tid = threadIdx.x;
   const int K = W.K, dc = W.dc, dcp = W.dcp, L = W.L;
+  const int ldy = schur_ldy(dcp);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Yt = reinterpret_cast<double*>(smem_raw);
-  double* sMb = Yt + (size_t)3 * A2_TILE * dcp;
+  double* sMb = Yt + (size_t)3 * A2_TILE * ldy + 8;
   double* sLib = sMb + (size_t)2 * K * A2_TILE * kMStride;
   double* sXb = sLib + 2 * A2_TILE * kLiStride;
   double* tws = sXb + 2 * A2_TILE * 4;
+  double* Sp = W.partA + (size_t)chunk * W.partA_stride;
+  const bool acc_smem = acc_copies > 0;
+  const int acc_n = (dc + 1) * (dc + 2) / 2;
+  double* Sacc = acc_smem ? tws + 4 * K : Sp;     // packed lower triangles in shared memory, or the global partial itself
+  const int n_acc = acc_smem ? acc_copies * acc_n : dcp * dcp;
 
   for (int f = tid; f < K; f += A2_THREADS) {
     tws[4 * f] = W.pose_c[7 * f]; tws[4 * f + 1] = W.pose_c[7 * f + 1]; tws[4 * f + 2] = W.pose_c[7 * f + 2];
   }
+  for (int i = tid; i < n_acc; i += A2_THREADS) Sacc[i] = 0.0;
 
-  // ---- SYRK thread mapping (4x4 micro-tiles of the lower triangle of the dcp x dcp matrix)
-  const int NT = dcp >> 2;
-  const int NTT = NT * (NT + 1) / 2;
-  int KS = 1;
-  if (TPT == 1) { KS = A2_THREADS / NTT; if (KS < 1) KS = 1; }
-  const int ks = (TPT == 1) ? tid / NTT : 0;
-  int ti[TPT], tj[TPT];
-  bool syrk_on[TPT];
-  double acc[TPT][16];
-#pragma unroll
-  for (int m = 0; m < TPT; ++m) {
-    const int tt = (TPT == 1) ? tid % NTT : tid + m * A2_THREADS;
-    syrk_on[m] = (TPT == 1) ? (ks < KS) : (tt < NTT);
-    const int tq = syrk_on[m] ? tt : 0;
-    int a = (int)((sqrt(8.0 * tq + 1.0) - 1.0) * 0.5);
-    while (a * (a + 1) / 2 > tq) --a;
-    while ((a + 1) * (a + 2) / 2 <= tq) ++a;
-    ti[m] = a;
-    tj[m] = tq - a * (a + 1) / 2;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[m][i] = 0.0;
-  }
-
-  const int lm_begin = chunk * W.lm_per_chunk;
+  const int lm_begin = chunk * W.lm_per_chunk;     // multiple of A2_TILE
   const int lm_end = min(L, lm_begin + W.lm_per_chunk);
 
-  // asynchronous staging of one tile (cp.async, 8-byte elements, no registers held):
-  //   M  [f][l][6] (global, zero where unobserved) -> [ll][f][kMStride]
+  // asynchronous staging of one tile (cp.async, 8-byte elements, no registers held), frames [fa, fb] only:
+  //   M  [f][6][l] (global, zero where unobserved) -> [ll][f][kMStride]
   //   Li [l][9] -> [ll][kLiStride],  X = lm_c [l][4] -> [ll][4]
-  auto stage = [&](int base, int buf) {
+  auto stage = [&](int base, int buf, uint32_t tr) {
+    const int fa = tr & 0xffu, fb = tr >> 8;
+    if (fa > fb) { cp_async_commit(); return; }
     double* sM = sMb + (size_t)buf * K * A2_TILE * kMStride;
     double* sLi = sLib + buf * A2_TILE * kLiStride;
     double* sX = sXb + buf * A2_TILE * 4;
     const int nl = min(A2_TILE, lm_end - base);
-    for (int i = tid; i < K * A2_TILE * 6; i += A2_THREADS) {
-      const int f = i / (A2_TILE * 6), r = i % (A2_TILE * 6);
-      const int ll = r / 6, e = r % 6;
-      if (ll < nl) cp_async8(sM + ((size_t)ll * K + f) * kMStride + e, W.lm_M + ((size_t)f * L + base) * 6 + r);
+    const int nf = fb - fa + 1;
+    for (int i = tid; i < nf * A2_TILE * 6; i += A2_THREADS) {
+      const int f = fa + i / (A2_TILE * 6), r = i % (A2_TILE * 6);
+      const int e = r / A2_TILE, ll = r % A2_TILE;
+      if (ll < nl) cp_async8(sM + ((size_t)ll * K + f) * kMStride + e, W.lm_M + (size_t)(f * 6 + e) * L + base + ll);
     }
     for (int i = tid; i < A2_TILE * 9; i += A2_THREADS) {
       const int ll = i / 9, e = i % 9;
@@ -306,30 +340,144 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
     cp_async_commit();
   };
 
+  // ---- lane -> (block pair, column split) map of the current frame range: tid = kg * n_act + item
+  uint32_t cur_key = 0xffffffffu;
+  int KS = 1, kg = 0, n_act = 0, n_pairs = 0, n_pass = 1;
+  int a_off = 0, b_off = 0, row0 = 0, col0 = 0;
+  bool on = false, aug = false;
+  double acc[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+
+  auto decode = [&](int item, int fa) {
+    aug = false;
+    if (item >= n_act) { on = false; return; }
+    if (item < n_pairs) {
+      int i = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);
+      while (i * (i + 1) / 2 > item) --i;
+      while ((i + 1) * (i + 2) / 2 <= item) ++i;
+      const int j = item - i * (i + 1) / 2;
+      row0 = 6 * (fa + i); col0 = 6 * (fa + j);
+    } else {
+      aug = true;
+      row0 = dc; col0 = 6 * (fa + item - n_pairs);
+    }
+    a_off = row0; b_off = col0;
+  };
+  // Adds the accumulators to the chunk accumulator and clears them.  Called at CTA-uniform points only.
+  // Shared-memory mode: column split kg owns copy kg, so all lanes add concurrently (a later flush that
+  // touches the same element from another lane is separated by the tile loop's barriers); the copies are
+  // summed in fixed order at the end => deterministic.  Global mode: KS rounds separated by barriers.
+  // Few instructions per element: flushes run on all 12 warps at once and are issue-bound.
+  double* Ssm = tws + 4 * K;
+  auto flush_smem = [&](int copy) {
+    double* cp = Ssm + (size_t)copy * acc_n + col0;
+    if (aug) {
+      double* rp = cp + (size_t)dc * (dc + 1) / 2;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) rp[c] += acc[c];
+    } else if (row0 == col0) {        // diagonal block: lower triangle only
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double* rp = cp + (size_t)(row0 + r) * (row0 + r + 1) / 2;
+#pragma unroll
+        for (int c = 0; c <= r; ++c) rp[c] += acc[r * 6 + c];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double* rp = cp + (size_t)(row0 + r) * (row0 + r + 1) / 2;
+        double t[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) t[c] = rp[c];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) rp[c] = t[c] + acc[r * 6 + c];
+      }
+    }
+  };
+  auto flush_global = [&]() {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+      const int rr = row0 + i / 6, cc = col0 + i % 6;
+      if ((!aug || i < 6) && cc <= rr) Sp[(size_t)rr * dcp + cc] += acc[i];
+    }
+  };
+  auto flush = [&]() {
+    if (acc_smem && acc_copies >= KS) {
+      if (on) flush_smem(kg);                  // every column split has its own copy
+    } else {
+      for (int r = 0; r < KS; ++r) {           // one copy: the splits add in turn
+        if (on && kg == r) { if (acc_smem) flush_smem(0); else flush_global(); }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+  };
+
+#ifdef OKB_SCHUR_PROF     // per-phase cycle counters of chunk 0 / thread 0 (costs ~18 registers: diagnostics builds only)
+  const bool prof = (tid == 0 && chunk == 0);
+  unsigned long long t_ph = 0, ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto now = []() { return (unsigned long long)clock64(); };
+#define SCHUR_MARK(i) do { if (prof) { const unsigned long long n_ = now(); ph[i] += n_ - t_ph; t_ph = n_; } } while (0)
+  if (prof) t_ph = now();
+#else
+#define SCHUR_MARK(i) do { } while (0)
+#endif
   int buf = 0;
-  if (lm_begin < lm_end) stage(lm_begin, 0);
+  // frame ranges are fetched two tiles ahead so that no global-load latency sits on the tile loop
+  const int last_tile = (lm_end - 1) >> 5;
+  uint32_t tr_cur = (lm_begin < lm_end) ? W.tile_range[lm_begin >> 5] : 1u;
+  uint32_t tr_n1 = (lm_begin + A2_TILE < lm_end) ? W.tile_range[(lm_begin >> 5) + 1] : 1u;
+  if (lm_begin < lm_end) stage(lm_begin, 0, tr_cur);
   for (int base = lm_begin; base < lm_end; base += A2_TILE) {
+    const uint32_t tr_n2 = W.tile_range[min((base >> 5) + 2, last_tile)];
     const int nl = min(A2_TILE, lm_end - base);
     const double* sM = sMb + (size_t)buf * K * A2_TILE * kMStride;
     const double* sLi = sLib + buf * A2_TILE * kLiStride;
     const double* sX = sXb + buf * A2_TILE * 4;
     cp_async_wait_all();
     __syncthreads();                       // tile `buf` is complete; the previous SYRK has finished
-    if (base + A2_TILE < lm_end) stage(base + A2_TILE, buf ^ 1);   // overlaps with this tile's math
-    // ---- augmented row z and the padding rows of the Y tile
+    SCHUR_MARK(0);
+    if (base + A2_TILE < lm_end) stage(base + A2_TILE, buf ^ 1, tr_n1);   // overlaps with this tile's math
+    SCHUR_MARK(6);
+    const uint32_t tr = tr_cur;
+    tr_cur = tr_n1; tr_n1 = tr_n2;
+    const int fa = tr & 0xffu, fb = tr >> 8;
+    buf ^= 1;
+    if (fa > fb) continue;                 // no observed landmark in this tile (CTA-uniform)
+    const int u = fb - fa + 1;
+    if (tr != cur_key) {
+      flush();
+      cur_key = tr;
+      n_pairs = u * (u + 1) / 2;
+      n_act = n_pairs + u;
+      KS = max(1, min(8, A2_THREADS / n_act));
+      n_pass = (n_act + A2_THREADS - 1) / A2_THREADS;        // > 1 only beyond 26 frames
+      if (n_pass == 1) {
+        kg = tid / n_act;
+        decode(tid % n_act, fa);
+        on = kg < KS;
+      } else {
+        kg = 0;
+      }
+    }
+    SCHUR_MARK(1);
+    // ---- augmented row z
     if (tid < A2_TILE) {
       const int ll = tid;
-      double* yz = Yt + (size_t)(3 * ll) * dcp + dc;
-      if (ll < nl) { yz[0] = sLi[ll * kLiStride + 6]; yz[dcp] = sLi[ll * kLiStride + 7]; yz[2 * dcp] = sLi[ll * kLiStride + 8]; }
-      else { yz[0] = 0.0; yz[dcp] = 0.0; yz[2 * dcp] = 0.0; }
-      for (int r = dc + 1; r < dcp; ++r) { Yt[(size_t)(3 * ll) * dcp + r] = 0.0; Yt[(size_t)(3 * ll + 1) * dcp + r] = 0.0; Yt[(size_t)(3 * ll + 2) * dcp + r] = 0.0; }
+      double* yz = Yt + (size_t)(3 * ll) * ldy + dc;
+      const bool v = ll < nl;
+      yz[0] = v ? sLi[ll * kLiStride + 6] : 0.0;
+      yz[ldy] = v ? sLi[ll * kLiStride + 7] : 0.0;
+      yz[2 * ldy] = v ? sLi[ll * kLiStride + 8] : 0.0;
     }
-    // ---- Y_f = W_f L^-T for every (landmark, frame) pair of the tile
-    for (int pidx = tid; pidx < A2_TILE * K; pidx += A2_THREADS) {
-      const int ll = pidx / K, f = pidx % K;
-      double* y0 = Yt + (size_t)(3 * ll) * dcp + 6 * f;
-      double* y1 = y0 + dcp;
-      double* y2 = y1 + dcp;
+    // ---- Y_f = W_f L^-T for every (landmark, frame) pair of the tile, frames [fa, fb]
+    for (int pidx = tid; pidx < A2_TILE * u; pidx += A2_THREADS) {
+      const int ll = pidx / u, f = fa + pidx % u;
+      double* y0 = Yt + (size_t)(3 * ll) * ldy + 6 * f;
+      double* y1 = y0 + ldy;
+      double* y2 = y1 + ldy;
       double M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0;
       if (ll < nl) {
         const double* sp = sM + ((size_t)ll * K + f) * kMStride;
@@ -353,49 +501,57 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
         for (int i = 0; i < 6; ++i) { y0[i] = 0.0; y1[i] = 0.0; y2[i] = 0.0; }
       }
     }
+    SCHUR_MARK(2);
     __syncthreads();
-    // ---- SYRK over the tile
+    SCHUR_MARK(3);
+    // ---- SYRK over the tile's 3*nl columns
+    const int ncols = 3 * nl;
+    for (int pass = 0; pass < n_pass; ++pass) {
+      if (n_pass > 1) { on = true; decode(pass * A2_THREADS + tid, fa); }   // more block pairs than lanes
+      if (on) {
+        const double* pa = Yt + a_off + (size_t)kg * ldy;
+        const double* pb = Yt + b_off + (size_t)kg * ldy;
+        const int step = KS * ldy;
+#pragma unroll 1
+        for (int k = kg; k < ncols; k += KS) {
+          const double2 a01 = *reinterpret_cast<const double2*>(pa);
+          const double2 a23 = *reinterpret_cast<const double2*>(pa + 2);
+          const double2 a45 = *reinterpret_cast<const double2*>(pa + 4);
+          const double2 b01 = *reinterpret_cast<const double2*>(pb);
+          const double2 b23 = *reinterpret_cast<const double2*>(pb + 2);
+          const double2 b45 = *reinterpret_cast<const double2*>(pb + 4);
+          const double av[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+          const double bv[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
 #pragma unroll
-    for (int m = 0; m < TPT; ++m) {
-      if (syrk_on[m]) {
-        const int ncols = 3 * A2_TILE;
-#pragma unroll 2
-        for (int k = ks; k < ncols; k += KS) {
-          const double* row = Yt + (size_t)k * dcp;
-          const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * ti[m]);
-          const double2 a23 = *reinterpret_cast<const double2*>(row + 4 * ti[m] + 2);
-          const double2 b01 = *reinterpret_cast<const double2*>(row + 4 * tj[m]);
-          const double2 b23 = *reinterpret_cast<const double2*>(row + 4 * tj[m] + 2);
-          const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-          const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+          for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[m][i * 4 + j] += a[i] * b[j];
+            for (int j = 0; j < 6; ++j) acc[i * 6 + j] += av[i] * bv[j];
+          pa += step; pb += step;
         }
       }
+      if (n_pass > 1) flush();
     }
-    buf ^= 1;
+    SCHUR_MARK(4);
   }
   __syncthreads();
-
-  // ---- epilogue: chunk partial of the Schur accumulator (deterministic k-split order)
-  double* Sp = W.partA + (size_t)chunk * W.partA_stride;
-  for (int s = 0; s < KS; ++s) {
-#pragma unroll
-    for (int m = 0; m < TPT; ++m) {
-      if (syrk_on[m] && ks == s) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            double* p = Sp + (size_t)(4 * ti[m] + i) * dcp + 4 * tj[m] + j;
-            *p = (s == 0) ? acc[m][i * 4 + j] : (*p + acc[m][i * 4 + j]);
-          }
+  if (n_pass == 1) flush();
+  if (acc_smem) {
+    __syncthreads();
+    for (int i = tid; i < (dc + 1) * dcp; i += A2_THREADS) {
+      const int r = i / dcp, cidx = i % dcp;
+      if (cidx <= r) {
+        const int e = r * (r + 1) / 2 + cidx;
+        double v = Sacc[e];
+        for (int q = 1; q < acc_copies; ++q) v += Sacc[(size_t)q * acc_n + e];
+        Sp[i] = v;
       }
     }
-    __syncthreads();
   }
+  SCHUR_MARK(5);
+#ifdef OKB_SCHUR_PROF
+  if (prof) for (int i = 0; i < 8; ++i) st->phase_ns[8 + i] += ph[i];
+#endif
+#undef SCHUR_MARK
 }
 
 // Sums the per-chunk Schur accumulators of a window into chunk 0 (fixed order => deterministic), in
