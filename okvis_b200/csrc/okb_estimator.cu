@@ -30,6 +30,14 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
+// The transfer stream gets the highest priority: its small kernels (k_zero / k_prepare) are scheduled as soon
+// as CTA slots free up instead of waiting behind the solver kernels of other slots.
+static cudaError_t create_transfer_stream(cudaStream_t* s) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi);
+}
+
 extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
   if (!out || max_windows < 1) return OKB_ERR_INVALID_ARG;
   *out = nullptr;
@@ -51,7 +59,7 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->stream_imu, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_round, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_imu, cudaEventDisableTiming) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->stream_xfer, cudaStreamNonBlocking) != cudaSuccess ||
+      create_transfer_stream(&c->stream_xfer) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     g_create_error = "cudaStreamCreate / cudaEventCreate failed";
     delete c;
@@ -149,7 +157,26 @@ void mark_work(okb_ctx* c, int first, int count) {
 }
 }  // namespace
 
-extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) {
+// Device-side epilogue of uploads of slots [first, first+count): two kernels for the whole range.
+static int upload_finish(okb_ctx* c, int first, int count) {
+  int max_work = 1;
+  for (int i = first; i < first + count; ++i) {
+    const WinDev& W = c->host[i];
+    max_work = std::max(max_work, std::max(std::max(W.n_obs, 4 * W.L), std::max(7 * W.K, 9 * W.NSB)));
+  }
+  const int gx = std::max(1, std::min((max_work + 255) / 256, std::max(4, (8 * c->sm_count + count - 1) / count)));
+  k_zero<<<dim3(gx, count), 256, 0, c->stream_xfer>>>(c->d_wins, first);
+  k_prepare<<<dim3(gx, count), 256, 0, c->stream_xfer>>>(c->d_wins, first);
+  OKB_CUDA(c, cudaGetLastError());
+  return OKB_OK;
+}
+
+static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finish);
+
+extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) { return upload_pack(c, win, D, true); }
+
+// Host packing + H2D copies of one window (transfer stream); `finish` also launches the device epilogue.
+static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finish) {
   if (!c || !D || win < 0 || win >= c->max_windows) return OKB_ERR_INVALID_ARG;
   cudaSetDevice(c->device);
   const int K = D->n_poses, NSB = D->n_speed_bias, NE = D->n_extrinsics, L = D->n_landmarks, NC = D->n_cameras;
@@ -373,7 +400,6 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   if (S.done_idx >= 0) OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
   OKB_CUDA(c, cudaMemcpyAsync(A, H, input_bytes, cudaMemcpyHostToDevice, xs));
   OKB_CUDA(c, cudaEventRecord(S.copied, xs));
-  OKB_CUDA(c, cudaMemsetAsync(A + o_zero, 0, zero_bytes, xs));
 
   auto dp = [&](size_t o) { return reinterpret_cast<double*>(A + o); };
   W.pose = dp(o_pose); W.sb = dp(o_sb); W.ext = dp(o_ext); W.lm = dp(o_lm);
@@ -384,6 +410,7 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   W.obs_z = reinterpret_cast<double2*>(A + o_obsz);
   W.obs_w = dp(o_obsw);
   W.lm_vis = reinterpret_cast<uint32_t*>(A + o_vis);
+  W.zero_ptr = A + o_zero; W.zero_bytes = zero_bytes;
   W.lm_inv = reinterpret_cast<const uint32_t*>(A + o_inv);
   W.tile_range = reinterpret_cast<const uint32_t*>(A + o_trange);
   W.obs_list = reinterpret_cast<const okb_observation*>(A + o_obsl);
@@ -410,10 +437,9 @@ extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) 
   S.uploaded = true;
   S.h2d_bytes = input_bytes;
   OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + win, &c->host[win], sizeof(WinDev), cudaMemcpyHostToDevice, xs));
-  {
-    const int work = std::max(std::max(D->n_obs, 4 * L), std::max(7 * K, 9 * NSB));
-    k_prepare<<<(work + 255) / 256, 256, 0, xs>>>(c->d_wins, win);
-    OKB_CUDA(c, cudaGetLastError());
+  if (finish) {
+    const int rc = upload_finish(c, win, 1);
+    if (rc) return rc;
   }
   // No synchronisation here: uploads of different slots pipeline behind each other on the transfer stream
   // and overlap solver kernels of other windows.  The staging buffer belongs to this slot; its next upload
@@ -426,27 +452,25 @@ extern "C" int okb_window_upload_batch(okb_ctx* c, int first, int count, const o
   if (!c || !descs || count < 1 || first < 0 || first + count > c->max_windows) return OKB_ERR_INVALID_ARG;
   int T = host_threads > 0 ? host_threads : 8;
   T = std::max(1, std::min(T, count));
-  if (T == 1) {
-    for (int i = 0; i < count; ++i) {
-      const int rc = okb_window_upload(c, first + i, descs + i);
-      if (rc) return rc;
-    }
-    return OKB_OK;
-  }
   std::vector<int> rcs(T, OKB_OK);
-  std::vector<std::thread> th;
-  th.reserve(T);
-  for (int t = 0; t < T; ++t)
-    th.emplace_back([=, &rcs]() {
-      for (int i = t; i < count; i += T) {
-        const int rc = okb_window_upload(c, first + i, descs + i);
-        if (rc) { rcs[t] = rc; return; }
-      }
-    });
-  for (auto& x : th) x.join();
+  if (T == 1) {
+    for (int i = 0; i < count && !rcs[0]; ++i) rcs[0] = upload_pack(c, first + i, descs + i, false);
+  } else {
+    std::vector<std::thread> th;
+    th.reserve(T);
+    for (int t = 0; t < T; ++t)
+      th.emplace_back([=, &rcs]() {
+        for (int i = t; i < count; i += T) {
+          const int rc = upload_pack(c, first + i, descs + i, false);
+          if (rc) { rcs[t] = rc; return; }
+        }
+      });
+    for (auto& x : th) x.join();
+  }
   for (int t = 0; t < T; ++t)
     if (rcs[t]) return rcs[t];
-  return OKB_OK;
+  cudaSetDevice(c->device);
+  return upload_finish(c, first, count);      // one k_zero + one k_prepare for the whole range
 }
 
 // ---- optional event timing around solver kernels

@@ -86,6 +86,8 @@ struct WinDev {
   // Landmarks are stored sorted by (first, last) observing frame (okb_window_upload): tracks are runs of
   // consecutive frames, so neighbouring landmarks see nearly the same frames -> warp-coherent visibility
   // in k_linearize and block-sparse Schur tiles in k_schur.
+  unsigned char* zero_ptr;                     // region cleared by k_zero at upload
+  size_t zero_bytes;
   const uint32_t* lm_inv;                      // [L] caller's landmark index -> internal (sorted) index
   const uint32_t* tile_range;                  // [ceil(L/32)] frames seen by the tile: first | last << 8 (first > last: none)
   // per-landmark solver data

@@ -671,20 +671,30 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
 }
 
 // resets the solver state (and optionally the parameter state) of a range of windows
-// Runs once per upload (transfer stream): scatters the compact observation list into the slot-major
-// grid (zeroed by a memset just before) and keeps the uploaded state for okb_window_reset.
-__global__ void k_prepare(const WinDev* __restrict__ wins, int win) {
-  const WinDev& W = wins[win];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < W.n_obs) {
-    const okb_observation ob = W.obs_list[i];
-    const size_t g = (size_t)((int)ob.pose_idx * W.CP + (int)ob.cam_idx) * W.L + W.lm_inv[ob.lm_idx];
-    W.obs_z[g] = make_double2(ob.z[0], ob.z[1]);
-    W.obs_w[g] = ob.sqrt_info;
+// Upload epilogue on the transfer stream, batched over windows (blockIdx.y): k_zero clears each window's
+// zero region (observation grid, M blocks, caches, quality); k_prepare then scatters the compact
+// observation list into the slot-major grid and keeps the uploaded state for okb_window_reset.
+__global__ void __launch_bounds__(256) k_zero(const WinDev* __restrict__ wins, int win_first) {
+  const WinDev& W = wins[win_first + blockIdx.y];
+  uint4* p = reinterpret_cast<uint4*>(W.zero_ptr);
+  const size_t n = W.zero_bytes / sizeof(uint4);          // regions are 256-byte multiples
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+}
+__global__ void __launch_bounds__(256) k_prepare(const WinDev* __restrict__ wins, int win_first) {
+  const WinDev& W = wins[win_first + blockIdx.y];
+  const int work = max(max(W.n_obs, 4 * W.L), max(7 * W.K, 9 * W.NSB));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < work; i += gridDim.x * blockDim.x) {
+    if (i < W.n_obs) {
+      const okb_observation ob = W.obs_list[i];
+      const size_t g = (size_t)((int)ob.pose_idx * W.CP + (int)ob.cam_idx) * W.L + W.lm_inv[ob.lm_idx];
+      W.obs_z[g] = make_double2(ob.z[0], ob.z[1]);
+      W.obs_w[g] = ob.sqrt_info;
+    }
+    if (i < 7 * W.K) W.pose_init[i] = W.pose[i];
+    if (i < 9 * W.NSB) W.sb_init[i] = W.sb[i];
+    if (i < 4 * W.L) W.lm_init[i] = W.lm[i];
   }
-  if (i < 7 * W.K) W.pose_init[i] = W.pose[i];
-  if (i < 9 * W.NSB) W.sb_init[i] = W.sb[i];
-  if (i < 4 * W.L) W.lm_init[i] = W.lm[i];
 }
 
 __global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int restore_params) {

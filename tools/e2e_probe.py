@@ -35,3 +35,24 @@ for T in (2, 4, 8):
     run(2)
     t0 = time.perf_counter(); run(6); dt = time.perf_counter() - t0
     print("pipelined, %d threads: %.2f ms/step -> %.0f iter/s" % (T, dt / 6 * 1e3, 6 * Be * 10 / dt), flush=True)
+# which leg fails to overlap?
+T = 8
+def loop(n, do_up, do_down):
+    ctx.upload_batch(0, rw, T, descs); ctx.upload_batch(Be, rw, T, descs); pending = None
+    t0 = time.perf_counter()
+    tt = {"async": 0.0, "down": 0.0, "up": 0.0, "finish": 0.0}
+    for st in range(n):
+        base = (st % 2) * Be
+        a = time.perf_counter(); ctx.optimize_async(base, Be, max_iterations=10); b = time.perf_counter()
+        if do_down and pending is not None: ctx.download_batch(pending, Be, outs[pending])
+        c = time.perf_counter()
+        if do_up and st + 1 < n: ctx.upload_batch(((st + 1) % 2) * Be, rw, T, descs)
+        d = time.perf_counter()
+        ctx.optimize_finish(base, Be); e = time.perf_counter()
+        tt["async"] += b - a; tt["down"] += c - b; tt["up"] += d - c; tt["finish"] += e - d
+        pending = base
+    dt = time.perf_counter() - t0
+    return dt / n * 1e3, {k: round(v / n * 1e3, 2) for k, v in tt.items()}
+for up, down in ((False, False), (False, True), (True, False), (True, True)):
+    loop(2, up, down)
+    print("upload=%d download=%d: %.2f ms/step  %s" % (up, down, *loop(6, up, down)), flush=True)
