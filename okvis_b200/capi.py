@@ -83,7 +83,7 @@ class Context:
         out = np.zeros(16)
         self._check(lib().okb_debug_phase_ns(self._h, int(win), _p(out)))
         names = ["dense_terms", "gather", "assemble", "cholesky", "substitution", "backsub", "dogleg", "_",
-                 "schur_wait_top", "schur_stage_flush", "schur_Y", "schur_wait_Y", "schur_syrk", "schur_epilogue", "_a", "_b"]
+                 "p8", "p9", "p10", "p11", "p12", "p13", "p14", "p15"]   # OKB_SCHUR_PROF / OKB_CHOL_PROF builds: cycles
         return {n: v * 1e-3 for n, v in zip(names, out)}
 
     def h2d_bytes(self, win):

@@ -12,13 +12,23 @@ namespace okb {
 
 constexpr int CH_NB = 16;
 
-// In-place lower Cholesky of the d x d row-major matrix M (only the lower triangle is referenced
-// and written).  `panel` is shared scratch of CH_NB * ld_p doubles (ld_p >= d rounded up to 4),
-// `flag` a shared int.  Returns 0 on success, 1 on a non-positive pivot (uniform over the CTA).
-__device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, double* rdiag, int* flag) {
+// In-place lower Cholesky of the leading d x d block of the row-major matrix M (row stride ldm; only
+// the lower triangle is referenced and written).  M has nrows >= d rows: rows d..nrows-1 are carried
+// along like any sub-diagonal row, so an appended right-hand side row g^T comes out as (L^-1 g)^T -- the
+// forward substitution rides on the factorisation.  `panel` is shared scratch of CH_NB * ld_p doubles
+// (ld_p >= nrows rounded up to 4), `flag` a shared int.  Returns 0 on success, 1 on a non-positive
+// pivot (uniform over the CTA).
+__device__ inline int block_cholesky(double* M, int d, int ldm, int nrows, double* panel, int ld_p, double* rdiag, int* flag,
+                                     unsigned long long* prof = nullptr) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *flag = 0;
   __syncthreads();
+#ifdef OKB_CHOL_PROF   // cycles of thread 0 per sub-phase: diagonal block | panel solve | trailing update
+  unsigned long long t_ph = clock64();
+#define CHOL_MARK(i) do { if (tid == 0 && prof) { const unsigned long long n_ = clock64(); prof[i] += n_ - t_ph; t_ph = n_; } } while (0)
+#else
+#define CHOL_MARK(i) do { } while (0)
+#endif
   for (int kb = 0; kb < d; kb += CH_NB) {
     const int nb = min(CH_NB, d - kb);
     // ---- (1) diagonal block, warp 0, lane = row
@@ -26,7 +36,7 @@ __device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, 
       double row[CH_NB];
       const int r = kb + lane;
 #pragma unroll
-      for (int c = 0; c < CH_NB; ++c) row[c] = (lane < nb && c <= lane && c < nb) ? M[(size_t)r * d + kb + c] : ((c == lane) ? 1.0 : 0.0);
+      for (int c = 0; c < CH_NB; ++c) row[c] = (lane < nb && c <= lane && c < nb) ? M[(size_t)r * ldm + kb + c] : ((c == lane) ? 1.0 : 0.0);
       bool bad = false;
 #pragma unroll
       for (int j = 0; j < CH_NB; ++j) {
@@ -44,25 +54,27 @@ __device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, 
       }
       if (lane < nb) {
 #pragma unroll
-        for (int c = 0; c < CH_NB; ++c) if (c <= lane && c < nb) M[(size_t)r * d + kb + c] = row[c];
+        for (int c = 0; c < CH_NB; ++c) if (c <= lane && c < nb) M[(size_t)r * ldm + kb + c] = row[c];
       }
       if (bad && lane == 0) *flag = 1;
     }
     __syncthreads();
+    CHOL_MARK(0);
     if (*flag) return 1;
     const int r0 = kb + nb;            // first trailing row
-    const int n = d - r0;
+    const int n = nrows - r0;          // trailing rows (including the appended ones)
+    const int ncol = d - r0;           // trailing columns that still get factored
     if (n <= 0) break;
     // ---- (2) panel solve: X * L_d^T = A  (row per thread), result also stored k-major in `panel`
     for (int i = tid; i < n; i += nthr) {
       double x[CH_NB];
-      double* arow = M + (size_t)(r0 + i) * d + kb;
+      double* arow = M + (size_t)(r0 + i) * ldm + kb;
 #pragma unroll
       for (int c = 0; c < CH_NB; ++c) x[c] = (c < nb) ? arow[c] : 0.0;
 #pragma unroll
       for (int j = 0; j < CH_NB; ++j) {
         if (j < nb) {
-          const double* lrow = M + (size_t)(kb + j) * d + kb;
+          const double* lrow = M + (size_t)(kb + j) * ldm + kb;
           double s = x[j];
 #pragma unroll
           for (int c = 0; c < CH_NB; ++c) if (c < j) s -= x[c] * lrow[c];
@@ -79,6 +91,7 @@ __device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, 
     const int n4 = (n + 3) & ~3;
     for (int e = tid; e < CH_NB * (n4 - n); e += nthr) panel[(size_t)(e / (n4 - n)) * ld_p + n + e % (n4 - n)] = 0.0;
     __syncthreads();
+    CHOL_MARK(1);
     // ---- (3) trailing update: A[r0+i][r0+j] -= sum_c P[c][i] P[c][j], i >= j, 4x4 micro-tiles
     const int nt = n4 >> 2;
     const int ntt = nt * (nt + 1) / 2;
@@ -109,39 +122,20 @@ __device__ inline int block_cholesky(double* M, int d, double* panel, int ld_p, 
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int i = 4 * ti + ii, j = 4 * tj + jj;
-          if (i < n && j <= i) M[(size_t)(r0 + i) * d + r0 + j] -= acc[ii * 4 + jj];
+          if (i < n && j <= i && j < ncol) M[(size_t)(r0 + i) * ldm + r0 + j] -= acc[ii * 4 + jj];
         }
     }
     __syncthreads();
+    CHOL_MARK(2);
   }
+#undef CHOL_MARK
   return 0;
 }
 
-// Solves L L^T x = b in place in `x` (shared memory vector of length d, initialised with b).
-__device__ inline void block_cholesky_solve(const double* M, int d, const double* rdiag, double* x) {
+// Solves L^T u = z in place in `x` (shared memory vector of length d holding z = L^-1 b, which the
+// factorisation produced in the appended row).
+__device__ inline void block_cholesky_backward(const double* M, int d, int ldm, const double* rdiag, double* x) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  // forward: L z = b
-  for (int kb = 0; kb < d; kb += CH_NB) {
-    const int nb = min(CH_NB, d - kb);
-    if (warp == 0) {
-      double t = (lane < nb) ? x[kb + lane] : 0.0;
-      for (int j = 0; j < nb; ++j) {
-        const double zj = __shfl_sync(0xffffffffu, t, j) * rdiag[kb + j];
-        if (lane == j) t = zj;
-        else if (lane > j && lane < nb) t -= M[(size_t)(kb + lane) * d + kb + j] * zj;
-      }
-      if (lane < nb) x[kb + lane] = t;
-    }
-    __syncthreads();
-    for (int i = kb + nb + tid; i < d; i += nthr) {
-      const double* lrow = M + (size_t)i * d + kb;
-      double s = x[i];
-      for (int c = 0; c < nb; ++c) s -= lrow[c] * x[kb + c];
-      x[i] = s;
-    }
-    __syncthreads();
-  }
-  // backward: L^T u = z
   const int nblocks = (d + CH_NB - 1) / CH_NB;
   for (int bi = nblocks - 1; bi >= 0; --bi) {
     const int kb = bi * CH_NB;
@@ -151,14 +145,14 @@ __device__ inline void block_cholesky_solve(const double* M, int d, const double
       for (int j = nb - 1; j >= 0; --j) {
         const double uj = __shfl_sync(0xffffffffu, t, j) * rdiag[kb + j];
         if (lane == j) t = uj;
-        else if (lane < j) t -= M[(size_t)(kb + j) * d + kb + lane] * uj;
+        else if (lane < j) t -= M[(size_t)(kb + j) * ldm + kb + lane] * uj;
       }
       if (lane < nb) x[kb + lane] = t;
     }
     __syncthreads();
     for (int i = tid; i < kb; i += nthr) {
       double s = x[i];
-      for (int c = 0; c < nb; ++c) s -= M[(size_t)(kb + c) * d + i] * x[kb + c];
+      for (int c = 0; c < nb; ++c) s -= M[(size_t)(kb + c) * ldm + i] * x[kb + c];
       x[i] = s;
     }
     __syncthreads();

@@ -257,7 +257,7 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
   const size_t o_Hd = P.take(sizeof(double) * (size_t)d * d);
   for (int b = 0; b < 2; ++b) { o_gd[b] = P.take(sizeof(double) * d); o_Ed[b] = P.take(sizeof(double) * d); }
   const size_t o_ud = P.take(sizeof(double) * d), o_scd = P.take(sizeof(double) * d);
-  const size_t o_chol = P.take(sizeof(double) * (size_t)d * d);
+  const size_t o_chol = P.take(sizeof(double) * (size_t)(d + 1) * (d + 1));
   // one contiguous region zeroed by a single memset per upload
   const size_t o_zero = P.total;
   const size_t o_obsz = P.take(sizeof(double2) * (size_t)L * NS);

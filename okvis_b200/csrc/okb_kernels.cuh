@@ -166,8 +166,8 @@ __host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_im
   b += (size_t)K * 4 * sizeof(double);                     // committed frame translations
   b += (size_t)3 * (n_marg > 0 ? n_marg : 1) * sizeof(double);   // marg: dchi, e, Jte
   b = (b + 31) & ~(size_t)31;
-  b += (size_t)CH_NB * ((d + 3) & ~3) * sizeof(double);      // Cholesky panel (k-major)
-  b += chol_in_smem ? (size_t)d * d * sizeof(double) : 16;   // the reduced system itself
+  b += (size_t)CH_NB * ((d + 1 + 3) & ~3) * sizeof(double);  // Cholesky panel (k-major)
+  b += chol_in_smem ? (size_t)(d + 1) * (d + 1) * sizeof(double) : 16;   // the reduced system + appended rhs row
   return b;
 }
 
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   double* s_dchi = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
   double* s_me = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
   double* s_mJte = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
-  const int ld_p = (d + 3) & ~3;
+  const int ld_p = (d + 1 + 3) & ~3;
   off = (off + 31) & ~(size_t)31;
   double* s_panel = reinterpret_cast<double*>(smem_raw + off); off += (size_t)CH_NB * ld_p * 8;
   double* s_big = reinterpret_cast<double*>(smem_raw + off);   // the reduced system (when it fits)
@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     // reduced system M = Hd + mu E - [Sacc], rhs = g - [sum Y z]
     double* Mx = chol_in_smem ? s_big : W.chol;
     const double mu = st->mu;
+    const int ldm = d + 1;                     // row d carries the right-hand side through the factorisation
     for (int i = tid; i < d * d; i += S_THREADS) {
       const int r0 = i / d, c0 = i % d;
       double v = Hd[i];
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
         const int rr = r0 >= c0 ? r0 : c0, cc = r0 >= c0 ? c0 : r0;
         v -= W.partA[(size_t)rr * dcp + cc];     // chunk partials were summed by k_reduce_partials
       }
-      Mx[i] = v;
+      Mx[(size_t)r0 * ldm + c0] = v;
     }
     for (int i = tid; i < d; i += S_THREADS) {
       double v = s_g[i];
@@ -461,17 +462,18 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
         v -= W.partA[(size_t)dc * dcp + i];
       }
       s_rhs[i] = v;
+      Mx[(size_t)d * ldm + i] = v;
     }
     __syncthreads();
     PHASE_MARK(2);
-    // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh)
+    // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh); row d comes out as z = L^-1 rhs
     int chol_fail = sh->fail;
-    if (!chol_fail) chol_fail = block_cholesky(Mx, d, s_panel, ld_p, s_col, &sh->chol_flag);
+    if (!chol_fail) chol_fail = block_cholesky(Mx, d, ldm, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8);
     PHASE_MARK(3);
     if (!chol_fail) {
-      for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = s_rhs[i];
+      for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = Mx[(size_t)d * ldm + i];
       __syncthreads();
-      block_cholesky_solve(Mx, d, s_col, s_tmp);
+      block_cholesky_backward(Mx, d, ldm, s_col, s_tmp);
       for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
       __syncthreads();
     }
