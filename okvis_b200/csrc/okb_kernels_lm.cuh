@@ -74,6 +74,28 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
       return;
     }
   }
+  // All global loads of this thread are issued before anything waits on them (one memory round trip instead
+  // of a chain visibility -> landmark -> observations): the visibility mask, the landmark, the observations of
+  // the first two cameras and, in STEP mode, the stored step.  Speculative for unobserved pairs; with
+  // sorted landmarks those are few inside a CTA that is not skipped.
+  const int mode = st->mode, cur = st->cur;
+  const bool cauchy = W.use_cauchy != 0;
+  const int l = cx * L1_THREADS + tid;
+  const int lc = min(l, L - 1);
+  const uint32_t vmask = W.lm_vis[lc];
+  const double4 x4 = *reinterpret_cast<const double4*>(W.lm + 4 * (size_t)lc);
+  const size_t gi0 = (size_t)(f * CP) * L + lc;
+  double w0 = W.obs_w[gi0], w1 = 0.0;
+  double2 z0 = W.obs_z[gi0], z1 = make_double2(0, 0);
+  if (CP > 1) { w1 = W.obs_w[gi0 + L]; z1 = W.obs_z[gi0 + L]; }
+  double sg[3] = {0, 0, 0}, sE[3] = {1, 1, 1}, sgn[3] = {0, 0, 0};
+  if (mode == MODE_STEP) {
+    const double* g = W.lm_g[cur] + 3 * (size_t)lc;
+    const double* E = W.lm_E[cur] + 3 * (size_t)lc;
+    const double* gn = W.lm_gn + 3 * (size_t)lc;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { sg[c] = g[c]; sE[c] = E[c]; sgn[c] = gn[c]; }
+  }
   {
     const double* src = reinterpret_cast<const double*>(W.slot_ctx + f * CP);
     double* dst = reinterpret_cast<double*>(slots);
@@ -81,35 +103,20 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
     for (int i = tid; i < n; i += L1_THREADS) dst[i] = src[i];
   }
   if (tid < 3) s_tw[tid] = W.pose_c[7 * f + tid];
-  const int mode = st->mode, cur = st->cur;
-  const bool cauchy = W.use_cauchy != 0;
-  const int l = cx * L1_THREADS + tid;
 #pragma unroll
   for (int i = 0; i < 29; ++i) sred[i][tid] = 0.0;   // contributions go straight to shared memory (no live registers)
   __syncthreads();
 
   if (l < L) {
-    const bool vis = (W.lm_vis[l] >> f) & 1u;
+    const bool vis = (vmask >> f) & 1u;
     if (vis || f == 0) {
-      // all independent global loads first: the landmark, the observations of the first two cameras
-      const double4 x4 = *reinterpret_cast<const double4*>(W.lm + 4 * (size_t)l);
-      const size_t gi0 = (size_t)(f * CP) * L + l;
-      double w0 = 0.0, w1 = 0.0;
-      double2 z0 = make_double2(0, 0), z1 = make_double2(0, 0);
-      if (vis) {
-        w0 = W.obs_w[gi0]; z0 = W.obs_z[gi0];
-        if (CP > 1) { w1 = W.obs_w[gi0 + L]; z1 = W.obs_z[gi0 + L]; }
-      }
       double X[4] = {x4.x, x4.y, x4.z, x4.w};
       if (mode == MODE_STEP) {
         const double a = st->a, b = st->b;
-        const double* g = W.lm_g[cur] + 3 * (size_t)l;
-        const double* E = W.lm_E[cur] + 3 * (size_t)l;
-        const double* gn = W.lm_gn + 3 * (size_t)l;
         double dn = 0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const double dlt = a * g[c] / E[c] + b * gn[c];
+          const double dlt = a * sg[c] / sE[c] + b * sgn[c];
           X[c] += dlt;
           dn += dlt * dlt;
         }
@@ -167,13 +174,20 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
       }
     }
   }
-  // ---- CTA reduction of the 29 used values (fixed order -> deterministic)
+  // ---- CTA reduction of the 29 used values (fixed order -> deterministic): 4 threads per value, each sums
+  // 32 of the 128 columns serially (no shuffles), then two shuffle steps combine the four partials
   __syncthreads();
-  for (int e = warp; e < 29; e += L1_THREADS / 32) {
-    double s = sred[e][lane] + sred[e][lane + 32] + sred[e][lane + 64] + sred[e][lane + 96];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) W.partH[((size_t)cx * W.K + f) * kPartH + e] = s;
+  {
+    const int e = tid >> 2, q = tid & 3;
+    double s = 0.0;
+    if (e < 29) {
+      const double* row = &sred[e][q * 32];
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) s += row[(i + 4 * q) & 31];     // rotated start: the four partial sums hit different banks
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (e < 29 && q == 0) W.partH[((size_t)cx * W.K + f) * kPartH + e] = s;
   }
 }
 
