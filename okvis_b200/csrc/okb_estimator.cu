@@ -241,14 +241,15 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
   const size_t o_pose_i = P.take(sizeof(double) * 7 * K), o_sb_i = P.take(sizeof(double) * 9 * std::max(NSB, 1));
   const size_t o_lm_i = P.take(sizeof(double) * 4 * L);
   const size_t o_pose_c = P.take(sizeof(double) * 7 * K), o_sb_c = P.take(sizeof(double) * 9 * std::max(NSB, 1));
-  const size_t o_lm_c = P.take(sizeof(double) * 4 * L);
+  const int Lp = (L + 31) & ~31;
+  const size_t o_lm_c = P.take(sizeof(double) * 4 * Lp);
   size_t o_lmg[2], o_lmE[2], o_gd[2], o_Ed[2];
   for (int b = 0; b < 2; ++b) { o_lmg[b] = P.take(sizeof(double) * 3 * L); o_lmE[b] = P.take(sizeof(double) * 3 * L); }
   const size_t o_Rinv = P.take(sizeof(double) * 6 * L);
   const size_t o_slotctx = P.take(sizeof(SlotCtx) * NSP);
-  const size_t o_mf = P.take(sizeof(double) * 3 * (size_t)L * K);
+  const size_t o_mf = P.take(sizeof(double) * 3 * (size_t)Lp * K);
   const size_t o_gn = P.take(sizeof(double) * 3 * L);
-  const size_t o_Li = P.take(sizeof(double) * 9 * L);
+  const size_t o_Li = P.take(sizeof(double) * 9 * Lp);
   const size_t o_scale = P.take(sizeof(double) * 3 * L);
   const int pstride = dcp * dcp;
   const int n_cx = (L + L1_THREADS - 1) / L1_THREADS;
@@ -262,7 +263,7 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
   const size_t o_zero = P.total;
   const size_t o_obsz = P.take(sizeof(double2) * (size_t)L * NS);
   const size_t o_obsw = P.take(sizeof(double) * (size_t)L * NS);
-  const size_t o_M = P.take(sizeof(double) * 6 * (size_t)L * K);
+  const size_t o_M = P.take(sizeof(double) * 6 * (size_t)Lp * K);
   const size_t o_quality = P.take(sizeof(double) * L);
   const size_t o_cache = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
   const size_t o_cache_i = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
@@ -410,6 +411,7 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
   W.obs_z = reinterpret_cast<double2*>(A + o_obsz);
   W.obs_w = dp(o_obsw);
   W.lm_vis = reinterpret_cast<uint32_t*>(A + o_vis);
+  W.Lp = Lp;
   W.zero_ptr = A + o_zero; W.zero_bytes = zero_bytes;
   W.lm_inv = reinterpret_cast<const uint32_t*>(A + o_inv);
   W.tile_range = reinterpret_cast<const uint32_t*>(A + o_trange);

@@ -62,6 +62,7 @@ struct SlotCtx;   // per (frame, camera) transform + intrinsics at the candidate
 
 struct WinDev {
   int K, NSB, NE, L, NC;
+  int Lp;              // L rounded up to whole tiles of 32: leading dimension of lm_M / lm_mf, rows of lm_Li / lm_c (bulk copies stay aligned)
   int CP;              // cameras per frame padded to a power of two
   int NS;              // slots = K * CP  (slot = frame * CP + cam)
   int NG;              // slot groups of 32 lanes
@@ -94,8 +95,8 @@ struct WinDev {
   double* lm_g[2];                             // [L][3] gradient block (double buffered: cur / speculative)
   double* lm_E[2];                             // [L][3] metric (Ceres diagonal^2 / scale^2)
   double* lm_Rinv;                             // [L][6] (H_ll + mu E)^-1, symmetric packed
-  double* lm_M;                                // [K][6][L] per-frame sum of rho' A^T A (element-major: coalesced per landmark)
-  double* lm_mf;                               // [K][3][L] per-frame sum of rho' A^T r
+  double* lm_M;                                // [K][6][Lp] per-frame sum of rho' A^T A (element-major: coalesced per landmark)
+  double* lm_mf;                               // [K][3][Lp] per-frame sum of rho' A^T r
   SlotCtx* slot_ctx;                           // [NS] built by k_reset / k_solve whenever the candidate poses change
   double* lm_Li;                               // [L][9] L^-1 of (H_ll + mu E) (6) and z = L^-1 g_l (3)
   double* lm_gn;                               // [L][3] Gauss-Newton step of the current linearisation

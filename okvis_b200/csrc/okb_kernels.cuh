@@ -498,8 +498,9 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       const uint32_t vis = W.lm_vis[l];
       for (int f = 0; f < K; ++f) {
         if (!((vis >> f) & 1u)) continue;
-        const double* Mo = W.lm_M + (size_t)(f * 6) * L + l;
-        const double M0 = Mo[0], M1 = Mo[(size_t)L], M2 = Mo[2 * (size_t)L], M3 = Mo[3 * (size_t)L], M4 = Mo[4 * (size_t)L], M5 = Mo[5 * (size_t)L];
+        const size_t Lp = (size_t)W.Lp;
+        const double* Mo = W.lm_M + (size_t)(f * 6) * Lp + l;
+        const double M0 = Mo[0], M1 = Mo[Lp], M2 = Mo[2 * Lp], M3 = Mo[3 * Lp], M4 = Mo[4 * Lp], M5 = Mo[5 * Lp];
         const double p0 = X.x - s_tws[4 * f] * X.w, p1 = X.y - s_tws[4 * f + 1] * X.w, p2 = X.z - s_tws[4 * f + 2] * X.w;
         const double* uf = s_u + 6 * f;
         const double* vf = s_v + 6 * f;

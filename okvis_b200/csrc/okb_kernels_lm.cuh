@@ -150,10 +150,11 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
           const size_t gi = gi0 + (size_t)c * L;
           add_obs(slots[c], W.obs_w[gi], W.obs_z[gi]);
         }
-        double* Mo = W.lm_M + (size_t)(f * 6) * L + l;         // [f][e][l]: coalesced stores
-        Mo[0] = M0; Mo[(size_t)L] = M1; Mo[2 * (size_t)L] = M2; Mo[3 * (size_t)L] = M3; Mo[4 * (size_t)L] = M4; Mo[5 * (size_t)L] = M5;
-        double* mo = W.lm_mf + (size_t)(f * 3) * L + l;
-        mo[0] = m0; mo[(size_t)L] = m1; mo[2 * (size_t)L] = m2;
+        const size_t Lp = (size_t)W.Lp;
+        double* Mo = W.lm_M + (size_t)(f * 6) * Lp + l;        // [f][e][l]: coalesced stores
+        Mo[0] = M0; Mo[Lp] = M1; Mo[2 * Lp] = M2; Mo[3 * Lp] = M3; Mo[4 * Lp] = M4; Mo[5 * Lp] = M5;
+        double* mo = W.lm_mf + (size_t)(f * 3) * Lp + l;
+        mo[0] = m0; mo[Lp] = m1; mo[2 * Lp] = m2;
         // pose-block contributions: G = [w I, -[p]x], p = X - t_WS w
         const double w = X[3];
         const double p0 = X[0] - s_tw[0] * w, p1 = X[1] - s_tw[1] * w, p2 = X[2] - s_tw[2] * w;
@@ -209,11 +210,12 @@ __global__ void __launch_bounds__(128) k_lmblock(const WinDev* __restrict__ wins
   uint32_t vis = W.lm_vis[l];
   for (int f = 0; f < K; ++f) {
     if ((vis >> f) & 1u) {
-      const double* Mo = W.lm_M + (size_t)(f * 6) * L + l;
-      const double* mo = W.lm_mf + (size_t)(f * 3) * L + l;
+      const size_t Lp = (size_t)W.Lp;
+      const double* Mo = W.lm_M + (size_t)(f * 6) * Lp + l;
+      const double* mo = W.lm_mf + (size_t)(f * 3) * Lp + l;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) H[i] += Mo[(size_t)i * L];
-      gl[0] -= mo[0]; gl[1] -= mo[(size_t)L]; gl[2] -= mo[2 * (size_t)L];
+      for (int i = 0; i < 6; ++i) H[i] += Mo[(size_t)i * Lp];
+      gl[0] -= mo[0]; gl[1] -= mo[Lp]; gl[2] -= mo[2 * Lp];
     }
   }
   double sc3[3], E[3];
@@ -270,8 +272,7 @@ __global__ void __launch_bounds__(128) k_lmblock(const WinDev* __restrict__ wins
 // across tiles with the same range and are flushed (shuffle-reduced over the KS lanes, then added to the
 // chunk's partial in global memory by one lane, fixed order => deterministic) when the range changes.
 // ------------------------------------------------------------------------------------------------
-constexpr int kMStride = 7;    // doubles per (landmark, frame) M block in shared memory (6 + 1 pad)
-constexpr int kLiStride = 10;  // L^-1 (6) | z (3) | pad
+constexpr int kLiStride = 9;   // L^-1 (6) | z (3), as in global memory (one bulk copy per tile)
 
 __host__ __device__ inline int schur_ldy(int dcp) { return dcp + 2; }   // Y row stride: rows shift by 16 B across banks
 
@@ -280,9 +281,9 @@ __host__ __device__ inline int schur_ldy(int dcp) { return dcp + 2; }   // Y row
 // 0: accumulate in the chunk's global partial instead (windows with many frames).
 __host__ __device__ inline size_t schur_acc_doubles(int K) { return (size_t)(6 * K + 1) * (6 * K + 2) / 2; }
 __host__ __device__ inline size_t smemA2_bytes(int K, int dcp, int acc_copies) {
-  size_t b = 0;
+  size_t b = 16;                                                    // two mbarriers (TMA completion per buffer)
   b += ((size_t)3 * A2_TILE * schur_ldy(dcp) + 8) * sizeof(double);   // Y tile, k-major (+ pad: the augmented-row lanes read 6 wide)
-  b += (size_t)2 * K * A2_TILE * kMStride * sizeof(double);        // M tiles (double buffered)
+  b += (size_t)2 * K * 6 * A2_TILE * sizeof(double);               // M tiles [f][e][ll] (double buffered)
   b += (size_t)2 * A2_TILE * kLiStride * sizeof(double);           // L^-1 | z
   b += (size_t)2 * A2_TILE * 4 * sizeof(double);                   // X
   b += (size_t)K * 4 * sizeof(double);                             // frame translations
@@ -290,12 +291,29 @@ __host__ __device__ inline size_t smemA2_bytes(int K, int dcp, int acc_copies) {
   return b;
 }
 
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
+// ---- TMA bulk copies (cp.async.bulk, 1-D) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restrict__ wins, int win_first, int acc_copies) {
   const WinDev& W = wins[win_first + blockIdx.y];
@@ -308,9 +326,10 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   const int ldy = schur_ldy(dcp);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* Yt = reinterpret_cast<double*>(smem_raw);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);            // [2]: TMA completion of tile buffer 0 / 1
+  double* Yt = reinterpret_cast<double*>(smem_raw + 16);
   double* sMb = Yt + (size_t)3 * A2_TILE * ldy + 8;
-  double* sLib = sMb + (size_t)2 * K * A2_TILE * kMStride;
+  double* sLib = sMb + (size_t)2 * K * 6 * A2_TILE;
   double* sXb = sLib + 2 * A2_TILE * kLiStride;
   double* tws = sXb + 2 * A2_TILE * 4;
   double* Sp = W.partA + (size_t)chunk * W.partA_stride;
@@ -327,31 +346,38 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   const int lm_begin = chunk * W.lm_per_chunk;     // multiple of A2_TILE
   const int lm_end = min(L, lm_begin + W.lm_per_chunk);
 
-  // asynchronous staging of one tile (cp.async, 8-byte elements, no registers held), frames [fa, fb] only:
-  //   M  [f][6][l] (global, zero where unobserved) -> [ll][f][kMStride]
-  //   Li [l][9] -> [ll][kLiStride],  X = lm_c [l][4] -> [ll][4]
+  // Asynchronous staging of one tile by the TMA engine (cp.async.bulk, issued by warp 0, completion on
+  // mbar[buf]); frames [fa, fb] only.  Global and shared layouts agree, so every piece is one contiguous copy:
+  //   M  [f][6][Lp] -> sM[f][6][32] : 256-byte rows, one copy per (frame, element)
+  //   Li [l][9] -> sLi[32][9] (2304 B),  X = lm_c [l][4] -> sX[32][4] (1024 B)
+  // Rows beyond the chunk's last landmark read allocated padding (Lp) and are never used.
+  const int warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_proxy_async(); }
+  __syncthreads();
+  uint32_t phase_bits = 0;      // bit b: parity to wait for on mbar[b]
   auto stage = [&](int base, int buf, uint32_t tr) {
     const int fa = tr & 0xffu, fb = tr >> 8;
-    if (fa > fb) { cp_async_commit(); return; }
-    double* sM = sMb + (size_t)buf * K * A2_TILE * kMStride;
+    if (fa > fb || warp != 0) return;
+    double* sM = sMb + (size_t)buf * K * 6 * A2_TILE;
     double* sLi = sLib + buf * A2_TILE * kLiStride;
     double* sX = sXb + buf * A2_TILE * 4;
-    const int nl = min(A2_TILE, lm_end - base);
-    const int nf = fb - fa + 1;
-    for (int i = tid; i < nf * A2_TILE * 6; i += A2_THREADS) {
-      const int f = fa + i / (A2_TILE * 6), r = i % (A2_TILE * 6);
-      const int e = r / A2_TILE, ll = r % A2_TILE;
-      if (ll < nl) cp_async8(sM + ((size_t)ll * K + f) * kMStride + e, W.lm_M + (size_t)(f * 6 + e) * L + base + ll);
+    const int rows = (fb - fa + 1) * 6;
+    if (lane == 0) {
+      fence_proxy_async();      // the buffer was last read through the generic proxy (previous tile's Y phase)
+      mbar_arrive_expect_tx(&mbar[buf], (uint32_t)(rows * A2_TILE * 8 + A2_TILE * kLiStride * 8 + A2_TILE * 4 * 8));
     }
-    for (int i = tid; i < A2_TILE * 9; i += A2_THREADS) {
-      const int ll = i / 9, e = i % 9;
-      if (ll < nl) cp_async8(sLi + ll * kLiStride + e, W.lm_Li + 9 * (size_t)base + i);
+    __syncwarp();
+    const size_t Lp = (size_t)W.Lp;
+    for (int r = lane; r < rows + 2; r += 32) {
+      if (r < rows) {
+        const int fe = fa * 6 + r;
+        bulk_g2s(sM + (size_t)fe * A2_TILE, W.lm_M + (size_t)fe * Lp + base, A2_TILE * 8, &mbar[buf]);
+      } else if (r == rows) {
+        bulk_g2s(sLi, W.lm_Li + (size_t)kLiStride * base, A2_TILE * kLiStride * 8, &mbar[buf]);
+      } else {
+        bulk_g2s(sX, W.lm_c + 4 * (size_t)base, A2_TILE * 4 * 8, &mbar[buf]);
+      }
     }
-    for (int i = tid; i < A2_TILE * 4; i += A2_THREADS) {
-      const int ll = i / 4;
-      if (ll < nl) cp_async8(sX + i, W.lm_c + 4 * (size_t)base + i);
-    }
-    cp_async_commit();
   };
 
   // ---- lane -> (block pair, column split) map of the current frame range: tid = kg * n_act + item
@@ -447,11 +473,14 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   for (int base = lm_begin; base < lm_end; base += A2_TILE) {
     const uint32_t tr_n2 = W.tile_range[min((base >> 5) + 2, last_tile)];
     const int nl = min(A2_TILE, lm_end - base);
-    const double* sM = sMb + (size_t)buf * K * A2_TILE * kMStride;
+    const double* sM = sMb + (size_t)buf * K * 6 * A2_TILE;
     const double* sLi = sLib + buf * A2_TILE * kLiStride;
     const double* sX = sXb + buf * A2_TILE * 4;
-    cp_async_wait_all();
-    __syncthreads();                       // tile `buf` is complete; the previous SYRK has finished
+    if ((tr_cur & 0xffu) <= (tr_cur >> 8)) {           // this tile was staged: wait for its bytes
+      mbar_wait(&mbar[buf], (phase_bits >> buf) & 1u);
+      phase_bits ^= 1u << buf;
+    }
+    __syncthreads();                       // the previous SYRK has finished (Y tile and the other buffer are free)
     SCHUR_MARK(0);
     if (base + A2_TILE < lm_end) stage(base + A2_TILE, buf ^ 1, tr_n1);   // overlaps with this tile's math
     SCHUR_MARK(6);
@@ -488,14 +517,14 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
     }
     // ---- Y_f = W_f L^-T for every (landmark, frame) pair of the tile, frames [fa, fb]
     for (int pidx = tid; pidx < A2_TILE * u; pidx += A2_THREADS) {
-      const int ll = pidx / u, f = fa + pidx % u;
+      const int ll = pidx % A2_TILE, f = fa + pidx / A2_TILE;      // landmark fastest: conflict-free reads of sM
       double* y0 = Yt + (size_t)(3 * ll) * ldy + 6 * f;
       double* y1 = y0 + ldy;
       double* y2 = y1 + ldy;
       double M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0;
       if (ll < nl) {
-        const double* sp = sM + ((size_t)ll * K + f) * kMStride;
-        M0 = sp[0]; M1 = sp[1]; M2 = sp[2]; M3 = sp[3]; M4 = sp[4]; M5 = sp[5];
+        const double* sp = sM + (size_t)(f * 6) * A2_TILE + ll;
+        M0 = sp[0]; M1 = sp[A2_TILE]; M2 = sp[2 * A2_TILE]; M3 = sp[3 * A2_TILE]; M4 = sp[4 * A2_TILE]; M5 = sp[5 * A2_TILE];
       }
       if (M0 != 0.0 || M3 != 0.0 || M5 != 0.0) {
         const double* Li = sLi + ll * kLiStride;
