@@ -391,7 +391,8 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
 
   auto decode = [&](int item, int fa) {
     aug = false;
-    if (item >= n_act) { on = false; return; }
+    on = item < n_act;
+    if (!on) return;
     if (item < n_pairs) {
       int i = (int)((sqrtf(8.0f * (float)item + 1.0f) - 1.0f) * 0.5f);
       while (i * (i + 1) / 2 > item) --i;
@@ -442,15 +443,16 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
       if ((!aug || i < 6) && cc <= rr) Sp[(size_t)rr * dcp + cc] += acc[i];
     }
   };
+  // The KS column splits of a block pair are adjacent lanes of one warp: they are summed with shuffles (fixed
+  // order) and the kg == 0 lane adds the result to the accumulator -- no barrier, one writer per element.
   auto flush = [&]() {
-    if (acc_smem && acc_copies >= KS) {
-      if (on) flush_smem(kg);                  // every column split has its own copy
-    } else {
-      for (int r = 0; r < KS; ++r) {           // one copy: the splits add in turn
-        if (on && kg == r) { if (acc_smem) flush_smem(0); else flush_global(); }
-        __syncthreads();
-      }
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+      double v = acc[i];
+      for (int o = 1; o < KS; ++o) v += __shfl_down_sync(0xffffffffu, acc[i], o);
+      acc[i] = v;
     }
+    if (on && kg == 0) { if (acc_smem) flush_smem(0); else flush_global(); }
 #pragma unroll
     for (int i = 0; i < 36; ++i) acc[i] = 0.0;
   };
@@ -495,14 +497,19 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
       cur_key = tr;
       n_pairs = u * (u + 1) / 2;
       n_act = n_pairs + u;
-      KS = max(1, min(8, A2_THREADS / n_act));
-      n_pass = (n_act + A2_THREADS - 1) / A2_THREADS;        // > 1 only beyond 26 frames
-      if (n_pass == 1) {
-        kg = tid / n_act;
-        decode(tid % n_act, fa);
-        on = kg < KS;
-      } else {
-        kg = 0;
+      // block pairs are dealt to the warps (ipw per warp); inside a warp lane = pair * KS + split
+      constexpr int NW = A2_THREADS / 32;
+      const int ipw = (n_act + NW - 1) / NW;
+      if (ipw <= 32) {
+        n_pass = 1;
+        KS = max(1, min(8, 32 / ipw));
+        kg = lane % KS;
+        const int il = lane / KS;
+        decode(warp * ipw + il, fa);
+        on = on && il < ipw;
+      } else {                     // more block pairs than lanes (beyond 17 frames): one pair per lane, several passes
+        n_pass = (n_act + A2_THREADS - 1) / A2_THREADS;
+        KS = 1; kg = 0;
       }
     }
     SCHUR_MARK(1);
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
     // ---- SYRK over the tile's 3*nl columns
     const int ncols = 3 * nl;
     for (int pass = 0; pass < n_pass; ++pass) {
-      if (n_pass > 1) { on = true; decode(pass * A2_THREADS + tid, fa); }   // more block pairs than lanes
+      if (n_pass > 1) decode(pass * A2_THREADS + tid, fa);
       if (on) {
         const double* pa = Yt + a_off + (size_t)kg * ldy;
         const double* pb = Yt + b_off + (size_t)kg * ldy;
