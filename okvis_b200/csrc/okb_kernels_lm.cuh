@@ -362,8 +362,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
     double* sLi = sLib + buf * A2_TILE * kLiStride;
     double* sX = sXb + buf * A2_TILE * 4;
     const int rows = (fb - fa + 1) * 6;
-    if (lane == 0) {
-      fence_proxy_async();      // the buffer was last read through the generic proxy (previous tile's Y phase)
+    if (lane == 0) {       // (the buffer's last generic-proxy reads are ordered before this point by the CTA barrier)
       mbar_arrive_expect_tx(&mbar[buf], (uint32_t)(rows * A2_TILE * 8 + A2_TILE * kLiStride * 8 + A2_TILE * 4 * 8));
     }
     __syncwarp();
@@ -381,7 +380,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   };
 
   // ---- lane -> (block pair, column split) map of the current frame range: tid = kg * n_act + item
-  uint32_t cur_key = 0xffffffffu;
+  int cur_fa = -1, lane_fmax = 0;
   int KS = 1, kg = 0, n_act = 0, n_pairs = 0, n_pass = 1;
   int a_off = 0, b_off = 0, row0 = 0, col0 = 0;
   bool on = false, aug = false;
@@ -399,9 +398,11 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
       while ((i + 1) * (i + 2) / 2 <= item) ++i;
       const int j = item - i * (i + 1) / 2;
       row0 = 6 * (fa + i); col0 = 6 * (fa + j);
+      lane_fmax = fa + i;
     } else {
       aug = true;
       row0 = dc; col0 = 6 * (fa + item - n_pairs);
+      lane_fmax = fa + item - n_pairs;
     }
     a_off = row0; b_off = col0;
   };
@@ -492,11 +493,16 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
     buf ^= 1;
     if (fa > fb) continue;                 // no observed landmark in this tile (CTA-uniform)
     const int u = fb - fa + 1;
-    if (tr != cur_key) {
+    // The lane -> block-pair map is rebuilt only when the tile's FIRST frame changes (landmarks are sorted by it:
+    // at most K times per chunk) and covers the frames [fa, K-1]; lanes whose pair reaches beyond the tile's last
+    // frame fb sit the tile out (their Y rows are not even written).  Pairs are enumerated row-major, so far-apart
+    // frame pairs share warps and whole warps skip narrow tiles.
+    if (fa != cur_fa) {
       flush();
-      cur_key = tr;
-      n_pairs = u * (u + 1) / 2;
-      n_act = n_pairs + u;
+      cur_fa = fa;
+      const int um = K - fa;
+      n_pairs = um * (um + 1) / 2;
+      n_act = n_pairs + um;
       // block pairs are dealt to the warps (ipw per warp); inside a warp lane = pair * KS + split
       constexpr int NW = A2_THREADS / 32;
       const int ipw = (n_act + NW - 1) / NW;
@@ -558,7 +564,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
     const int ncols = 3 * nl;
     for (int pass = 0; pass < n_pass; ++pass) {
       if (n_pass > 1) decode(pass * A2_THREADS + tid, fa);
-      if (on) {
+      if (on && lane_fmax <= fb) {
         const double* pa = Yt + a_off + (size_t)kg * ldy;
         const double* pb = Yt + b_off + (size_t)kg * ldy;
         const int step = KS * ldy;
