@@ -58,6 +58,11 @@ struct SolverState {
 
 // Everything kernels need to know about one window.  All pointers are device pointers into the
 // window's arena.
+// lm_M / lm_mf are tile-major: [tile of 32 landmarks][frame][element][32] -- a warp's accesses are 256-byte rows and
+// the frames [a, b] of one tile are ONE contiguous block (a single TMA bulk copy in k_schur).
+__host__ __device__ inline size_t lm_M_index(int l, int f, int K) { return ((size_t)(l >> 5) * K + f) * 192 + (l & 31); }   // + 32 * element (0..5)
+__host__ __device__ inline size_t lm_mf_index(int l, int f, int K) { return ((size_t)(l >> 5) * K + f) * 96 + (l & 31); }    // + 32 * element (0..2)
+
 struct SlotCtx;   // per (frame, camera) transform + intrinsics at the candidate state (okb_kernels_lm.cuh)
 
 struct WinDev {
@@ -95,8 +100,8 @@ struct WinDev {
   double* lm_g[2];                             // [L][3] gradient block (double buffered: cur / speculative)
   double* lm_E[2];                             // [L][3] metric (Ceres diagonal^2 / scale^2)
   double* lm_Rinv;                             // [L][6] (H_ll + mu E)^-1, symmetric packed
-  double* lm_M;                                // [K][6][Lp] per-frame sum of rho' A^T A (element-major: coalesced per landmark)
-  double* lm_mf;                               // [K][3][Lp] per-frame sum of rho' A^T r
+  double* lm_M;                                // [Lp/32][K][6][32] per-frame sum of rho' A^T A (lm_M_index)
+  double* lm_mf;                               // [Lp/32][K][3][32] per-frame sum of rho' A^T r (lm_mf_index)
   SlotCtx* slot_ctx;                           // [NS] built by k_reset / k_solve whenever the candidate poses change
   double* lm_Li;                               // [L][9] L^-1 of (H_ll + mu E) (6) and z = L^-1 g_l (3)
   double* lm_gn;                               // [L][3] Gauss-Newton step of the current linearisation

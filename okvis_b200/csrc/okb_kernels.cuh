@@ -494,13 +494,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
       double q0 = 0, q1 = 0, q2 = 0;        // sum_f M_f (G_f u_f)
       double hv = 0;                        // sum_f v^T M_f (v - 2 G_f v_f)
       // landmarks are sorted by observing-frame range, so the visibility test is warp-coherent; M is
-      // element-major ([f][6][l]): every load is coalesced
+      // tile-major (lm_M_index): every load is a 256-byte row per warp
       const uint32_t vis = W.lm_vis[l];
       for (int f = 0; f < K; ++f) {
         if (!((vis >> f) & 1u)) continue;
-        const size_t Lp = (size_t)W.Lp;
-        const double* Mo = W.lm_M + (size_t)(f * 6) * Lp + l;
-        const double M0 = Mo[0], M1 = Mo[Lp], M2 = Mo[2 * Lp], M3 = Mo[3 * Lp], M4 = Mo[4 * Lp], M5 = Mo[5 * Lp];
+        const double* Mo = W.lm_M + lm_M_index(l, f, K);
+        const double M0 = Mo[0], M1 = Mo[32], M2 = Mo[64], M3 = Mo[96], M4 = Mo[128], M5 = Mo[160];
         const double p0 = X.x - s_tws[4 * f] * X.w, p1 = X.y - s_tws[4 * f + 1] * X.w, p2 = X.z - s_tws[4 * f + 2] * X.w;
         const double* uf = s_u + 6 * f;
         const double* vf = s_v + 6 * f;

@@ -150,11 +150,10 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
           const size_t gi = gi0 + (size_t)c * L;
           add_obs(slots[c], W.obs_w[gi], W.obs_z[gi]);
         }
-        const size_t Lp = (size_t)W.Lp;
-        double* Mo = W.lm_M + (size_t)(f * 6) * Lp + l;        // [f][e][l]: coalesced stores
-        Mo[0] = M0; Mo[Lp] = M1; Mo[2 * Lp] = M2; Mo[3 * Lp] = M3; Mo[4 * Lp] = M4; Mo[5 * Lp] = M5;
-        double* mo = W.lm_mf + (size_t)(f * 3) * Lp + l;
-        mo[0] = m0; mo[Lp] = m1; mo[2 * Lp] = m2;
+        double* Mo = W.lm_M + lm_M_index(l, f, W.K);          // tile-major: a warp stores 256-byte rows
+        Mo[0] = M0; Mo[32] = M1; Mo[64] = M2; Mo[96] = M3; Mo[128] = M4; Mo[160] = M5;
+        double* mo = W.lm_mf + lm_mf_index(l, f, W.K);
+        mo[0] = m0; mo[32] = m1; mo[64] = m2;
         // pose-block contributions: G = [w I, -[p]x], p = X - t_WS w
         const double w = X[3];
         const double p0 = X[0] - s_tw[0] * w, p1 = X[1] - s_tw[1] * w, p2 = X[2] - s_tw[2] * w;
@@ -210,12 +209,11 @@ __global__ void __launch_bounds__(128) k_lmblock(const WinDev* __restrict__ wins
   uint32_t vis = W.lm_vis[l];
   for (int f = 0; f < K; ++f) {
     if ((vis >> f) & 1u) {
-      const size_t Lp = (size_t)W.Lp;
-      const double* Mo = W.lm_M + (size_t)(f * 6) * Lp + l;
-      const double* mo = W.lm_mf + (size_t)(f * 3) * Lp + l;
+      const double* Mo = W.lm_M + lm_M_index(l, f, K);
+      const double* mo = W.lm_mf + lm_mf_index(l, f, K);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) H[i] += Mo[(size_t)i * Lp];
-      gl[0] -= mo[0]; gl[1] -= mo[Lp]; gl[2] -= mo[2 * Lp];
+      for (int i = 0; i < 6; ++i) H[i] += Mo[32 * i];
+      gl[0] -= mo[0]; gl[1] -= mo[32]; gl[2] -= mo[64];
     }
   }
   double sc3[3], E[3];
@@ -348,7 +346,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
 
   // Asynchronous staging of one tile by the TMA engine (cp.async.bulk, issued by warp 0, completion on
   // mbar[buf]); frames [fa, fb] only.  Global and shared layouts agree, so every piece is one contiguous copy:
-  //   M  [f][6][Lp] -> sM[f][6][32] : 256-byte rows, one copy per (frame, element)
+  //   M  [tile][f][6][32] -> sM[f][6][32] : frames [fa, fb] are one contiguous block
   //   Li [l][9] -> sLi[32][9] (2304 B),  X = lm_c [l][4] -> sX[32][4] (1024 B)
   // Rows beyond the chunk's last landmark read allocated padding (Lp) and are never used.
   const int warp = tid >> 5, lane = tid & 31;
@@ -361,21 +359,13 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
     double* sM = sMb + (size_t)buf * K * 6 * A2_TILE;
     double* sLi = sLib + buf * A2_TILE * kLiStride;
     double* sX = sXb + buf * A2_TILE * 4;
-    const int rows = (fb - fa + 1) * 6;
+    // three copies per tile: the M block of frames [fa, fb] (contiguous in the tile-major layout), L^-1|z, X
     if (lane == 0) {       // (the buffer's last generic-proxy reads are ordered before this point by the CTA barrier)
-      mbar_arrive_expect_tx(&mbar[buf], (uint32_t)(rows * A2_TILE * 8 + A2_TILE * kLiStride * 8 + A2_TILE * 4 * 8));
-    }
-    __syncwarp();
-    const size_t Lp = (size_t)W.Lp;
-    for (int r = lane; r < rows + 2; r += 32) {
-      if (r < rows) {
-        const int fe = fa * 6 + r;
-        bulk_g2s(sM + (size_t)fe * A2_TILE, W.lm_M + (size_t)fe * Lp + base, A2_TILE * 8, &mbar[buf]);
-      } else if (r == rows) {
-        bulk_g2s(sLi, W.lm_Li + (size_t)kLiStride * base, A2_TILE * kLiStride * 8, &mbar[buf]);
-      } else {
-        bulk_g2s(sX, W.lm_c + 4 * (size_t)base, A2_TILE * 4 * 8, &mbar[buf]);
-      }
+      const uint32_t m_bytes = (uint32_t)(fb - fa + 1) * 6 * A2_TILE * 8;
+      mbar_arrive_expect_tx(&mbar[buf], m_bytes + A2_TILE * kLiStride * 8 + A2_TILE * 4 * 8);
+      bulk_g2s(sM + (size_t)fa * 6 * A2_TILE, W.lm_M + lm_M_index(base, fa, K), m_bytes, &mbar[buf]);
+      bulk_g2s(sLi, W.lm_Li + (size_t)kLiStride * base, A2_TILE * kLiStride * 8, &mbar[buf]);
+      bulk_g2s(sX, W.lm_c + 4 * (size_t)base, A2_TILE * 4 * 8, &mbar[buf]);
     }
   };
 
