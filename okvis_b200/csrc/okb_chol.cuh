@@ -37,17 +37,25 @@ __device__ inline int block_cholesky(double* M, int d, int ldm, int nrows, doubl
       const int r = kb + lane;
 #pragma unroll
       for (int c = 0; c < CH_NB; ++c) row[c] = (lane < nb && c <= lane && c < nb) ? M[(size_t)r * ldm + kb + c] : ((c == lane) ? 1.0 : 0.0);
-      bool bad = false;
+      // The pivot of column j+1 is final after the first update of step j: its shuffle and reciprocal square
+      // root are issued right there, so that long dependent chain overlaps the remaining updates of step j.
+      double piv = __shfl_sync(0xffffffffu, row[0], 0);
+      bool bad = !(piv > 0.0);
+      double rs = rsqrt(piv);                    // one slow operation per column instead of sqrt + divide
 #pragma unroll
       for (int j = 0; j < CH_NB; ++j) {
-        const double piv = __shfl_sync(0xffffffffu, row[j], j);
-        if (!(piv > 0.0)) bad = true;
-        const double rs = rsqrt(piv);            // one slow operation per column instead of sqrt + divide
         const double lij = (lane == j) ? piv * rs : row[j] * rs;
         row[j] = lij;
         if (lane == j && j < nb) rdiag[kb + j] = rs;
+        if (j + 1 < CH_NB) {
+          const double l1 = __shfl_sync(0xffffffffu, lij, j + 1);
+          if (lane >= j + 1) row[j + 1] -= lij * l1;
+          piv = __shfl_sync(0xffffffffu, row[j + 1], j + 1);
+          if (!(piv > 0.0)) bad = true;
+          rs = rsqrt(piv);
+        }
 #pragma unroll
-        for (int c = j + 1; c < CH_NB; ++c) {
+        for (int c = j + 2; c < CH_NB; ++c) {
           const double lcj = __shfl_sync(0xffffffffu, lij, c);
           if (lane >= c) row[c] -= lij * lcj;
         }
@@ -142,10 +150,20 @@ __device__ inline void block_cholesky_backward(const double* M, int d, int ldm, 
     const int nb = min(CH_NB, d - kb);
     if (warp == 0) {
       double t = (lane < nb) ? x[kb + lane] : 0.0;
-      for (int j = nb - 1; j >= 0; --j) {
-        const double uj = __shfl_sync(0xffffffffu, t, j) * rdiag[kb + j];
-        if (lane == j) t = uj;
-        else if (lane < j) t -= M[(size_t)(kb + j) * ldm + kb + lane] * uj;
+      // the block's entries and reciprocal diagonal are fetched before the serial chain starts
+      double m[CH_NB], rd[CH_NB];
+#pragma unroll
+      for (int j = 0; j < CH_NB; ++j) {
+        m[j] = (j < nb && lane < j) ? M[(size_t)(kb + j) * ldm + kb + lane] : 0.0;
+        rd[j] = (j < nb) ? rdiag[kb + j] : 0.0;
+      }
+#pragma unroll
+      for (int j = CH_NB - 1; j >= 0; --j) {
+        if (j < nb) {
+          const double uj = __shfl_sync(0xffffffffu, t, j) * rd[j];
+          if (lane == j) t = uj;
+          else if (lane < j) t -= m[j] * uj;
+        }
       }
       if (lane < nb) x[kb + lane] = t;
     }
