@@ -109,7 +109,7 @@ struct SShared {
 };
 
 // r = S e etc. are tiny; one warp handles all priors.
-__device__ void dense_priors(const WinDev& W, double* Hd, double* gd, double* cost_out) {
+__device__ void dense_priors(const WinDev& W, double* Hd, int ldh, double* gd, double* cost_out) {
   const int lane = threadIdx.x & 31, d = W.d;
   double cost = 0.0;
   for (int i = 0; i < W.n_pp; ++i) {
@@ -121,7 +121,7 @@ __device__ void dense_priors(const WinDev& W, double* Hd, double* gd, double* co
       const int a = e / 6, b = e % 6;
       double s = 0;
       for (int k = 0; k < 6; ++k) s += J[k * 6 + a] * J[k * 6 + b];
-      Hd[(size_t)(o + a) * d + o + b] += s;
+      Hd[(size_t)(o + a) * ldh + o + b] += s;
     }
     if (lane < 6) {
       double s = 0;
@@ -146,7 +146,7 @@ __device__ void dense_priors(const WinDev& W, double* Hd, double* gd, double* co
       const int a = e / 9, b = e % 9;
       double s = 0;
       for (int k = 0; k < 9; ++k) s += pr.sqrt_info[k * 9 + a] * pr.sqrt_info[k * 9 + b];
-      Hd[(size_t)(o + a) * d + o + b] += s;
+      Hd[(size_t)(o + a) * ldh + o + b] += s;
     }
     if (lane < 9) {
       double s = 0;
@@ -205,11 +205,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
 #define PHASE_MARK(i) do { if (tid == 0) { const unsigned long long n_ = globaltimer_ns(); st->phase_ns[i] += n_ - t_ph; t_ph = n_; } } while (0)
   const int mode = st->mode;
   const int spec = st->cur ^ 1;
-  double* Hd = W.Hd;
   double* gd = W.gd[spec];
 
   // ================= phase 1: dense terms at the candidate =================
-  for (int i = tid; i < d * d; i += S_THREADS) Hd[i] = 0.0;
+  // The dense Hessian is assembled directly in the shared-memory buffer that later holds the reduced system (row
+  // stride d+1: the extra row/column carry the right-hand side through the factorisation); windows whose system
+  // does not fit keep it in global memory.
+  double* Hd = chol_in_smem ? s_big : W.Hd;
+  const int ldh = chol_in_smem ? d + 1 : d;
+  for (int i = tid; i < d * ldh; i += S_THREADS) Hd[i] = 0.0;
   for (int i = tid; i < d; i += S_THREADS) gd[i] = 0.0;
   __syncthreads();
   double cost_dense_local = 0.0;   // accumulated by thread 0
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
         const int bb = (b < 6) ? 0 : (b < 15) ? 1 : (b < 21) ? 2 : 3;
         const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
         const int lb = b - ((bb == 0) ? 0 : (bb == 1) ? 6 : (bb == 2) ? 15 : 21);
-        Hd[(size_t)(offs[ba] + la) * d + offs[bb] + lb] += out[e];
+        Hd[(size_t)(offs[ba] + la) * ldh + offs[bb] + lb] += out[e];
       } else {
         const int a = e - 900;
         const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   // priors (warp 0)
   if (warp == 0) {
     double c = 0;
-    dense_priors(W, Hd, gd, &c);
+    dense_priors(W, Hd, ldh, gd, &c);
     if (lane == 0) cost_dense_local += c;
   }
   __syncthreads();
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
           for (int k = 0; k < 3; ++k)
             for (int k2 = 0; k2 < 3; ++k2) s += Bi[k * 3 + (a - 3)] * W.marg_H0[(size_t)(ci + 3 + k) * n + cj + 3 + k2] * Bj[k2 * 3 + (b - 3)];
         }
-        Hd[(size_t)(oi + a) * d + oj + b] += s;
+        Hd[(size_t)(oi + a) * ldh + oj + b] += s;
       }
       if (bi == bj) {
         for (int a = tid; a < mi; a += S_THREADS) {
@@ -333,18 +337,18 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     if (e < 6) {          // H_tt symmetric packed
       const int a = (e < 3) ? 0 : (e < 5) ? 1 : 2;
       const int b = (e < 3) ? e : (e < 5) ? e - 2 : 2;
-      Hd[(size_t)(o + a) * d + o + b] += s;
-      if (a != b) Hd[(size_t)(o + b) * d + o + a] += s;
+      Hd[(size_t)(o + a) * ldh + o + b] += s;
+      if (a != b) Hd[(size_t)(o + b) * ldh + o + a] += s;
     } else if (e < 15) {  // H_tr 3x3
       const int a = (e - 6) / 3, b = (e - 6) % 3;
-      Hd[(size_t)(o + a) * d + o + 3 + b] += s;
-      Hd[(size_t)(o + 3 + b) * d + o + a] += s;
+      Hd[(size_t)(o + a) * ldh + o + 3 + b] += s;
+      Hd[(size_t)(o + 3 + b) * ldh + o + a] += s;
     } else if (e < 21) {  // H_rr symmetric packed
       const int q = e - 15;
       const int a = (q < 3) ? 0 : (q < 5) ? 1 : 2;
       const int b = (q < 3) ? q : (q < 5) ? q - 2 : 2;
-      Hd[(size_t)(o + 3 + a) * d + o + 3 + b] += s;
-      if (a != b) Hd[(size_t)(o + 3 + b) * d + o + 3 + a] += s;
+      Hd[(size_t)(o + 3 + a) * ldh + o + 3 + b] += s;
+      if (a != b) Hd[(size_t)(o + 3 + b) * ldh + o + 3 + a] += s;
     } else {              // g_p
       gd[o + (e - 21)] += s;
     }
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     }
     // metric E_d (and, once, the Jacobi scale)
     for (int i = tid; i < d; i += S_THREADS) {
-      const double hjj = Hd[(size_t)i * d + i];
+      const double hjj = Hd[(size_t)i * ldh + i];
       double sc;
       if (mode == MODE_INIT) { sc = 1.0 / (1.0 + sqrt(hjj)); W.scale_d[i] = sc; }
       else sc = W.scale_d[i];
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     double vhv_loc = 0.0;
     for (int i = tid; i < d; i += S_THREADS) {
       double s = 0;
-      for (int j = 0; j < d; ++j) s += Hd[(size_t)i * d + j] * s_v[j];
+      for (int j = 0; j < d; ++j) s += Hd[(size_t)i * ldh + j] * s_v[j];
       vhv_loc += s_v[i] * s;
     }
     const double VHV_dd = block_sum(vhv_loc, sh->red);
@@ -448,11 +452,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     const int ldm = d + 1;                     // row d carries the right-hand side through the factorisation
     for (int i = tid; i < d * d; i += S_THREADS) {
       const int r0 = i / d, c0 = i % d;
-      double v = Hd[i];
+      if (c0 > r0) continue;                      // the factorisation only references the lower triangle
+      double v = Hd[(size_t)r0 * ldh + c0];       // in place when the system lives in shared memory (ldh == ldm)
       if (r0 == c0) v += mu * s_E[r0];
       if (r0 < dc && c0 < dc) {
-        const int rr = r0 >= c0 ? r0 : c0, cc = r0 >= c0 ? c0 : r0;
-        v -= W.partA[(size_t)rr * dcp + cc];     // chunk partials were summed by k_reduce_partials
+        v -= W.partA[(size_t)r0 * dcp + c0];     // chunk partials were summed by k_reduce_partials
       }
       Mx[(size_t)r0 * ldm + c0] = v;
     }
