@@ -164,3 +164,34 @@ def test_batch_transfer_api_matches_single_calls(ctx):
     for a, b, c in zip(single, outs, again):
         for k in ("poses", "speed_bias", "landmarks", "quality"):
             assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
+
+
+def test_tracks_with_gaps_and_shuffled_landmark_order(ctx, oracle):
+    """Visibility that is NOT a run of consecutive frames (random dropouts, landmarks seen only in the first and
+    the last frame) and a shuffled caller-side landmark order: the internal sort by observing-frame range, the
+    per-tile frame ranges and the block-pair lanes that sit out must not change any result."""
+    w = synthetic.make_window(2, 11, cfg=dataclasses.replace(synthetic.CONFIGS[2], n_landmarks=427))
+    rng = np.random.Generator(np.random.PCG64(7))
+    obs = w.obs
+    K = len(w.poses)
+    keep = np.ones(len(obs), bool)
+    # (1) random dropouts of whole (landmark, frame) pairs
+    pair = obs["lm_idx"].astype(np.int64) * K + obs["pose_idx"]
+    drop_pairs = rng.choice(np.unique(pair), size=len(np.unique(pair)) // 4, replace=False)
+    keep &= ~np.isin(pair, drop_pairs)
+    # (2) every 9th landmark only keeps its first and last observing frame
+    for l in range(0, len(w.landmarks), 9):
+        fr = np.unique(obs["pose_idx"][(obs["lm_idx"] == l) & keep])
+        if len(fr) > 2:
+            keep &= ~((obs["lm_idx"] == l) & (obs["pose_idx"] != fr[0]) & (obs["pose_idx"] != fr[-1]))
+    # landmarks must stay constrained: restore everything for those left with fewer than 2 frames
+    for l in range(len(w.landmarks)):
+        if len(np.unique(obs["pose_idx"][(obs["lm_idx"] == l) & keep])) < 2:
+            keep |= obs["lm_idx"] == l
+    obs = obs[keep]
+    # (3) shuffled landmark numbering on the caller's side
+    perm = rng.permutation(len(w.landmarks))
+    inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+    obs = obs.copy(); obs["lm_idx"] = inv[obs["lm_idx"]].astype(np.uint32)
+    w2 = dataclasses.replace(w, landmarks=np.ascontiguousarray(w.landmarks[perm]), obs=np.ascontiguousarray(obs[rng.permutation(len(obs))]))
+    compare(ctx, oracle, w2, max_iterations=8)
