@@ -120,6 +120,48 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def frontend_leg(ctx, cam):
+    """Secondary measurement (north_star rows S-V): keypoint detect/describe and the all-pairs Hamming matcher through
+    the C-ABI with host buffers, next to the CPU oracle on a bounded sample.  Reported inside the same JSON line."""
+    from okvis_b200 import images
+    from oracle import oracle_py as op
+    left, right = images.stereo_pair()
+    R = np.eye(3)
+    for s_, im in enumerate((left, right)):
+        ctx.detect_describe(im, cam, R, cam_slot=s_)
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        kl, dl = ctx.detect_describe(left, cam, R, cam_slot=0)
+        kr, dr = ctx.detect_describe(right, cam, R, cam_slot=1)
+    dd_ms = (time.perf_counter() - t0) * 1e3 / (2 * reps)
+    t0 = time.perf_counter()
+    op.detect_describe(left, cam, R)
+    dd_cpu_ms = (time.perf_counter() - t0) * 1e3
+    ctx.hamming_match(dl, dr)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        ctx.hamming_match(dl, dr)
+    m_us = (time.perf_counter() - t0) * 1e6 / 50
+    t0 = time.perf_counter()
+    for _ in range(5):
+        op.match_hamming(dl, dr)
+    m_cpu_us = (time.perf_counter() - t0) * 1e6 / 5
+    rng = np.random.Generator(np.random.PCG64(5))
+    A = rng.integers(0, 256, (8192, 48), dtype=np.uint8)
+    Bm = rng.integers(0, 256, (8192, 48), dtype=np.uint8)
+    ctx.hamming_match(A, Bm, threshold=200.0)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ctx.hamming_match(A, Bm, threshold=200.0)
+    big_s = (time.perf_counter() - t0) / 5
+    return {"detect_describe_ms_per_image": dd_ms, "image": "752x480 u8, <=400 keypoints, 48-byte descriptors", "keypoints": [int(len(kl)), int(len(kr))],
+            "cpu_oracle_detect_describe_ms_per_image": dd_cpu_ms,
+            "hamming_match_us": m_us, "hamming_match_shape": [int(len(dl)), int(len(dr))], "cpu_oracle_hamming_match_us": m_cpu_us,
+            "hamming_8192x8192_gcmp_per_s": 8192.0 * 8192.0 / big_s / 1e9,
+            "note": "host buffers in/out, host clock; sequential DenseMatcher semantics (assignbest on the device)"}
+
+
 def run_b200(args):
     import torch
     from okvis_b200 import capi
@@ -265,6 +307,10 @@ def run_b200(args):
         with ThreadPoolExecutor(max_workers=cores) as ex:
             cpu_iters = sum(ex.map(solve_one, range(n_cpu)))
         cpu_dt = time.perf_counter() - t0
+        try:
+            frontend = frontend_leg(ctx, windows[0].cameras[0])
+        except Exception as e:       # the headline measurement must not depend on this leg
+            frontend = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": iters_all / (elapsed_ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -287,6 +333,7 @@ def run_b200(args):
                          "k_solve_avg_launch_ms": sv_ms, "k_solve_share": prof["solve_ms"] / max(total_k, 1e-9)},
             "cpu_baseline": {"value": cpu_iters / cpu_dt, "unit": "iterations/s", "cores": cores, "kind": "port",
                              "sample": "%d windows x optimize(%d) + quality pass, one oracle thread per window, %d threads" % (n_cpu, ITERS, cores)},
+            "frontend": frontend,
         }
         print(json.dumps(line))
     ctx.close()
