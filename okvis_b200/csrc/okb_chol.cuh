@@ -1,5 +1,5 @@
 // Dense Cholesky + triangular solves of the reduced camera system inside one CTA (k_solve).
-// Blocked right-looking factorisation, panel width 16:
+// Blocked right-looking factorisation, panel width CH_NB:
 //   (1) the 16x16 diagonal block is factored by warp 0 with one matrix row per lane (registers +
 //       shuffles), (2) the panel below it is solved row-per-thread and transposed into a k-major
 //       shared buffer, (3) the trailing matrix gets a rank-16 update as a register-tiled SYRK
@@ -10,15 +10,18 @@
 
 namespace okb {
 
-constexpr int CH_NB = 16;
+constexpr int CH_NB = 8;
 
-// In-place lower Cholesky of the leading d x d block of the row-major matrix M (row stride ldm; only
-// the lower triangle is referenced and written).  M has nrows >= d rows: rows d..nrows-1 are carried
+// Packed lower-triangular storage: row r holds columns 0..r at offset r(r+1)/2.
+__host__ __device__ inline size_t tri_row(int r) { return (size_t)r * (r + 1) / 2; }
+
+// In-place lower Cholesky of the leading d x d block of the matrix M held in packed lower-triangular storage
+// (tri_row).  M has nrows >= d rows: rows d..nrows-1 are carried
 // along like any sub-diagonal row, so an appended right-hand side row g^T comes out as (L^-1 g)^T -- the
 // forward substitution rides on the factorisation.  `panel` is shared scratch of CH_NB * ld_p doubles
 // (ld_p >= nrows rounded up to 4), `flag` a shared int.  Returns 0 on success, 1 on a non-positive
 // pivot (uniform over the CTA).
-__device__ inline int block_cholesky(double* M, int d, int ldm, int nrows, double* panel, int ld_p, double* rdiag, int* flag,
+__device__ inline int block_cholesky(double* M, int d, int nrows, double* panel, int ld_p, double* rdiag, int* flag,
                                      unsigned long long* prof = nullptr) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *flag = 0;
@@ -36,7 +39,7 @@ __device__ inline int block_cholesky(double* M, int d, int ldm, int nrows, doubl
       double row[CH_NB];
       const int r = kb + lane;
 #pragma unroll
-      for (int c = 0; c < CH_NB; ++c) row[c] = (lane < nb && c <= lane && c < nb) ? M[(size_t)r * ldm + kb + c] : ((c == lane) ? 1.0 : 0.0);
+      for (int c = 0; c < CH_NB; ++c) row[c] = (lane < nb && c <= lane && c < nb) ? M[tri_row(r) + kb + c] : ((c == lane) ? 1.0 : 0.0);
       // The pivot of column j+1 is final after the first update of step j: its shuffle and reciprocal square
       // root are issued right there, so that long dependent chain overlaps the remaining updates of step j.
       double piv = __shfl_sync(0xffffffffu, row[0], 0);
@@ -62,7 +65,7 @@ __device__ inline int block_cholesky(double* M, int d, int ldm, int nrows, doubl
       }
       if (lane < nb) {
 #pragma unroll
-        for (int c = 0; c < CH_NB; ++c) if (c <= lane && c < nb) M[(size_t)r * ldm + kb + c] = row[c];
+        for (int c = 0; c < CH_NB; ++c) if (c <= lane && c < nb) M[tri_row(r) + kb + c] = row[c];
       }
       if (bad && lane == 0) *flag = 1;
     }
@@ -76,13 +79,13 @@ __device__ inline int block_cholesky(double* M, int d, int ldm, int nrows, doubl
     // ---- (2) panel solve: X * L_d^T = A  (row per thread), result also stored k-major in `panel`
     for (int i = tid; i < n; i += nthr) {
       double x[CH_NB];
-      double* arow = M + (size_t)(r0 + i) * ldm + kb;
+      double* arow = M + tri_row(r0 + i) + kb;
 #pragma unroll
       for (int c = 0; c < CH_NB; ++c) x[c] = (c < nb) ? arow[c] : 0.0;
 #pragma unroll
       for (int j = 0; j < CH_NB; ++j) {
         if (j < nb) {
-          const double* lrow = M + (size_t)(kb + j) * ldm + kb;
+          const double* lrow = M + tri_row(kb + j) + kb;
           double s = x[j];
 #pragma unroll
           for (int c = 0; c < CH_NB; ++c) if (c < j) s -= x[c] * lrow[c];
@@ -130,7 +133,7 @@ __device__ inline int block_cholesky(double* M, int d, int ldm, int nrows, doubl
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int i = 4 * ti + ii, j = 4 * tj + jj;
-          if (i < n && j <= i && j < ncol) M[(size_t)(r0 + i) * ldm + r0 + j] -= acc[ii * 4 + jj];
+          if (i < n && j <= i && j < ncol) M[tri_row(r0 + i) + r0 + j] -= acc[ii * 4 + jj];
         }
     }
     __syncthreads();
@@ -142,7 +145,7 @@ __device__ inline int block_cholesky(double* M, int d, int ldm, int nrows, doubl
 
 // Solves L^T u = z in place in `x` (shared memory vector of length d holding z = L^-1 b, which the
 // factorisation produced in the appended row).
-__device__ inline void block_cholesky_backward(const double* M, int d, int ldm, const double* rdiag, double* x) {
+__device__ inline void block_cholesky_backward(const double* M, int d, const double* rdiag, double* x) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int nblocks = (d + CH_NB - 1) / CH_NB;
   for (int bi = nblocks - 1; bi >= 0; --bi) {
@@ -154,7 +157,7 @@ __device__ inline void block_cholesky_backward(const double* M, int d, int ldm, 
       double m[CH_NB], rd[CH_NB];
 #pragma unroll
       for (int j = 0; j < CH_NB; ++j) {
-        m[j] = (j < nb && lane < j) ? M[(size_t)(kb + j) * ldm + kb + lane] : 0.0;
+        m[j] = (j < nb && lane < j) ? M[tri_row(kb + j) + kb + lane] : 0.0;
         rd[j] = (j < nb) ? rdiag[kb + j] : 0.0;
       }
 #pragma unroll
@@ -170,7 +173,7 @@ __device__ inline void block_cholesky_backward(const double* M, int d, int ldm, 
     __syncthreads();
     for (int i = tid; i < kb; i += nthr) {
       double s = x[i];
-      for (int c = 0; c < nb; ++c) s -= M[(size_t)(kb + c) * ldm + i] * x[kb + c];
+      for (int c = 0; c < nb; ++c) s -= M[tri_row(kb + c) + i] * x[kb + c];
       x[i] = s;
     }
     __syncthreads();

@@ -85,6 +85,8 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
   cudaMemset(c->d_states, 0, sizeof(SolverState) * max_windows);
   cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_schur, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_quality, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   *out = c;
   return OKB_OK;

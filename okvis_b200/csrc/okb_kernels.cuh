@@ -14,7 +14,7 @@
 
 namespace okb {
 
-constexpr int S_THREADS = 512;
+constexpr int S_THREADS = 256;    // two k_solve CTAs per SM (packed system: ~112 KB of shared memory each)
 constexpr int S_WARPS = S_THREADS / 32;
 constexpr int kImuScratch = 3 * 225 + 450 + 450 + 16 + 32 * kImuPre;   // doubles of shared scratch per IMU warp
 constexpr int kImuOut = 932;     // doubles per IMU term produced by k_imu: H30 | g30 | cost | pad
@@ -109,7 +109,13 @@ struct SShared {
 };
 
 // r = S e etc. are tiny; one warp handles all priors.
-__device__ void dense_priors(const WinDev& W, double* Hd, int ldh, double* gd, double* cost_out) {
+// The dense Hessian lives in packed lower-triangular storage: contributions to the upper triangle are dropped
+// (their mirror images are always added as well).
+__device__ __forceinline__ void hd_add(double* Hd, int r, int c, double v) {
+  if (r >= c) Hd[tri_row(r) + c] += v;
+}
+
+__device__ void dense_priors(const WinDev& W, double* Hd, double* gd, double* cost_out) {
   const int lane = threadIdx.x & 31, d = W.d;
   double cost = 0.0;
   for (int i = 0; i < W.n_pp; ++i) {
@@ -121,7 +127,7 @@ __device__ void dense_priors(const WinDev& W, double* Hd, int ldh, double* gd, d
       const int a = e / 6, b = e % 6;
       double s = 0;
       for (int k = 0; k < 6; ++k) s += J[k * 6 + a] * J[k * 6 + b];
-      Hd[(size_t)(o + a) * ldh + o + b] += s;
+      hd_add(Hd, (o + a), o + b, s);
     }
     if (lane < 6) {
       double s = 0;
@@ -146,7 +152,7 @@ __device__ void dense_priors(const WinDev& W, double* Hd, int ldh, double* gd, d
       const int a = e / 9, b = e % 9;
       double s = 0;
       for (int k = 0; k < 9; ++k) s += pr.sqrt_info[k * 9 + a] * pr.sqrt_info[k * 9 + b];
-      Hd[(size_t)(o + a) * ldh + o + b] += s;
+      hd_add(Hd, (o + a), o + b, s);
     }
     if (lane < 9) {
       double s = 0;
@@ -167,11 +173,11 @@ __host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_im
   b += (size_t)3 * (n_marg > 0 ? n_marg : 1) * sizeof(double);   // marg: dchi, e, Jte
   b = (b + 31) & ~(size_t)31;
   b += (size_t)CH_NB * ((d + 1 + 3) & ~3) * sizeof(double);  // Cholesky panel (k-major)
-  b += chol_in_smem ? (size_t)(d + 1) * (d + 1) * sizeof(double) : 16;   // the reduced system + appended rhs row
+  b += chol_in_smem ? tri_row(d + 1) * sizeof(double) + 16 : 16;        // the reduced system (packed lower triangle) + appended rhs row
   return b;
 }
 
-__global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict__ wins, int win_first, okb_solve_options opt,
+__global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict__ wins, int win_first, okb_solve_options opt,
                                                         int chol_in_smem) {
   const WinDev& W = wins[win_first + blockIdx.x];
   SolverState* st = W.st;
@@ -208,12 +214,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   double* gd = W.gd[spec];
 
   // ================= phase 1: dense terms at the candidate =================
-  // The dense Hessian is assembled directly in the shared-memory buffer that later holds the reduced system (row
-  // stride d+1: the extra row/column carry the right-hand side through the factorisation); windows whose system
+  // The dense Hessian is assembled directly in the shared-memory buffer that later holds the reduced system (packed
+  // lower triangle; an appended row carries the right-hand side through the factorisation); windows whose system
   // does not fit keep it in global memory.
   double* Hd = chol_in_smem ? s_big : W.Hd;
-  const int ldh = chol_in_smem ? d + 1 : d;
-  for (int i = tid; i < d * ldh; i += S_THREADS) Hd[i] = 0.0;
+  for (int i = tid; i < (int)tri_row(d); i += S_THREADS) Hd[i] = 0.0;
   for (int i = tid; i < d; i += S_THREADS) gd[i] = 0.0;
   __syncthreads();
   double cost_dense_local = 0.0;   // accumulated by thread 0
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
         const int bb = (b < 6) ? 0 : (b < 15) ? 1 : (b < 21) ? 2 : 3;
         const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
         const int lb = b - ((bb == 0) ? 0 : (bb == 1) ? 6 : (bb == 2) ? 15 : 21);
-        Hd[(size_t)(offs[ba] + la) * ldh + offs[bb] + lb] += out[e];
+        hd_add(Hd, offs[ba] + la, offs[bb] + lb, out[e]);
       } else {
         const int a = e - 900;
         const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
   // priors (warp 0)
   if (warp == 0) {
     double c = 0;
-    dense_priors(W, Hd, ldh, gd, &c);
+    dense_priors(W, Hd, gd, &c);
     if (lane == 0) cost_dense_local += c;
   }
   __syncthreads();
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
           for (int k = 0; k < 3; ++k)
             for (int k2 = 0; k2 < 3; ++k2) s += Bi[k * 3 + (a - 3)] * W.marg_H0[(size_t)(ci + 3 + k) * n + cj + 3 + k2] * Bj[k2 * 3 + (b - 3)];
         }
-        Hd[(size_t)(oi + a) * ldh + oj + b] += s;
+        hd_add(Hd, (oi + a), oj + b, s);
       }
       if (bi == bj) {
         for (int a = tid; a < mi; a += S_THREADS) {
@@ -337,18 +342,18 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     if (e < 6) {          // H_tt symmetric packed
       const int a = (e < 3) ? 0 : (e < 5) ? 1 : 2;
       const int b = (e < 3) ? e : (e < 5) ? e - 2 : 2;
-      Hd[(size_t)(o + a) * ldh + o + b] += s;
-      if (a != b) Hd[(size_t)(o + b) * ldh + o + a] += s;
+      hd_add(Hd, (o + a), o + b, s);
+      if (a != b) hd_add(Hd, (o + b), o + a, s);
     } else if (e < 15) {  // H_tr 3x3
       const int a = (e - 6) / 3, b = (e - 6) % 3;
-      Hd[(size_t)(o + a) * ldh + o + 3 + b] += s;
-      Hd[(size_t)(o + 3 + b) * ldh + o + a] += s;
+      hd_add(Hd, (o + a), o + 3 + b, s);
+      hd_add(Hd, (o + 3 + b), o + a, s);
     } else if (e < 21) {  // H_rr symmetric packed
       const int q = e - 15;
       const int a = (q < 3) ? 0 : (q < 5) ? 1 : 2;
       const int b = (q < 3) ? q : (q < 5) ? q - 2 : 2;
-      Hd[(size_t)(o + 3 + a) * ldh + o + 3 + b] += s;
-      if (a != b) Hd[(size_t)(o + 3 + b) * ldh + o + 3 + a] += s;
+      hd_add(Hd, (o + 3 + a), o + 3 + b, s);
+      if (a != b) hd_add(Hd, (o + 3 + b), o + 3 + a, s);
     } else {              // g_p
       gd[o + (e - 21)] += s;
     }
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     }
     // metric E_d (and, once, the Jacobi scale)
     for (int i = tid; i < d; i += S_THREADS) {
-      const double hjj = Hd[(size_t)i * ldh + i];
+      const double hjj = Hd[tri_row(i) + i];
       double sc;
       if (mode == MODE_INIT) { sc = 1.0 / (1.0 + sqrt(hjj)); W.scale_d[i] = sc; }
       else sc = W.scale_d[i];
@@ -440,25 +445,25 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
     __syncthreads();
     // VHV (dense-dense part): v^T H v
     double vhv_loc = 0.0;
-    for (int i = tid; i < d; i += S_THREADS) {
+    for (int i = tid; i < d; i += S_THREADS) {     // v^T H v from the lower triangle
+      const double* hrow = Hd + tri_row(i);
       double s = 0;
-      for (int j = 0; j < d; ++j) s += Hd[(size_t)i * ldh + j] * s_v[j];
-      vhv_loc += s_v[i] * s;
+      for (int j = 0; j < i; ++j) s += hrow[j] * s_v[j];
+      vhv_loc += s_v[i] * (2.0 * s + hrow[i] * s_v[i]);
     }
     const double VHV_dd = block_sum(vhv_loc, sh->red);
     // reduced system M = Hd + mu E - [Sacc], rhs = g - [sum Y z]
     double* Mx = chol_in_smem ? s_big : W.chol;
     const double mu = st->mu;
-    const int ldm = d + 1;                     // row d carries the right-hand side through the factorisation
     for (int i = tid; i < d * d; i += S_THREADS) {
       const int r0 = i / d, c0 = i % d;
       if (c0 > r0) continue;                      // the factorisation only references the lower triangle
-      double v = Hd[(size_t)r0 * ldh + c0];       // in place when the system lives in shared memory (ldh == ldm)
+      double v = Hd[tri_row(r0) + c0];            // in place when the system lives in shared memory
       if (r0 == c0) v += mu * s_E[r0];
       if (r0 < dc && c0 < dc) {
         v -= W.partA[(size_t)r0 * dcp + c0];     // chunk partials were summed by k_reduce_partials
       }
-      Mx[(size_t)r0 * ldm + c0] = v;
+      Mx[tri_row(r0) + c0] = v;
     }
     for (int i = tid; i < d; i += S_THREADS) {
       double v = s_g[i];
@@ -466,18 +471,18 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_solve(const WinDev* __restrict
         v -= W.partA[(size_t)dc * dcp + i];
       }
       s_rhs[i] = v;
-      Mx[(size_t)d * ldm + i] = v;
+      Mx[tri_row(d) + i] = v;            // appended row: the right-hand side
     }
     __syncthreads();
     PHASE_MARK(2);
     // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh); row d comes out as z = L^-1 rhs
     int chol_fail = sh->fail;
-    if (!chol_fail) chol_fail = block_cholesky(Mx, d, ldm, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8);
+    if (!chol_fail) chol_fail = block_cholesky(Mx, d, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8);
     PHASE_MARK(3);
     if (!chol_fail) {
-      for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = Mx[(size_t)d * ldm + i];
+      for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = Mx[tri_row(d) + i];
       __syncthreads();
-      block_cholesky_backward(Mx, d, ldm, s_col, s_tmp);
+      block_cholesky_backward(Mx, d, s_col, s_tmp);
       for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
       __syncthreads();
     }
