@@ -279,20 +279,44 @@ __global__ void __launch_bounds__(256) k_uniformity(const unsigned long long* __
 }
 
 // integral image (H+1) x (W+1), uint32
-__global__ void k_integral_rows(const uint8_t* __restrict__ img, int W, int H, uint32_t* II) {
-  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+// row pass: one warp per image row, 32 pixels per step (warp inclusive scan + running carry): coalesced byte loads
+// and 128-byte stores
+__global__ void __launch_bounds__(128) k_integral_rows(const uint8_t* __restrict__ img, int W, int H, uint32_t* II) {
+  const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (y > H) return;
   uint32_t* row = II + (size_t)y * (W + 1);
-  if (y == 0) { for (int x = 0; x <= W; ++x) row[x] = 0; return; }
-  uint32_t s = 0;
-  row[0] = 0;
-  for (int x = 0; x < W; ++x) { s += img[(size_t)(y - 1) * W + x]; row[x + 1] = s; }
+  if (y == 0) { for (int x = lane; x <= W; x += 32) row[x] = 0; return; }
+  if (lane == 0) row[0] = 0;
+  const uint8_t* src = img + (size_t)(y - 1) * W;
+  uint32_t carry = 0;
+  for (int x0 = 0; x0 < W; x0 += 32) {
+    const int x = x0 + lane;
+    uint32_t v = (x < W) ? src[x] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (x < W) row[x + 1] = carry + v;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
 }
-__global__ void k_integral_cols(int W, int H, uint32_t* II) {
+// column pass: one thread per column; 16 independent loads are in flight per step instead of one dependent load
+__global__ void __launch_bounds__(64) k_integral_cols(int W, int H, uint32_t* II) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x > W) return;
   uint32_t s = 0;
-  for (int y = 0; y <= H; ++y) { s += II[(size_t)y * (W + 1) + x]; II[(size_t)y * (W + 1) + x] = s; }
+  for (int y0 = 0; y0 <= H; y0 += 16) {
+    uint32_t v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (y0 + k <= H) ? II[(size_t)(y0 + k) * (W + 1) + x] : 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      s += v[k];
+      if (y0 + k <= H) II[(size_t)(y0 + k) * (W + 1) + x] = s;
+    }
+  }
 }
 
 __device__ void undistort_gn(const CamIntr& cam, double d0, double d1, double* pu) {
@@ -440,8 +464,8 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   if (occ_bytes > 48 * 1024 - 64)
     FE_CUDA(c, cudaFuncSetAttribute(k_uniformity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occ_bytes));
   k_uniformity<<<1, 256, occ_bytes, st>>>(S.d_keys_sorted, S.d_count, kMaxCand, W, H, prm->uniformity_radius, maxk, S.d_kp, S.d_count + 1);
-  k_integral_rows<<<(H + 1 + 127) / 128, 128, 0, st>>>(S.d_img, W, H, S.d_integral);
-  k_integral_cols<<<(W + 1 + 127) / 128, 128, 0, st>>>(W, H, S.d_integral);
+  k_integral_rows<<<(H + 1 + 3) / 4, 128, 0, st>>>(S.d_img, W, H, S.d_integral);
+  k_integral_cols<<<(W + 1 + 63) / 64, 64, 0, st>>>(W, H, S.d_integral);
   k_describe<<<(maxk + 3) / 4, 128, 0, st>>>(S.d_integral, W, H, *cam, d_gC, prm->rotation_invariance, F->d_half, F->d_pi, F->d_pj,
                                              F->d_lut, prm->desc_bytes, S.d_kp, S.d_count + 1, S.d_desc);
   c->launches += 6 + 3;   // + the radix-sort passes issued by CUB
