@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--batch", type=int, default=592, help="resident windows per GPU (4 per SM)")
     ap.add_argument("--e2e-batch", type=int, default=296)
     ap.add_argument("--skip-cpu", action="store_true", help="tuning runs only: shrink the cpu_baseline sample to one window")
-    ap.add_argument("--host-threads", type=int, default=8, help="host threads packing/uploading windows in the e2e leg")
+    ap.add_argument("--host-threads", type=int, default=12, help="host threads packing/uploading windows in the e2e leg")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic windows per rank (replicated to fill the batch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

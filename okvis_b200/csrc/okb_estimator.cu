@@ -739,7 +739,9 @@ extern "C" int okb_window_download_batch(okb_ctx* c, int first, int count, doubl
   WinStore& S0 = c->wins[first];
   OKB_CUDA(c, cudaEventRecord(S0.down, xs));
   OKB_CUDA(c, cudaEventSynchronize(S0.down));
-  for (int i = first; i < first + count; ++i) {
+  // pinned staging -> caller's buffers (landmarks / qualities scattered back to the caller's order); a few host
+  // threads share the slots of a large batch
+  auto copy_out = [&](int i) {
     const WinDev& W = c->host[i];
     const WinStore& S = c->wins[i];
     const int k = i - first;
@@ -751,6 +753,16 @@ extern "C" int okb_window_download_batch(okb_ctx* c, int first, int count, doubl
     unpermute_landmarks(S, W.L, reinterpret_cast<const double*>(S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base)),
                         reinterpret_cast<const double*>(S.out_staging + span), landmarks ? landmarks[k] : nullptr,
                         quality ? quality[k] : nullptr);
+  };
+  const int T = std::max(1, std::min(8, count / 16));
+  if (T == 1) {
+    for (int i = first; i < first + count; ++i) copy_out(i);
+  } else {
+    std::vector<std::thread> th;
+    th.reserve(T);
+    for (int t = 0; t < T; ++t)
+      th.emplace_back([&, t]() { for (int i = first + t; i < first + count; i += T) copy_out(i); });
+    for (auto& x : th) x.join();
   }
   return OKB_OK;
 }
