@@ -196,7 +196,9 @@ int64_t okb_kernel_launches(const okb_ctx* ctx);
 /* Raw CUDA stream (cudaStream_t) the context launches on, for event timing by the caller. */
 void* okb_stream(const okb_ctx* ctx);
 
-/* Packs and uploads one window into slot `win` (0 <= win < max_windows). */
+/* Packs and uploads one window into slot `win` (0 <= win < max_windows).  The library stores landmarks internally
+ * sorted by observing-frame range; indices and results at this boundary always use the caller's order.  A slot must
+ * not be uploaded while an okb_optimize_async on it is still in flight (call okb_optimize_finish first). */
 int okb_window_upload(okb_ctx* ctx, int win, const okb_window_desc* desc);
 /* Uploads `count` windows into slots [win_first, win_first+count); descs[i] describes slot win_first+i.
  * The packing of different slots is spread over up to `host_threads` host threads (<= 0: library default).
