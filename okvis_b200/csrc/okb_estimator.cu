@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "okb_ctx.h"
+#include "okb_hostpack.hpp"
 #include "okb_kernels.cuh"
 
 using namespace okb;
@@ -334,32 +335,14 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
   {
     S.perm.resize(L);
     uint32_t* inv = reinterpret_cast<uint32_t*>(H + o_inv);
-    std::vector<uint32_t> count(32 * 32 + 2, 0u);
-    auto key_of = [&](uint32_t m) -> uint32_t {
-      if (!m) return 32u * 32u;
-      return (uint32_t)__builtin_ctz(m) * 32u + (31u - (uint32_t)__builtin_clz(m));
-    };
-    for (int l = 0; l < L; ++l) ++count[key_of(vis[l]) + 1];
-    for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
-    for (int l = 0; l < L; ++l) {
-      const uint32_t j = count[key_of(vis[l])]++;
-      S.perm[j] = (uint32_t)l;
-      inv[l] = j;
-    }
+    uint32_t* trange = reinterpret_cast<uint32_t*>(H + o_trange);
+    sort_landmarks_by_frame_range(vis.data(), L, S.perm.data(), inv, trange);     // okb_hostpack.hpp
     uint32_t* vis_s = reinterpret_cast<uint32_t*>(H + o_vis);
     double* lm_s = reinterpret_cast<double*>(H + o_lm);
-    uint32_t* trange = reinterpret_cast<uint32_t*>(H + o_trange);
-    for (int t = 0; t < n_tiles; ++t) trange[t] = 1u;      // first = 1 > last = 0: nothing observed
     for (int j = 0; j < L; ++j) {
-      const uint32_t l = S.perm[j], m = vis[l];
-      vis_s[j] = m;
+      const uint32_t l = S.perm[j];
+      vis_s[j] = vis[l];
       std::memcpy(lm_s + 4 * (size_t)j, D->landmarks + 4 * (size_t)l, sizeof(double) * 4);
-      if (m) {
-        const uint32_t fi = (uint32_t)__builtin_ctz(m), la = 31u - (uint32_t)__builtin_clz(m);
-        uint32_t& tr = trange[j >> 5];
-        const uint32_t a = tr & 0xffu, b = tr >> 8;
-        tr = (a > b) ? (fi | (la << 8)) : (std::min(a, fi) | (std::max(b, la) << 8));
-      }
     }
   }
   if (D->n_obs) std::memcpy(H + o_obsl, D->obs, sizeof(okb_observation) * D->n_obs);

@@ -43,3 +43,10 @@ int hc_imu_propagate(const okb_imu_params* prm, const okb_imu_sample* s, int n, 
   return imu_propagate(cx, s, n, *prm, t0, t1, pose, sb, cov, jac, wk);
 }
 }
+
+
+// ---- host packing logic (okb_hostpack.hpp)
+#include "../../okvis_b200/csrc/okb_hostpack.hpp"
+extern "C" void hc_sort_landmarks(const uint32_t* vis, int L, uint32_t* perm, uint32_t* inv, uint32_t* tile_range) {
+  okb::sort_landmarks_by_frame_range(vis, L, perm, inv, tile_range);
+}

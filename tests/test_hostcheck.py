@@ -19,7 +19,8 @@ def hc():
     src = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
     so = os.path.join(HERE, "hostcheck", "libhostcheck.so")
     deps = [src, os.path.join(HERE, "..", "okvis_b200", "csrc", "okb_math.cuh"),
-            os.path.join(HERE, "..", "okvis_b200", "csrc", "okb_imu.cuh")]
+            os.path.join(HERE, "..", "okvis_b200", "csrc", "okb_imu.cuh"),
+            os.path.join(HERE, "..", "okvis_b200", "csrc", "okb_hostpack.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-x", "c++", "-shared", "-o", so, src])
     return C.CDLL(so)
@@ -139,3 +140,45 @@ def test_imu_matches_oracle(hc, oracle):
                 assert np.abs(a - b).max() < 1e-6 * np.abs(b).max()
             # cost parity (what the solver sees)
             assert abs(r @ r - r0 @ r0) < 1e-7 * (r0 @ r0)
+
+
+def test_landmark_sort_by_frame_range(hc):
+    """okb_window_upload's internal landmark order (okb_hostpack.hpp): a stable permutation sorted by
+    (first, last) observing frame, unobserved landmarks last, consistent inverse map and per-tile frame ranges."""
+    rng = np.random.default_rng(5)
+    for L in (1, 31, 32, 33, 300, 2000):
+        K = int(rng.integers(2, 21))
+        vis = np.zeros(L, np.uint32)
+        for l in range(L):
+            kind = rng.integers(0, 10)
+            if kind == 0:
+                continue                                            # unobserved
+            a = int(rng.integers(0, K)); b = int(rng.integers(a, K))
+            m = ((1 << (b + 1)) - 1) ^ ((1 << a) - 1)                # run [a, b]
+            if kind == 1:
+                m &= int(rng.integers(1, 1 << 20)) | (1 << a) | (1 << b)   # gaps inside the run
+            vis[l] = m
+        perm, inv = np.zeros(L, np.uint32), np.zeros(L, np.uint32)
+        n_tiles = (L + 31) // 32
+        tr = np.zeros(n_tiles, np.uint32)
+        hc.hc_sort_landmarks(p(vis), L, p(perm), p(inv), p(tr))
+        assert sorted(perm.tolist()) == list(range(L))
+        assert np.array_equal(inv[perm], np.arange(L))
+
+        def key(m):
+            m = int(m)
+            if m == 0:
+                return 32 * 32
+            return ((m & -m).bit_length() - 1) * 32 + (m.bit_length() - 1)
+        keys = [key(vis[l]) for l in perm]
+        assert keys == sorted(keys)
+        for k in set(keys):                                         # stable inside a key
+            idx = [int(perm[j]) for j in range(L) if keys[j] == k]
+            assert idx == sorted(idx)
+        for t in range(n_tiles):
+            ms = [int(vis[perm[j]]) for j in range(32 * t, min(L, 32 * t + 32)) if vis[perm[j]]]
+            a, b = int(tr[t]) & 0xff, int(tr[t]) >> 8
+            if not ms:
+                assert a > b
+            else:
+                assert a == min((m & -m).bit_length() - 1 for m in ms) and b == max(m.bit_length() - 1 for m in ms)
