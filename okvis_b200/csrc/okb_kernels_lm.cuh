@@ -1,13 +1,13 @@
 // Landmark-side kernels of the solver round (sm_100a):
 //   k_linearize ("A1"): one thread per (landmark, frame).  Reprojection residuals + Jacobian factors of
 //       the frame's cameras, Cauchy weighting, per-frame M_f = sum rho' A^T A and m_f = sum rho' A^T r
-//       (stored, [K][L] layouts -> fully coalesced), plus the pose-block contributions
-//       H_pp,f = G^T M_f G and g_p,f = G^T m_f reduced per CTA.  Light on registers: many resident
-//       warps hide the FP64 dependency chains.
-//   k_schur ("A2"): one CTA per (landmark chunk, window), tiles of 32 landmarks.  Landmark block
-//       H_ll = sum_f M_f, (H_ll + mu E)^-1 by Cholesky, Y_f = W_f L^-T into a shared-memory tile, then the
-//       Schur complement as a register-tiled dense SYRK  S += Y Y^T (4x4 micro-tiles, accumulators live
-//       in registers for the whole chunk).
+//       (stored tile-major, see lm_M_index), plus the pose-block contributions H_pp,f = G^T M_f G and
+//       g_p,f = G^T m_f reduced per CTA.  All global loads are issued up front; CTAs whose landmarks
+//       do not see the frame exit immediately (landmarks are sorted by observing-frame range).
+//   k_lmblock ("A1b"): one thread per landmark: H_ll = sum_f M_f, (H_ll + mu E)^-1 by 3x3 Cholesky.
+//   k_schur ("A2"): one CTA per (landmark chunk, window), tiles of 32 landmarks staged by TMA bulk copies:
+//       Y_f = W_f L^-T into a shared-memory tile, then the Schur complement as a block-sparse SYRK
+//       S += Y Y^T with one lane per 6x6 frame-block pair (details at the kernel).
 //   k_quality: post-solve landmark quality (Estimator.cpp:880-894), one thread per landmark.
 #pragma once
 #include "okb_estimator.cuh"
@@ -263,20 +263,22 @@ __global__ void __launch_bounds__(128) k_lmblock(const WinDev* __restrict__ wins
 // reduced right-hand side).
 //
 // Landmarks arrive sorted by (first, last) observing frame, so a tile of 32 consecutive landmarks only
-// touches the frames [a, b] listed in W.tile_range.  The SYRK is therefore done per 6x6 frame block over
-// the u(u+1)/2 block pairs of the tile's range (u = b-a+1) instead of the dense K(K+1)/2: one lane owns one
-// block pair (36 accumulators in registers, 12 operand doubles per 36 multiply-adds) and KS in {1,2,4,8} adjacent lanes split the
-// tile's columns.  The lane -> block-pair map only depends on (a, b); accumulators stay in registers
-// across tiles with the same range and are flushed (shuffle-reduced over the KS lanes, then added to the
-// chunk's partial in global memory by one lane, fixed order => deterministic) when the range changes.
+// touches the frames [a, b] listed in W.tile_range.  The SYRK is done per 6x6 frame block: one lane owns one
+// block pair (36 accumulators in registers, 12 operand doubles per 36 multiply-adds) and KS <= 8 adjacent
+// lanes of the same warp split the tile's 96 columns.  The lane -> block-pair map covers the frames
+// [a, K-1] and is rebuilt only when the tile's first frame a changes (landmarks are sorted by it: at most K
+// times per chunk); lanes whose pair reaches beyond the tile's last frame b sit the tile out, and since pairs
+// are dealt to the warps row-major, whole warps skip narrow tiles.  On a rebuild the accumulators are summed
+// over the KS lanes with shuffles (fixed order) and added by one lane to the chunk's packed accumulator in
+// shared memory (or to the global partial for windows with many frames): one writer per element, no barrier
+// => deterministic.
 // ------------------------------------------------------------------------------------------------
 constexpr int kLiStride = 9;   // L^-1 (6) | z (3), as in global memory (one bulk copy per tile)
 
 __host__ __device__ inline int schur_ldy(int dcp) { return dcp + 2; }   // Y row stride: rows shift by 16 B across banks
 
-// acc_copies: number of copies of the chunk's Schur accumulator (packed lower triangle of the (dc+1) x (dc+1)
-// matrix) kept in shared memory, one per column split, so that flushes need no ordering between splits;
-// 0: accumulate in the chunk's global partial instead (windows with many frames).
+// acc_copies: 1 = the chunk's Schur accumulator (packed lower triangle of the (dc+1) x (dc+1) matrix) lives in
+// shared memory; 0 = accumulate in the chunk's global partial instead (windows with many frames).
 __host__ __device__ inline size_t schur_acc_doubles(int K) { return (size_t)(6 * K + 1) * (6 * K + 2) / 2; }
 __host__ __device__ inline size_t smemA2_bytes(int K, int dcp, int acc_copies) {
   size_t b = 16;                                                    // two mbarriers (TMA completion per buffer)
