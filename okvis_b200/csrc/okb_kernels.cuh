@@ -1,12 +1,11 @@
-// Kernels of the batched dogleg/Schur solver (sm_100a).  Two kernels per solver round:
-//   k_landmarks ("A"): one CTA per (landmark chunk, window).  Warp per landmark, lane per
-//       (frame,camera) slot: reprojection residual + Jacobian factors, Cauchy weighting, landmark
-//       block H_ll / g_l, (H_ll + mu E)^-1, per-frame M_f; Schur complement accumulated as a
-//       register-tiled dense SYRK  S += Y Y^T over shared-memory tiles of Y = W L^-T.
-//   k_solve ("S"): one CTA per window.  IMU / prior / marginalisation terms, step acceptance
-//       (Ceres 1.9 trust-region logic), dense Cholesky of the reduced system, back-substitution,
-//       traditional dogleg step, candidate state.
-// plus k_quality (post-solve landmark quality, Estimator.cpp:880-894) and small utility kernels.
+// Kernels of the batched dogleg/Schur solver (sm_100a).  One solver round is
+//   k_imu (side stream) || k_linearize -> k_lmblock -> k_schur -> k_reduce_partials   (okb_kernels_lm.cuh), then
+//   k_solve ("S"): one CTA of 256 threads per window, two CTAs per SM.  IMU / prior / marginalisation terms
+//       assembled directly in the shared-memory system buffer (packed lower triangle), step acceptance
+//       (Ceres 1.9 trust-region logic), blocked Cholesky with the right-hand side as an appended row,
+//       backward substitution, landmark back-substitution, traditional dogleg step, candidate state and
+//       the (frame, camera) contexts of the next linearisation.
+// plus k_imu (one warp per IMU term), k_zero / k_prepare (upload epilogue on the transfer stream), k_reset.
 #pragma once
 #include "okb_chol.cuh"
 #include "okb_estimator.cuh"
