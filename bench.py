@@ -76,6 +76,28 @@ def make_windows(n_distinct, base_idx):
     return [synthetic.make_window(2, base_idx + i) for i in range(n_distinct)]
 
 
+def host_cpus():
+    """CPUs this process may really use: os.cpu_count() capped by the affinity mask and the cgroup CPU quota."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(round(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p_ = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(round(q / p_))))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
 def cpu_oracle_pass(windows, n_win, threads):
     """One bounded CPU sample: n_win cfg-2 windows, each solved by one oracle thread (optimize(ITERS) + the
     landmark-quality pass of Estimator::optimize), `threads` windows in flight.  Building the problems (the
@@ -104,12 +126,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cpus()
     windows = make_windows(8, 0)
-    # warm-up doubles as the choice of the thread count: all hardware threads are not always the fastest
-    # configuration (SMT siblings, memory bandwidth), so the best of {all, half, quarter} is kept
+    # warm-up doubles as the choice of the thread count: the usable CPUs (cgroup quota, affinity) and a little
+    # oversubscription are tried and the fastest configuration is kept
     best_t, best_rate = cores, 0.0
-    cand = sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True)
+    cand = sorted({cores, 2 * cores, max(1, cores // 2)}, reverse=True)
     for wstep in range(max(args.warmup, len(cand))):
         t_ = cand[wstep % len(cand)]
         it, dt = cpu_oracle_pass(windows, 2 * t_, t_)
@@ -309,10 +331,10 @@ def run_b200(args):
                 traffic = traffic * B / float(tj.get("windows", B))
                 traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read+write.sum of the three kernels at %d windows)" % tj.get("windows", B)
         # CPU baseline: bounded sample of the same workload on this box's host cores -- one oracle thread per
-        # window, the best of {all, half} hardware threads in flight (the windows are independent)
-        cores = os.cpu_count() or 1
+        # window; as many windows in flight as there are usable CPUs (cgroup quota) or twice that, whichever is faster
+        cores = host_cpus()
         cpu_iters, cpu_dt, n_cpu = 0, 1.0, 1
-        for t_ in ([1] if args.skip_cpu else sorted({cores, max(1, cores // 2)}, reverse=True)):
+        for t_ in ([1] if args.skip_cpu else sorted({cores, 2 * cores}, reverse=True)):
             it_, dt_ = cpu_oracle_pass(windows, t_, t_)
             if it_ / dt_ > cpu_iters / cpu_dt:
                 cpu_iters, cpu_dt, n_cpu = it_, dt_, t_
