@@ -566,7 +566,7 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
     prof_begin(c, 0);
     k_linearize<<<dim3(max_cx, max_K, count), L1_THREADS, 0, c->stream>>>(c->d_wins, first);
     k_lmblock<<<dim3(max_cx, count), 128, 0, c->stream>>>(c->d_wins, first);
-    k_schur<<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first, acc_copies);
+    k_schur<<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first, acc_copies, opt.max_iterations);
     if (max_chunks > 1) { k_reduce_partials<<<dim3(8, count), 256, 0, c->stream>>>(c->d_wins, first); c->launches += 1; }
     prof_end(c);
     c->launches += 2;

@@ -488,7 +488,6 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
 namespace {
 constexpr int MT = 128;          // threads per CTA = A rows per CTA
 constexpr int MB_TILE = 128;     // B descriptors staged per shared-memory tile
-constexpr int MAX_WORDS = 32;    // descriptor words (<= 128 bytes)
 constexpr int MAX_BEST = 8;
 
 // thread per A: sequential scan over B with the reference's insertion rule (listBIteration)

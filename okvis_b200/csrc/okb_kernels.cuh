@@ -115,7 +115,7 @@ __device__ __forceinline__ void hd_add(double* Hd, int r, int c, double v) {
 }
 
 __device__ void dense_priors(const WinDev& W, double* Hd, double* gd, double* cost_out) {
-  const int lane = threadIdx.x & 31, d = W.d;
+  const int lane = threadIdx.x & 31;
   double cost = 0.0;
   for (int i = 0; i < W.n_pp; ++i) {
     const okb_pose_prior& pr = W.pp[i];
@@ -442,48 +442,55 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       s_v[i] = gd[i] / E;
     }
     __syncthreads();
-    // VHV (dense-dense part): v^T H v
-    double vhv_loc = 0.0;
-    for (int i = tid; i < d; i += S_THREADS) {     // v^T H v from the lower triangle
-      const double* hrow = Hd + tri_row(i);
-      double s = 0;
-      for (int j = 0; j < i; ++j) s += hrow[j] * s_v[j];
-      vhv_loc += s_v[i] * (2.0 * s + hrow[i] * s_v[i]);
-    }
-    const double VHV_dd = block_sum(vhv_loc, sh->red);
-    // reduced system M = Hd + mu E - [Sacc], rhs = g - [sum Y z]
-    double* Mx = chol_in_smem ? s_big : W.chol;
-    const double mu = st->mu;
-    for (int i = tid; i < d * d; i += S_THREADS) {
-      const int r0 = i / d, c0 = i % d;
-      if (c0 > r0) continue;                      // the factorisation only references the lower triangle
-      double v = Hd[tri_row(r0) + c0];            // in place when the system lives in shared memory
-      if (r0 == c0) v += mu * s_E[r0];
-      if (r0 < dc && c0 < dc) {
-        v -= W.partA[(size_t)r0 * dcp + c0];     // chunk partials were summed by k_reduce_partials
-      }
-      Mx[tri_row(r0) + c0] = v;
-    }
-    for (int i = tid; i < d; i += S_THREADS) {
-      double v = s_g[i];
-      if (i < dc) {
-        v -= W.partA[(size_t)dc * dcp + i];
-      }
-      s_rhs[i] = v;
-      Mx[tri_row(d) + i] = v;            // appended row: the right-hand side
-    }
-    __syncthreads();
-    PHASE_MARK(2);
-    // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh); row d comes out as z = L^-1 rhs
+    // If the iteration limit is reached, the step that was just judged is the last one: the new linearisation
+    // is only committed (state, gradient norm for the tolerance test) -- no reduced system, no factorisation,
+    // no new step (k_schur skips the same rounds).
+    const bool skip_solve = (st->iteration >= opt.max_iterations) && !sh->fail;
+    double VHV_dd = 0.0;
     int chol_fail = sh->fail;
-    if (!chol_fail) chol_fail = block_cholesky(Mx, d, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8);
-    PHASE_MARK(3);
-    if (!chol_fail) {
-      for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = Mx[tri_row(d) + i];
+    if (!skip_solve) {
+      // VHV (dense-dense part): v^T H v
+      double vhv_loc = 0.0;
+      for (int i = tid; i < d; i += S_THREADS) {     // v^T H v from the lower triangle
+        const double* hrow = Hd + tri_row(i);
+        double s = 0;
+        for (int j = 0; j < i; ++j) s += hrow[j] * s_v[j];
+        vhv_loc += s_v[i] * (2.0 * s + hrow[i] * s_v[i]);
+      }
+      VHV_dd = block_sum(vhv_loc, sh->red);
+      // reduced system M = Hd + mu E - [Sacc], rhs = g - [sum Y z]
+      double* Mx = chol_in_smem ? s_big : W.chol;
+      const double mu = st->mu;
+      for (int i = tid; i < d * d; i += S_THREADS) {
+        const int r0 = i / d, c0 = i % d;
+        if (c0 > r0) continue;                      // the factorisation only references the lower triangle
+        double v = Hd[tri_row(r0) + c0];            // in place when the system lives in shared memory
+        if (r0 == c0) v += mu * s_E[r0];
+        if (r0 < dc && c0 < dc) {
+          v -= W.partA[(size_t)r0 * dcp + c0];     // chunk partials were summed by k_reduce_partials
+        }
+        Mx[tri_row(r0) + c0] = v;
+      }
+      for (int i = tid; i < d; i += S_THREADS) {
+        double v = s_g[i];
+        if (i < dc) {
+          v -= W.partA[(size_t)dc * dcp + i];
+        }
+        s_rhs[i] = v;
+        Mx[tri_row(d) + i] = v;            // appended row: the right-hand side
+      }
       __syncthreads();
-      block_cholesky_backward(Mx, d, s_col, s_tmp);
-      for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
-      __syncthreads();
+      PHASE_MARK(2);
+      // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh); row d comes out as z = L^-1 rhs
+      if (!chol_fail) chol_fail = block_cholesky(Mx, d, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8);
+      PHASE_MARK(3);
+      if (!chol_fail) {
+        for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = Mx[tri_row(d) + i];
+        __syncthreads();
+        block_cholesky_backward(Mx, d, s_col, s_tmp);
+        for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
+        __syncthreads();
+      }
     }
     PHASE_MARK(4);
     // ---- landmarks: commit, back-substitute, scalar reductions
@@ -497,6 +504,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       xn2 += X.x * X.x + X.y * X.y + X.z * X.z + X.w * X.w;
       if (chol_fail) continue;
       const double g0 = gl_[3 * (size_t)l], g1 = gl_[3 * (size_t)l + 1], g2 = gl_[3 * (size_t)l + 2];
+      if (skip_solve) { gmax = fmax(gmax, fmax(fabs(g0), fmax(fabs(g1), fabs(g2)))); continue; }
       const double E0 = El_[3 * (size_t)l], E1 = El_[3 * (size_t)l + 1], E2 = El_[3 * (size_t)l + 2];
       const double v0 = g0 / E0, v1 = g1 / E1, v2 = g2 / E2;
       double q0 = 0, q1 = 0, q2 = 0;        // sum_f M_f (G_f u_f)
@@ -538,7 +546,9 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
     }
     for (int i = tid; i < d; i += S_THREADS) {
       if (chol_fail) break;
-      const double u = s_u[i], g = s_g[i], E = s_E[i];
+      const double g = s_g[i], E = s_E[i];
+      if (skip_solve) { gmax = fmax(gmax, fabs(g)); continue; }
+      const double u = s_u[i];
       if (!isfinite(u)) bad = 1;
       N2 += E * u * u; GU += g * u; G2 += g * g / E;
       gmax = fmax(gmax, fabs(g));

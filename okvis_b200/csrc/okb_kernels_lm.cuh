@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
   const int f = blockIdx.y;
   const int cx = blockIdx.x;
   if (f >= W.K || cx * L1_THREADS >= W.L) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int L = W.L, CP = W.CP;
 
   __shared__ SlotCtx slots[32];                 // the frame's cameras (CP <= 32)
@@ -315,10 +315,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restrict__ wins, int win_first, int acc_copies) {
+__global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restrict__ wins, int win_first, int acc_copies, int max_iterations) {
   const WinDev& W = wins[win_first + blockIdx.y];
   SolverState* st = W.st;
   if (st->done) return;
+  // the step being judged in this round is the last one (iteration limit): k_solve will not build another
+  // reduced system, so the Schur complement of this linearisation is never used
+  if (st->iteration >= max_iterations) return;
   const int chunk = blockIdx.x;
   if (chunk >= W.n_chunks) return;
   const int tid = threadIdx.x;
