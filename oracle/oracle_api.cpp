@@ -5,6 +5,7 @@
 
 #include "oracle_brisk.hpp"
 #include "oracle_errors.hpp"
+#include "oracle_marg.hpp"
 #include "oracle_matcher.hpp"
 #include "oracle_solver.hpp"
 #ifdef _OPENMP
@@ -163,6 +164,34 @@ int oko_hamming_candidates(const uint8_t* A, int nA, const uint8_t* B, int nB, i
 int oko_detect_describe(const uint8_t* img, int W, int H, int stride, const okb_camera* cam, const double* R_CW,
                         const okb_detect_params* prm, okb_keypoint* kps, uint8_t* desc, int max_out) {
   return detect_describe(img, W, H, stride, *cam, R_CW, *prm, kps, desc, max_out);
+}
+
+// ---- marginalisation numeric core (NEXT TIER groundwork, oracle_marg.hpp)
+// ranges: [n_ranges][2] = (start, length), sorted and non-overlapping.  H (n x n) / b are overwritten with the reduced
+// system in their leading n_out * n_out / n_out entries (row stride n_out).  Returns n_out.
+int oko_marginalize_stage(double* H, double* b, int n, const int* ranges, int n_ranges, int landmark_blocks) {
+  std::vector<double> Hv(H, H + (size_t)n * n), bv(b, b + n);
+  std::vector<std::pair<int, int>> r;
+  for (int i = 0; i < n_ranges; ++i) r.emplace_back(ranges[2 * i], ranges[2 * i + 1]);
+  int nn = n;
+  marginalize_stage(Hv, bv, nn, r, landmark_blocks != 0);
+  std::memcpy(H, Hv.data(), sizeof(double) * (size_t)nn * nn);
+  std::memcpy(b, bv.data(), sizeof(double) * nn);
+  return nn;
+}
+int oko_marg_update_error_computation(const double* H, const double* b, int n, double* J, double* e0) {
+  std::vector<double> Hv(H, H + (size_t)n * n), bv(b, b + n), Jv, ev;
+  const int rank = marg_update_error_computation(Hv, bv, n, Jv, ev);
+  std::memcpy(J, Jv.data(), sizeof(double) * (size_t)n * n);
+  std::memcpy(e0, ev.data(), sizeof(double) * n);
+  return rank;
+}
+int oko_sym_eig(const double* A, int n, double* evals, double* evecs) {
+  std::vector<double> Av(A, A + (size_t)n * n), ev, V;
+  sym_eig(Av, n, ev, V);
+  std::memcpy(evals, ev.data(), sizeof(double) * n);
+  std::memcpy(evecs, V.data(), sizeof(double) * (size_t)n * n);
+  return 0;
 }
 
 }  // extern "C"

@@ -303,3 +303,40 @@ def detect_describe(img, cam, R_CW, uniformity_radius=40.0, absolute_threshold=8
           C.c_void_p(R.ctypes.data), C.byref(prm), C.c_void_p(kps.ctypes.data), C.c_void_p(desc.ctypes.data),
           C.c_int(max_keypoints))
     return kps[:n].copy(), desc[:n].copy()
+
+
+# ---- marginalisation numeric core (NEXT TIER groundwork: oracle only, no device path yet)
+def _vp(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def marginalize_stage(H, b, ranges, landmark_blocks):
+    """One stage of MarginalizationError::marginalizeOut (MarginalizationError.cpp:618-741) on a copy of (H, b)."""
+    H = np.ascontiguousarray(H, dtype=np.float64).copy()
+    b = np.ascontiguousarray(b, dtype=np.float64).copy()
+    n = H.shape[0]
+    r = np.ascontiguousarray(np.asarray(ranges, dtype=np.int32).reshape(-1, 2))
+    f = lib().oko_marginalize_stage
+    f.restype = C.c_int
+    m = f(_vp(H), _vp(b), C.c_int(n), _vp(r), C.c_int(len(r)), C.c_int(int(bool(landmark_blocks))))
+    return H.reshape(-1)[:m * m].reshape(m, m).copy(), b[:m].copy()
+
+
+def marg_update_error_computation(H, b):
+    """MarginalizationError::updateErrorComputation (MarginalizationError.cpp:806-846): returns J, e0, rank."""
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    n = H.shape[0]
+    J, e0 = np.zeros((n, n)), np.zeros(n)
+    f = lib().oko_marg_update_error_computation
+    f.restype = C.c_int
+    rank = f(_vp(H), _vp(b), C.c_int(n), _vp(J), _vp(e0))
+    return J, e0, rank
+
+
+def sym_eig(A):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    w, V = np.zeros(n), np.zeros((n, n))
+    lib().oko_sym_eig(_vp(A), C.c_int(n), _vp(w), _vp(V))
+    return w, V
