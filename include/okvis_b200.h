@@ -200,7 +200,9 @@ void* okb_stream(const okb_ctx* ctx);
  * sorted by observing-frame range; indices and results at this boundary always use the caller's order.  A slot must
  * not be uploaded while an okb_optimize_async on it is still in flight (call okb_optimize_finish first). */
 int okb_window_upload(okb_ctx* ctx, int win, const okb_window_desc* desc);
-/* Uploads `count` windows into slots [win_first, win_first+count); descs[i] describes slot win_first+i.
+/* Batched form of okb_window_upload (no reference counterpart: one okvis::Estimator owns one window; this serves
+ * callers that keep many estimators / sessions on one GPU).  Uploads `count` windows into slots
+ * [win_first, win_first+count); descs[i] describes slot win_first+i.
  * The packing of different slots is spread over up to `host_threads` host threads (<= 0: library default).
  * Uploads run on the context's transfer stream: they overlap solver work already launched on OTHER
  * slots, and every later okb_optimize* / okb_window_reset is ordered after them.  Uploads of different slots
@@ -223,7 +225,8 @@ int okb_optimize_finish(okb_ctx* ctx, int win_first, int win_count, okb_summary*
  * of the landmark's 3x3 Hessian block as in Estimator.cpp:880-894 (0 if lambda_min < 1e-12). */
 int okb_window_download(okb_ctx* ctx, int win, double* poses, double* speed_bias,
                         double* landmarks, double* quality);
-/* Downloads the estimates of `count` slots with one synchronisation.  Each argument is an array of `count`
+/* Batched form of okb_window_download (no reference counterpart).  Downloads the estimates of `count` slots with one
+ * synchronisation.  Each argument is an array of `count`
  * host pointers (or NULL to skip that quantity; individual entries may be NULL too).  Like the uploads this
  * runs on the transfer stream: it waits only for solver work launched on these slots, not for other slots. */
 int okb_window_download_batch(okb_ctx* ctx, int win_first, int count, double* const* poses,
