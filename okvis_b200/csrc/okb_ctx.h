@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/okvis_b200.h"
 #include "okb_estimator.cuh"
 
 struct WinStore {
@@ -20,6 +21,7 @@ struct WinStore {
   size_t out_bytes = 0;
   cudaEvent_t down = nullptr;         // recorded after the D2H copies of a download
   std::vector<uint32_t> perm;         // internal (sorted) landmark index -> caller's index
+  okb_solve_options opt{};            // options of the last okb_optimize_async on this slot
   int done_idx = -1;                  // index into okb_ctx::done_ring of the last solver work launched on this slot
 };
 
@@ -49,7 +51,6 @@ struct okb_ctx {
   okb::WinDev* d_wins = nullptr;
   okb::SolverState* d_states = nullptr;
   okb::SolverState* h_states = nullptr;  // pinned
-  okb_solve_options last_opt{};
   void* hook_buf = nullptr;
   size_t hook_bytes = 0;
   okb_frontend_state* frontend = nullptr;

@@ -273,7 +273,34 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
   const size_t zero_bytes = P.total - o_zero;
   const size_t o_imu_out = P.take(sizeof(double) * kImuOut * std::max(W.n_imu, 1));
 
+  // ---- validation of everything that is copied to the device unchecked, BEFORE the slot is touched
+  for (int i = 0; i < D->n_pose_priors; ++i)
+    if ((int)D->pose_priors[i].pose_idx >= K) { c->set_error("pose prior index out of range"); return OKB_ERR_INVALID_ARG; }
+  for (int i = 0; i < D->n_sb_priors; ++i)
+    if ((int)D->sb_priors[i].sb_idx >= NSB) { c->set_error("speed/bias prior index out of range"); return OKB_ERR_INVALID_ARG; }
+  for (int t = 0; t < D->n_imu_terms; ++t) {
+    const okb_imu_term& T = D->imu_terms[t];
+    if ((int)T.pose0 >= K || (int)T.pose1 >= K || (int)T.sb0 >= NSB || (int)T.sb1 >= NSB ||
+        (uint64_t)T.sample_offset + (uint64_t)T.sample_count > (uint64_t)D->n_imu_samples || T.sample_count < 2) {
+      c->set_error("IMU term index out of range");
+      return OKB_ERR_INVALID_ARG;
+    }
+  }
+  if (marg_n) {
+    int col = 0;
+    for (int b = 0; b < marg_nb; ++b) {
+      const int kind = D->marg->block_kind[b];
+      const uint32_t idx = D->marg->block_idx[b];
+      const int lim = kind == OKB_BLOCK_POSE ? K : kind == OKB_BLOCK_SPEED_BIAS ? NSB : kind == OKB_BLOCK_EXTRINSICS ? NE : -1;
+      if (lim < 0) { c->set_error("marginalisation prior: unknown block kind"); return OKB_ERR_INVALID_ARG; }
+      if ((int)idx >= lim) { c->set_error("marginalisation prior: block index out of range"); return OKB_ERR_INVALID_ARG; }
+      if (kind != OKB_BLOCK_EXTRINSICS) col += (kind == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
+    }
+    if (col != marg_n) { c->set_error("marginalisation prior dimension mismatch"); return OKB_ERR_INVALID_ARG; }
+  }
+
   WinStore& S = c->wins[win];
+  S.uploaded = false;        // true again only when the whole upload has been issued successfully
   if (S.arena_bytes < P.total) {
     if (S.arena) cudaFree(S.arena);
     S.arena = nullptr; S.arena_bytes = 0;
@@ -346,14 +373,6 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
     }
   }
   if (D->n_obs) std::memcpy(H + o_obsl, D->obs, sizeof(okb_observation) * D->n_obs);
-  for (int t = 0; t < W.n_imu; ++t) {
-    const okb_imu_term& T = D->imu_terms[t];
-    if ((int)T.pose0 >= K || (int)T.pose1 >= K || (int)T.sb0 >= NSB || (int)T.sb1 >= NSB ||
-        T.sample_offset + T.sample_count > (uint32_t)W.n_samples || T.sample_count < 2) {
-      c->set_error("IMU term index out of range");
-      return OKB_ERR_INVALID_ARG;
-    }
-  }
   if (marg_n) {
     const okb_marg_prior& M = *D->marg;
     int32_t* mk = reinterpret_cast<int32_t*>(H + o_mkind);
@@ -368,7 +387,6 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
       if (!fixed) col += (M.block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
       xo += (M.block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
     }
-    if (col != marg_n) { c->set_error("marginalisation prior dimension mismatch"); return OKB_ERR_INVALID_ARG; }
     std::memcpy(H + o_mx0, M.x0, sizeof(double) * marg_xdim);
     std::memcpy(H + o_mJ, M.J, sizeof(double) * marg_n * marg_n);
     std::memcpy(H + o_me0, M.e0, sizeof(double) * marg_n);
@@ -616,7 +634,7 @@ extern "C" int okb_optimize_async(okb_ctx* c, int first, int count, const okb_so
   OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + first, &c->host[first], sizeof(WinDev) * count, cudaMemcpyHostToDevice, c->stream));
   k_reset<<<count, 128, 0, c->stream>>>(c->d_wins, first, 0);
   c->launches += 1;
-  c->last_opt = *opt;
+  for (int i = first; i < first + count; ++i) c->wins[i].opt = *opt;     // okb_optimize_finish relaunches with the range's own options
   // round 0 linearises at the initial state; each later round judges one step and proposes the next
   rc = launch_rounds(c, first, count, *opt, opt->max_iterations + 1);
   if (rc) return rc;
@@ -638,7 +656,7 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
     bool all_done = true;
     for (int i = first; i < first + count; ++i) all_done = all_done && c->h_states[i].done;
     if (all_done) break;
-    rc = launch_rounds(c, first, count, c->last_opt, 2);
+    rc = launch_rounds(c, first, count, c->wins[first].opt, 2);
     if (rc) return rc;
     rc = launch_quality(c, first, count);
     if (rc) return rc;
