@@ -232,6 +232,28 @@ int okb_window_download(okb_ctx* ctx, int win, double* poses, double* speed_bias
 int okb_window_download_batch(okb_ctx* ctx, int win_first, int count, double* const* poses,
                               double* const* speed_bias, double* const* landmarks, double* const* quality);
 
+/* ----------------------------------------------------- landmark-sharded single window (multi-GPU)
+ * No reference counterpart (the reference is single-process CPU code); this is the partition SURVEY.md 8(e) row 2 /
+ * BASELINE.json configs[4] name: the landmarks (and their observations) of ONE large window are dealt to `world`
+ * ranks (lm_idx mod world), every rank holds all poses / speed-bias / IMU / prior blocks.  Per solver round each
+ * rank builds the Schur complement of its shard, the partial reduced systems are all-reduced over NVLink peer
+ * memory (push into every rank's mailbox + flags, fused into the chunk-reduction kernel and the reduced-solve
+ * kernel's prologue), every rank solves the reduced system redundantly and back-substitutes its own landmarks.
+ * A context is made a shard member BEFORE its windows are uploaded; every rank then uploads its shard into the
+ * same slot and all ranks issue the same okb_optimize* calls.  time_limit_s uses rank 0's clock.
+ *   multi-process (one process per GPU): okb_shard_export on every rank, exchange the OKB_SHARD_HANDLE_BYTES-byte
+ *     handles out of band (e.g. torch.distributed.all_gather), okb_shard_connect with all `world` handles in rank order.
+ *   single process driving several contexts (same or different devices): okb_shard_connect_local.
+ * max_frames bounds the keyframes of any sharded window (mailbox sizing). */
+#define OKB_SHARD_HANDLE_BYTES 64
+int okb_shard_export(okb_ctx* ctx, int rank, int world, int max_frames, void* handle_out /* OKB_SHARD_HANDLE_BYTES */);
+int okb_shard_connect(okb_ctx* ctx, const void* handles /* [world][OKB_SHARD_HANDLE_BYTES] */);
+int okb_shard_connect_local(okb_ctx* const* ctxs /* [world], rank order */, int world, int max_frames);
+/* After okb_optimize_finish: out[0] = exchange rounds of the last optimize of `win`, out[1] = microseconds this rank
+ * spent waiting for and summing the peers' partial systems (device clock), out[2] = 1 if a peer timed out,
+ * out[3] = exchange epoch. */
+int okb_shard_stats(okb_ctx* ctx, int win, double out[4]);
+
 /* Optional per-kernel device timing: CUDA events on the context stream around every solver kernel
  * launch.  okb_profile_enable(ctx,1) clears the counters; okb_profile_read synchronises and returns
  * out[0] = ms in k_landmarks, out[1] = its launches, out[2] = ms in k_solve, out[3] = launches,

@@ -73,6 +73,29 @@ class Context:
         return dict(landmarks_ms=out[0], landmarks_launches=int(out[1]), solve_ms=out[2], solve_launches=int(out[3]),
                     quality_ms=out[4], quality_launches=int(out[5]))
 
+    # ---------------------------------------------------------------- landmark-sharded window (multi-GPU)
+    def shard_export(self, rank, world, max_frames=32):
+        """okb_shard_export: allocates this rank's mailbox; returns the 64-byte IPC handle (numpy uint8)."""
+        h = np.zeros(64, np.uint8)
+        self._check(lib().okb_shard_export(self._h, int(rank), int(world), int(max_frames), _p(h)))
+        return h
+
+    def shard_connect(self, handles):
+        h = np.ascontiguousarray(handles, dtype=np.uint8)
+        self._check(lib().okb_shard_connect(self._h, _p(h)))
+
+    @staticmethod
+    def shard_connect_local(ctxs, max_frames=32):
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        rc = lib().okb_shard_connect_local(arr, len(ctxs), int(max_frames))
+        if rc != 0:
+            raise OkbError(rc, "; ".join(lib().okb_last_error(c._h).decode() for c in ctxs))
+
+    def shard_stats(self, win=0):
+        out = np.zeros(4)
+        self._check(lib().okb_shard_stats(self._h, int(win), _p(out)))
+        return dict(rounds=int(out[0]), wait_us=float(out[1]), fault=int(out[2]), epoch=int(out[3]))
+
     # ---------------------------------------------------------------- estimator path
     def upload(self, win, window):
         d = window.desc()

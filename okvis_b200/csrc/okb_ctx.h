@@ -54,6 +54,12 @@ struct okb_ctx {
   void* hook_buf = nullptr;
   size_t hook_bytes = 0;
   okb_frontend_state* frontend = nullptr;
+  // landmark-sharded windows (okb_shard_*): this rank's mailbox and the peers' mailboxes as mapped on this device
+  int shard_rank = 0, shard_world = 1, shard_box_cap = 0;
+  size_t shard_win_bytes = 0;
+  unsigned char* shard_local = nullptr;                       // cudaMalloc'ed, exported through cudaIpc
+  unsigned char* shard_peer[okb::kMaxShard] = {};             // [rank]; own entry = shard_local
+  bool shard_peer_ipc[okb::kMaxShard] = {};                   // opened with cudaIpcOpenMemHandle (closed at destroy)
   int64_t launches = 0;
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)

@@ -109,6 +109,9 @@ extern "C" void okb_ctx_destroy(okb_ctx* c) {
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream_xfer) cudaStreamDestroy(c->stream_xfer);
   okb_frontend_release(c);
+  for (int r = 0; r < kMaxShard; ++r)
+    if (c->shard_peer_ipc[r] && c->shard_peer[r]) cudaIpcCloseMemHandle(c->shard_peer[r]);
+  if (c->shard_local) cudaFree(c->shard_local);
   if (c->d_wins) cudaFree(c->d_wins);
   if (c->d_states) cudaFree(c->d_states);
   if (c->h_states) cudaFreeHost(c->h_states);
@@ -438,6 +441,14 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
   W.marg_off = reinterpret_cast<int32_t*>(A + o_moff);
   W.marg_x0 = dp(o_mx0); W.marg_J = dp(o_mJ); W.marg_e0 = dp(o_me0); W.marg_H0 = dp(o_mH0);
   W.st = c->d_states + win;
+  W.shard_rank = c->shard_rank; W.shard_world = c->shard_world; W.shard_box_cap = c->shard_box_cap;
+  if (c->shard_world > 1) {
+    if (shard_box_doubles(K, dcp) > (size_t)c->shard_box_cap) { c->set_error("window exceeds the shard mailbox (max_frames of okb_shard_export)"); return OKB_ERR_CAPACITY; }
+    for (int r = 0; r < c->shard_world; ++r) {
+      if (!c->shard_peer[r]) { c->set_error("landmark sharding: okb_shard_connect has not been called"); return OKB_ERR_INVALID_ARG; }
+      W.shard_mail[r] = c->shard_peer[r] + (size_t)win * c->shard_win_bytes;
+    }
+  }
   c->host[win] = W;
   S.uploaded = true;
   S.h2d_bytes = input_bytes;
@@ -476,6 +487,83 @@ extern "C" int okb_window_upload_batch(okb_ctx* c, int first, int count, const o
     if (rcs[t]) return rcs[t];
   cudaSetDevice(c->device);
   return upload_finish(c, first, count);      // one k_zero + one k_prepare for the whole range
+}
+
+// ---------------------------------------------------------------------------------------------
+// landmark-sharded single window: mailbox set-up
+// ---------------------------------------------------------------------------------------------
+static int shard_alloc(okb_ctx* c, int rank, int world, int max_frames) {
+  if (!c || world < 2 || world > kMaxShard || rank < 0 || rank >= world || max_frames < 1 || max_frames > kMaxFrames) return OKB_ERR_INVALID_ARG;
+  if (c->shard_local) { c->set_error("landmark sharding is already set up on this context"); return OKB_ERR_INVALID_ARG; }
+  cudaSetDevice(c->device);
+  const int dcp = 4 * ((6 * max_frames + 1 + 3) / 4);
+  c->shard_box_cap = (int)shard_box_doubles(max_frames, dcp);
+  c->shard_win_bytes = shard_win_bytes(world, (size_t)c->shard_box_cap);
+  const size_t total = c->shard_win_bytes * (size_t)c->max_windows;
+  OKB_CUDA(c, cudaMalloc(&c->shard_local, total));
+  OKB_CUDA(c, cudaMemset(c->shard_local, 0, total));
+  OKB_CUDA(c, cudaDeviceSynchronize());
+  c->shard_rank = rank;
+  c->shard_world = world;
+  c->shard_peer[rank] = c->shard_local;
+  return OKB_OK;
+}
+
+extern "C" int okb_shard_export(okb_ctx* c, int rank, int world, int max_frames, void* handle_out) {
+  if (!handle_out) return OKB_ERR_INVALID_ARG;
+  int rc = shard_alloc(c, rank, world, max_frames);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == OKB_SHARD_HANDLE_BYTES, "handle size");
+  cudaIpcMemHandle_t h;
+  OKB_CUDA(c, cudaIpcGetMemHandle(&h, c->shard_local));
+  std::memcpy(handle_out, &h, sizeof h);
+  return OKB_OK;
+}
+
+extern "C" int okb_shard_connect(okb_ctx* c, const void* handles) {
+  if (!c || !handles || c->shard_world < 2 || !c->shard_local) return OKB_ERR_INVALID_ARG;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->shard_world; ++r) {
+    if (r == c->shard_rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * sizeof h, sizeof h);
+    void* p = nullptr;
+    OKB_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->shard_peer[r] = static_cast<unsigned char*>(p);
+    c->shard_peer_ipc[r] = true;
+  }
+  return OKB_OK;
+}
+
+extern "C" int okb_shard_connect_local(okb_ctx* const* ctxs, int world, int max_frames) {
+  if (!ctxs || world < 2 || world > kMaxShard) return OKB_ERR_INVALID_ARG;
+  for (int r = 0; r < world; ++r) {
+    if (!ctxs[r]) return OKB_ERR_INVALID_ARG;
+    if (ctxs[r]->max_windows != ctxs[0]->max_windows) { ctxs[r]->set_error("sharded contexts must have the same number of window slots"); return OKB_ERR_INVALID_ARG; }
+    const int rc = shard_alloc(ctxs[r], r, world, max_frames);
+    if (rc) return rc;
+  }
+  for (int r = 0; r < world; ++r) {
+    okb_ctx* c = ctxs[r];
+    cudaSetDevice(c->device);
+    for (int q = 0; q < world; ++q) {
+      if (q == r) continue;
+      if (ctxs[q]->device != c->device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { c->set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return OKB_ERR_CUDA; }
+        cudaGetLastError();
+      }
+      c->shard_peer[q] = ctxs[q]->shard_local;
+    }
+  }
+  return OKB_OK;
+}
+
+extern "C" int okb_shard_stats(okb_ctx* c, int win, double out[4]) {
+  if (!c || win < 0 || win >= c->max_windows || !out) return OKB_ERR_INVALID_ARG;
+  const SolverState& s = c->h_states[win];
+  out[0] = (double)s.shard_rounds; out[1] = 1e-3 * (double)s.shard_wait_ns; out[2] = (double)s.shard_fault; out[3] = (double)s.shard_epoch;
+  return OKB_OK;
 }
 
 // ---- optional event timing around solver kernels
@@ -585,7 +673,10 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
     k_linearize<<<dim3(max_cx, max_K, count), L1_THREADS, 0, c->stream>>>(c->d_wins, first);
     k_lmblock<<<dim3(max_cx, count), 128, 0, c->stream>>>(c->d_wins, first);
     k_schur<<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first, acc_copies, opt.max_iterations);
-    if (max_chunks > 1) { k_reduce_partials<<<dim3(8, count), 256, 0, c->stream>>>(c->d_wins, first); c->launches += 1; }
+    if (c->shard_world > 1) {    // chunk reduction fused with the push half of the all-reduce over peer memory
+      k_shard_push<<<dim3(std::max(1, std::min(16, c->sm_count / std::max(1, count))), count), 256, 0, c->stream>>>(c->d_wins, first);
+      c->launches += 1;
+    } else if (max_chunks > 1) { k_reduce_partials<<<dim3(8, count), 256, 0, c->stream>>>(c->d_wins, first); c->launches += 1; }
     prof_end(c);
     c->launches += 2;
     if (max_imu > 0) cudaStreamWaitEvent(c->stream, c->ev_imu, 0);

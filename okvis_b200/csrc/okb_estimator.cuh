@@ -13,6 +13,7 @@ constexpr int kMaxFrames = 32;        // frame visibility mask is one u32
 constexpr int kMaxChunks = 64;        // landmark chunks (CTAs) per window in kernel A
 constexpr int kMaxDense = 512;        // reduced-system dimension limit
 constexpr int kMaxMarg = 160;         // marginalisation prior dimension limit
+constexpr int kMaxShard = 8;          // ranks of a landmark-sharded window (one NVSwitch domain)
 
 // Ceres 1.9 defaults used by Estimator::optimize
 constexpr double kInitialRadius = 1e4;
@@ -54,7 +55,27 @@ struct SolverState {
   unsigned long long t_start_ns, t_last_iter_ns, t_iter_begin_ns;
   double solve_time_s;
   unsigned long long phase_ns[16];  // accumulated phase times (diagnostics): 0..7 k_solve, 8..13 k_schur (chunk 0, thread 0)
+  // Landmark-sharded windows: exchange epoch (one per solver round; never reset, so stale mailbox flags of an earlier
+  // optimize can not match) and the accumulated device time spent waiting for / summing the peers' partial systems.
+  unsigned long long shard_epoch;
+  unsigned long long shard_wait_ns, shard_rounds;
+  int shard_fault;     // 1 = a peer did not arrive within the time-out (the window terminates with FAILURE)
 };
+
+// ---- landmark-sharded single window: per-window mailbox in every rank's device memory.
+// Rank s PUSHES its reduced landmark partial (Schur accumulator, pose-block sums, cost) into box [parity][s] of every
+// rank's mailbox with plain stores over NVLink, then releases flag [parity][s]; the consumer (k_solve) acquires the
+// `world` flags in its own memory and adds the boxes in rank order, so every rank forms the bit-identical reduced
+// system.  Boxes are double-buffered by the parity of the round's epoch ("Multi-GPU").
+constexpr size_t kShardHeaderBytes = 4096;
+constexpr size_t kShardFlags1 = 0;       // u64 [2][kMaxShard]   reduced-system boxes ready
+constexpr size_t kShardFlags2 = 128;     // u64 [2][kMaxShard]   step scalars ready
+constexpr size_t kShardCounter = 256;    // u32                  last-CTA counter of k_shard_push (local use)
+constexpr size_t kShardScalars = 512;    // f64 [2][kMaxShard][16]
+__host__ __device__ inline size_t shard_box_doubles(int K, int dcp) { return (size_t)dcp * dcp + (size_t)K * 32 + 8; }
+__host__ __device__ inline size_t shard_win_bytes(int world, size_t box_cap) {
+  return (kShardHeaderBytes + 2 * (size_t)world * box_cap * sizeof(double) + 255) & ~(size_t)255;
+}
 
 // Everything kernels need to know about one window.  All pointers are device pointers into the
 // window's arena.
@@ -135,6 +156,10 @@ struct WinDev {
   int32_t* marg_col;                           // [marg_nb] first column of each block
   int32_t* marg_off;                           // [marg_nb] offset into x0
   double *marg_x0, *marg_J, *marg_e0, *marg_H0;  // H0 = J^T J
+  // landmark sharding: this rank holds the landmarks / observations of its shard and all dense blocks
+  int shard_rank, shard_world;                 // world <= 1: not sharded
+  int shard_box_cap;                           // doubles per box
+  unsigned char* shard_mail[kMaxShard];        // this window's mailbox in every rank's memory, as mapped on this device
   SolverState* st;
 };
 

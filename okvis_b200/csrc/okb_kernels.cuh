@@ -105,7 +105,51 @@ struct SShared {
   // broadcast scalars
   double cand_cost, cost_lm, stepn2_lm, cost_dense;
   int adopt, terminate, commit_only, fail, spec, chol_flag;
+  int shard_fault;
+  double x2[8];         // landmark-sharded windows: step scalars combined over the ranks
 };
+
+constexpr unsigned long long kShardTimeoutNs = 4000000000ull;   // a peer that does not arrive within 4 s: FAILURE, no hang
+
+// Landmark-sharded window, second exchange of a round (inside k_solve): the landmark parts of the dogleg scalars
+// [N2, GU, G2, VHV, ||x||^2, max|g|, #non-finite, elapsed+last (time-limit callback)] of every rank.  Each rank stores
+// its 8 doubles into slot [parity][rank] of every mailbox and releases the matching flag; then it acquires the
+// `world` flags of its own mailbox and combines the slots in rank order (sum, max for v[5], rank 0's clock for v[7]):
+// every rank obtains the same bits.  Called by all threads of the CTA; returns 0 on a time-out.
+__device__ inline int shard_exchange_scalars(const WinDev& W, SolverState* st, SShared* sh, double* v) {
+  const int tid = threadIdx.x, world = W.shard_world, me = W.shard_rank;
+  const unsigned long long epoch = st->shard_epoch;        // set by the prologue of this round
+  const int par = (int)(epoch & 1ull);
+  if (tid == 0) sh->shard_fault = 0;
+  __syncthreads();
+  if (tid < world) {
+    double* box = reinterpret_cast<double*>(W.shard_mail[tid] + kShardScalars) + ((size_t)par * kMaxShard + me) * 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) box[k] = v[k];
+    __threadfence_system();
+    st_release_sys_u64(shard_flag(W, tid, kShardFlags2, par, me), epoch);
+    const unsigned long long t0 = globaltimer_ns();
+    const unsigned long long* fl = shard_flag(W, me, kShardFlags2, par, tid);
+    while (ld_acquire_sys_u64(fl) < epoch)
+      if (globaltimer_ns() - t0 > kShardTimeoutNs) { sh->shard_fault = 1; break; }
+  }
+  __syncthreads();
+  if (sh->shard_fault) return 0;
+  if (tid < 8) {
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r) {
+      const double x = __ldcg(reinterpret_cast<const double*>(W.shard_mail[me] + kShardScalars) + ((size_t)par * kMaxShard + r) * 16 + tid);
+      if (tid == 5) acc = (r == 0) ? x : fmax(acc, x);
+      else if (tid == 7) acc = (r == 0) ? x : acc;
+      else acc += x;
+    }
+    sh->x2[tid] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = sh->x2[k];
+  return 1;
+}
 
 // r = S e etc. are tiny; one warp handles all priors.
 // The dense Hessian lives in packed lower-triangular storage: contributions to the upper triangle are dropped
@@ -327,8 +371,38 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
 
   PHASE_MARK(0);
   // ================= phase 2: gather the landmark-kernel partials =================
+  const bool sharded = W.shard_world > 1;
+  if (sharded) {
+    // receive half of the all-reduce: wait for every rank's box of this round (flags live in THIS rank's memory),
+    // add the boxes in rank order into the local partials.  The dense terms above did not depend on them.
+    const unsigned long long epoch = st->shard_epoch + 1;
+    const int par = (int)(epoch & 1ull), world = W.shard_world, me = W.shard_rank;
+    const unsigned long long t_w0 = globaltimer_ns();
+    if (tid == 0) sh->shard_fault = 0;
+    __syncthreads();
+    if (tid < world) {
+      const unsigned long long* fl = shard_flag(W, me, kShardFlags1, par, tid);
+      while (ld_acquire_sys_u64(fl) < epoch)
+        if (globaltimer_ns() - t_w0 > kShardTimeoutNs) { sh->shard_fault = 1; break; }
+    }
+    __syncthreads();
+    if (sh->shard_fault) {
+      if (tid == 0) { st->shard_fault = 1; st->termination = OKB_TERM_FAILURE; st->done = 1; st->shard_epoch = epoch; }
+      return;
+    }
+    const int nA = dcp * dcp, nH = K * kPartH;
+    for (int i = tid; i < nA + nH + 1; i += S_THREADS) {
+      double s = 0.0;
+      for (int r = 0; r < world; ++r) s += __ldcg(shard_box(W, me, par, r) + i);
+      if (i < nA) W.partA[i] = s;
+      else if (i < nA + nH) W.partH[i - nA] = s;          // record (cx = 0, frame f): the gather below runs with n_cx = 1
+      else st->numeric_fail = (s > 0.0) ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid == 0) { st->shard_epoch = epoch; st->shard_wait_ns += globaltimer_ns() - t_w0; st->shard_rounds += 1; }
+  }
   double cost_lm = 0.0, stepn2_lm = 0.0;
-  const int n_cx = (L + L1_THREADS - 1) / L1_THREADS;
+  const int n_cx = sharded ? 1 : (L + L1_THREADS - 1) / L1_THREADS;
   for (int i = 0; i < n_cx * K; ++i) {   // fixed order, replicated in all threads (small)
     cost_lm += W.partH[(size_t)i * kPartH + 27];
     stepn2_lm += W.partH[(size_t)i * kPartH + 28];
@@ -416,6 +490,9 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
   }
   const int adopt = sh->adopt;
   int cur = st->cur;
+  double xs[8] = {0, 0, 0, 0, 0, 0, 0, 0};     // N2, GU, G2, VHV, ||x||^2, max|g|, #non-finite, (sharded: rank clock)
+  int chol_fail_adopt = 0;
+  const bool dense_owner = !sharded || W.shard_rank == 0;   // sharded: the dense blocks are counted once
 
   // ================= phase 4: adopt the speculative linearisation =================
   if (adopt) {
@@ -545,7 +622,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       gmax = fmax(gmax, fmax(fabs(g0), fmax(fabs(g1), fabs(g2))));
     }
     for (int i = tid; i < d; i += S_THREADS) {
-      if (chol_fail) break;
+      if (chol_fail || !dense_owner) break;
       const double g = s_g[i], E = s_E[i];
       if (skip_solve) { gmax = fmax(gmax, fabs(g)); continue; }
       const double u = s_u[i];
@@ -553,23 +630,37 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       N2 += E * u * u; GU += g * u; G2 += g * g / E;
       gmax = fmax(gmax, fabs(g));
     }
-    for (int i = tid; i < 7 * K; i += S_THREADS) xn2 += W.pose[i] * W.pose[i];
-    for (int i = tid; i < 9 * W.NSB; i += S_THREADS) xn2 += W.sb[i] * W.sb[i];
-    N2 = block_sum(N2, sh->red);
-    GU = block_sum(GU, sh->red);
-    G2 = block_sum(G2, sh->red);
-    VHV = block_sum(VHV, sh->red) + VHV_dd;
-    xn2 = block_sum(xn2, sh->red);
-    gmax = block_max(gmax, sh->red);
-    const double badsum = block_sum((double)bad, sh->red);
+    if (dense_owner) {
+      for (int i = tid; i < 7 * K; i += S_THREADS) xn2 += W.pose[i] * W.pose[i];
+      for (int i = tid; i < 9 * W.NSB; i += S_THREADS) xn2 += W.sb[i] * W.sb[i];
+    }
+    xs[0] = block_sum(N2, sh->red);
+    xs[1] = block_sum(GU, sh->red);
+    xs[2] = block_sum(G2, sh->red);
+    xs[3] = block_sum(VHV, sh->red) + (dense_owner ? VHV_dd : 0.0);
+    xs[4] = block_sum(xn2, sh->red);
+    xs[5] = block_max(gmax, sh->red);
+    xs[6] = block_sum((double)bad, sh->red);
+    chol_fail_adopt = chol_fail;
+  }
+  if (sharded) {
+    // second exchange of the round: the landmark parts of the step scalars live on their shards; rank 0's clock
+    // drives the time-limit callback on every rank (the ranks must take identical decisions)
+    xs[7] = 1e-9 * ((double)(globaltimer_ns() - st->t_start_ns) + (double)st->t_last_iter_ns);
+    if (!shard_exchange_scalars(W, st, sh, xs)) {
+      if (tid == 0) { st->shard_fault = 1; st->termination = OKB_TERM_FAILURE; st->done = 1; }
+      return;
+    }
+  }
+  if (adopt) {
     if (tid == 0) {
-      st->x_norm2 = xn2;
-      st->grad_max = gmax;
+      st->x_norm2 = xs[4];
+      st->grad_max = xs[5];
       st->numeric_fail = 0;
-      if (chol_fail || badsum > 0) {
+      if (chol_fail_adopt || xs[6] > 0) {
         sh->fail = 1;
       } else {
-        st->G2 = G2; st->VHV = VHV; st->GU = GU; st->N2 = N2;
+        st->G2 = xs[2]; st->VHV = xs[3]; st->GU = xs[1]; st->N2 = xs[0];
         sh->fail = 0;
       }
     }
@@ -601,7 +692,8 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       // IterationCallback on the summary of the iteration that just ended
       const double elapsed = 1e-9 * (double)(now - st->t_start_ns);
       const double last = 1e-9 * (double)st->t_last_iter_ns;
-      if (!finish && opt.time_limit_s >= 0.0 && st->iteration >= opt.min_iterations && elapsed + last > opt.time_limit_s) {
+      const double t_cb = sharded ? sh->x2[7] : elapsed + last;     // sharded: rank 0's clock, exchanged above
+      if (!finish && opt.time_limit_s >= 0.0 && st->iteration >= opt.min_iterations && t_cb > opt.time_limit_s) {
         st->termination = OKB_TERM_TIME_LIMIT; finish = 1;
       }
       if (!finish && st->iteration >= opt.max_iterations) { st->termination = OKB_TERM_NO_CONVERGENCE; finish = 1; }
@@ -746,6 +838,7 @@ __global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int rest
     st->G2 = st->VHV = st->GU = st->N2 = 0; st->a = 0; st->b = 0;
     st->model_cost_change = 0; st->dogleg_step_norm = 0; st->cand_step_norm2_dense = 0; st->grad_max = 0;
     for (int i = 0; i < 16; ++i) st->phase_ns[i] = 0;
+    st->shard_wait_ns = 0; st->shard_rounds = 0; st->shard_fault = 0;     // shard_epoch is never reset
     st->t_start_ns = 0; st->t_last_iter_ns = 0; st->t_iter_begin_ns = 0; st->solve_time_s = 0;
     int redo = 0;
     for (int t = 0; t < W.n_imu; ++t) redo += W.imu_cache[t].redo_count;

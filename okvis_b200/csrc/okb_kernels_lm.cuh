@@ -619,6 +619,71 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const WinDev* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Landmark-sharded window: k_reduce_partials fused with the push half of the all-reduce.  Every rank sums its
+// chunk partials (Schur accumulator) and its per-CTA pose-block records in fixed order and stores the result with
+// plain stores into box [parity][rank] of EVERY rank's mailbox (its own included) -- remote stores travel over
+// NVLink / NVSwitch and are not waited for.  The last CTA of the window fences at system scope and releases the
+// `world` ready flags.  The sum over ranks happens in k_solve's prologue (every rank adds the boxes in rank order
+// => bit-identical reduced systems, so the redundant reduced solves stay in lock step).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double* shard_box(const WinDev& W, int dst, int parity, int src) {
+  return reinterpret_cast<double*>(W.shard_mail[dst] + kShardHeaderBytes) + ((size_t)parity * W.shard_world + src) * W.shard_box_cap;
+}
+__device__ __forceinline__ unsigned long long* shard_flag(const WinDev& W, int dst, size_t which, int parity, int src) {
+  return reinterpret_cast<unsigned long long*>(W.shard_mail[dst] + which) + parity * kMaxShard + src;
+}
+
+__global__ void __launch_bounds__(256) k_shard_push(const WinDev* __restrict__ wins, int win_first) {
+  const WinDev& W = wins[win_first + blockIdx.y];
+  SolverState* st = W.st;
+  if (st->done) return;
+  const int world = W.shard_world, me = W.shard_rank;
+  const unsigned long long epoch = st->shard_epoch + 1;
+  const int par = (int)(epoch & 1ull);
+  const int K = W.K, nA = W.dcp * W.dcp, nH = K * kPartH;
+  const int n = nA + nH + 8;
+  const int n_cx = (W.L + L1_THREADS - 1) / L1_THREADS;
+  double* dst[kMaxShard];
+#pragma unroll
+  for (int r = 0; r < kMaxShard; ++r) dst[r] = (r < world) ? shard_box(W, r, par, me) : nullptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    if (i < nA) {
+      s = W.partA[i];
+      for (int c = 1; c < W.n_chunks; ++c) s += W.partA[(size_t)c * W.partA_stride + i];
+    } else if (i < nA + nH) {
+      const int j = i - nA, f = j / kPartH, e = j % kPartH;
+      if (e < 29)
+        for (int c = 0; c < n_cx; ++c) s += W.partH[((size_t)c * K + f) * kPartH + e];
+    } else if (i == nA + nH) {
+      s = st->numeric_fail ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < kMaxShard; ++r)
+      if (r < world) dst[r][i] = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(W.shard_mail[me] + kShardCounter);
+    const unsigned int prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *counter = 0u;
+      __threadfence_system();
+      for (int r = 0; r < world; ++r) st_release_sys_u64(shard_flag(W, r, kShardFlags1, par, me), epoch);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Post-solve landmark quality: H = sum J_lm^T J_lm (sqrt-information weighted, no robust weight)
 // at the final estimate; quality = sqrt(lambda_min)/sqrt(lambda_max), 0 if lambda_min < 1e-12.
 // ------------------------------------------------------------------------------------------------

@@ -35,3 +35,31 @@ def gather_summaries(dist, summaries):
         for j, s in enumerate(part):
             merged[r + j * world] = s
     return merged
+
+
+def shard_window(window, rank, world):
+    """Landmark-block shard of ONE window (BASELINE.json configs[4]): rank r keeps the
+    landmarks with lm_idx % world == r and their observations; poses, speed/bias, extrinsics, IMU terms and priors
+    are replicated.  Returns (shard window, global landmark indices of the shard's landmarks)."""
+    import dataclasses
+    L = len(window.landmarks)
+    mine = np.arange(rank, L, world)
+    local = np.full(L, -1, np.int64)
+    local[mine] = np.arange(len(mine))
+    keep = local[window.obs["lm_idx"]] >= 0
+    obs = window.obs[keep].copy()
+    obs["lm_idx"] = local[obs["lm_idx"]].astype(np.uint32)
+    w = dataclasses.replace(window, landmarks=np.ascontiguousarray(window.landmarks[mine]), obs=np.ascontiguousarray(obs),
+                            name="%s/shard%d of %d" % (window.name, rank, world))
+    return w, mine
+
+
+def merge_shard_results(n_landmarks, parts):
+    """parts: list over ranks of (global landmark indices, download dict).  Dense blocks are identical on all ranks."""
+    out = dict(poses=parts[0][1]["poses"], speed_bias=parts[0][1]["speed_bias"],
+               landmarks=np.zeros((n_landmarks, 4)), quality=np.zeros(n_landmarks))
+    for idx, d in parts:
+        out["landmarks"][idx] = d["landmarks"]
+        if d.get("quality") is not None:
+            out["quality"][idx] = d["quality"]
+    return out

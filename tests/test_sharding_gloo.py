@@ -70,3 +70,19 @@ def test_partition_is_exact_cover():
         for n in (0, 1, 7, 64):
             all_idx = sorted(i for r in range(world) for i in sharding.shard_indices(n, world, r))
             assert all_idx == list(range(n))
+
+
+def test_landmark_shards_partition_one_window():
+    """shard_window: the shards' landmarks / observations are an exact cover of the window; dense blocks replicated."""
+    from okvis_b200 import synthetic
+    w = synthetic.make_window(1, 0)
+    for world in (2, 3, 8):
+        shards = [sharding.shard_window(w, r, world) for r in range(world)]
+        assert sorted(np.concatenate([idx for _, idx in shards]).tolist()) == list(range(len(w.landmarks)))
+        assert sum(len(s.obs) for s, _ in shards) == len(w.obs)
+        for s, idx in shards:
+            assert np.array_equal(s.landmarks, w.landmarks[idx]) and s.poses is w.poses and s.imu_terms is w.imu_terms
+            assert s.obs["lm_idx"].max() < len(idx)
+        back = np.concatenate([np.stack([idx[s.obs["lm_idx"]], s.obs["pose_idx"], s.obs["cam_idx"]], 1) for s, idx in shards])
+        orig = np.stack([w.obs["lm_idx"], w.obs["pose_idx"], w.obs["cam_idx"]], 1)
+        assert sorted(map(tuple, back.tolist())) == sorted(map(tuple, orig.tolist()))
