@@ -208,10 +208,58 @@ int okb_window_upload(okb_ctx* ctx, int win, const okb_window_desc* desc);
  * slots, and every later okb_optimize* / okb_window_reset is ordered after them.  Uploads of different slots
  * may also be issued concurrently from several caller threads. */
 int okb_window_upload_batch(okb_ctx* ctx, int win_first, int count, const okb_window_desc* descs, int host_threads);
-/* Bytes the last okb_window_upload of this slot copied host -> device (0 if the slot is empty). */
+/* ---- resident window: incremental graph updates -------------------------------------------------------------
+ * Replace the reference's graph bookkeeping between two optimize() calls -- Estimator::addStates
+ * (okvis_ceres/src/Estimator.cpp:110-343), addLandmark (:346-368), addObservation
+ * (include/okvis/implementation/Estimator.hpp:43-90), removeObservation (Estimator.cpp:371-413), set_T_WS /
+ * setSpeedAndBias / setLandmark (include/okvis/Estimator.hpp:343-409) and the frame / landmark removal part of
+ * applyMarginalizationStrategy (Estimator.cpp:434-773) -- so that a window stays resident on the device and only
+ * one frame's worth of data crosses PCIe per optimize.  Every call appends a command to the slot's pending stream
+ * on the host (no device work); okb_window_commit -- or the next okb_optimize* / okb_window_download* /
+ * okb_window_reset of the slot -- ships the stream with one copy and the device applies the commands in order and
+ * re-compiles its internal layout.  Index conventions: pose / speed-bias indices are positions in the window
+ * (removing position p moves every later frame down by one, exactly like erasing from the reference's ordered
+ * statesMap_); landmark indices are stable slots chosen by the caller (0 <= idx < max_landmarks).
+ * Indices are validated on the host against the mirrored dimensions (OKB_ERR_INVALID_ARG / OKB_ERR_CAPACITY
+ * synchronously); duplicate observations and inconsistent extrinsics are detected by the device and reported by
+ * the next okb_optimize_finish / okb_optimize. */
+
+/* Capacities of slot `win` for later incremental growth; call before okb_window_upload of that slot (an upload
+ * larger than the reservation simply enlarges it).  max_marg_dim <= 160. */
+int okb_window_reserve(okb_ctx* ctx, int win, int max_frames, int max_landmarks, int max_observations,
+                       int max_imu_samples, int max_marg_dim);
+/* Appends one frame: pose (index n_poses), optionally its speed/bias block (index n_speed_bias; NULL: none) and the
+ * ImuError term that links it (Estimator.cpp:288-306; NULL: none).  term->pose0/sb0/pose1/sb1 index the window
+ * AFTER the append; term->sample_offset is relative to `samples`. */
+int okb_window_add_frame(okb_ctx* ctx, int win, const double* pose /*7*/, const double* speed_bias /*9 or NULL*/,
+                         const okb_imu_term* term, const okb_imu_sample* samples, int n_samples);
+/* Removes a frame: its pose block, speed/bias block sb_idx (0xffffffff: none), every observation made in it, the IMU
+ * terms and priors attached to it.  Later frames move down one position everywhere (observations, IMU terms,
+ * priors, marginalisation-prior block list; a prior that still references the removed frame is an error). */
+int okb_window_remove_frame(okb_ctx* ctx, int win, uint32_t pose_idx, uint32_t sb_idx);
+/* Creates or overwrites landmark slots (Estimator::addLandmark / setLandmark). */
+int okb_window_set_landmarks(okb_ctx* ctx, int win, int n, const uint32_t* idx, const double* xyzw /*[n][4]*/);
+/* Removes landmarks and all their observations (Estimator::removeObservation loop of Estimator.cpp:625-725). */
+int okb_window_remove_landmarks(okb_ctx* ctx, int win, int n, const uint32_t* idx);
+int okb_window_add_observations(okb_ctx* ctx, int win, int n, const okb_observation* obs);
+typedef struct okb_obs_key { uint32_t pose_idx, lm_idx, cam_idx, _pad; } okb_obs_key;
+/* Estimator::removeObservation(landmarkId, poseId, camIdx, keypointIdx) (Estimator.cpp:371-413); unknown keys are ignored. */
+int okb_window_remove_observations(okb_ctx* ctx, int win, int n, const okb_obs_key* keys);
+/* Estimator::set_T_WS / setSpeedAndBias. */
+int okb_window_set_states(okb_ctx* ctx, int win, int n_poses, const uint32_t* pose_idx, const double* poses /*[n][7]*/,
+                          int n_sb, const uint32_t* sb_idx, const double* speed_bias /*[n][9]*/);
+/* Replaces the pose priors and speed/bias priors; marg != NULL also replaces the marginalisation prior
+ * (marg->n == 0 removes it), marg == NULL keeps the current one. */
+int okb_window_set_priors(okb_ctx* ctx, int win, int n_pose_priors, const okb_pose_prior* pose_priors, int n_sb_priors,
+                          const okb_sb_prior* sb_priors, const okb_marg_prior* marg);
+/* Ships the pending commands of slots [win_first, win_first+count) to the device (transfer stream; overlaps solver
+ * work on other slots).  Optional: the calls that need the result do it themselves. */
+int okb_window_commit(okb_ctx* ctx, int win_first, int count);
+
+/* Bytes the last commit (full upload or incremental commands) of this slot copied host -> device (0 if the slot is empty). */
 int64_t okb_window_h2d_bytes(const okb_ctx* ctx, int win);
-/* Restores the uploaded initial state of the slot on the device (no host traffic); used to
- * repeat a solve on resident data. */
+/* Restores the state of the last FULL upload of the slot on the device (no host traffic); used to repeat a solve
+ * on resident data.  The window must have the shape (frames, landmarks) it had at that upload. */
 int okb_window_reset(okb_ctx* ctx, int win_first, int win_count);
 /* Runs the dogleg/Schur solver on windows [win_first, win_first+win_count) in one batch.
  * summaries may be NULL; otherwise [win_count]. */

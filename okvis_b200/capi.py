@@ -102,6 +102,63 @@ class Context:
         self._check(lib().okb_window_upload(self._h, int(win), C.byref(d)))
         self._windows[win] = window
 
+    # ---- resident window: incremental graph updates (no device work until commit / optimize / download)
+    def reserve(self, win, max_frames, max_landmarks, max_observations, max_imu_samples, max_marg_dim=0):
+        self._check(lib().okb_window_reserve(self._h, int(win), int(max_frames), int(max_landmarks), int(max_observations),
+                                             int(max_imu_samples), int(max_marg_dim)))
+
+    def add_frame(self, win, pose, speed_bias=None, term=None, samples=None):
+        pose = _f64(pose)
+        sb = _f64(speed_bias) if speed_bias is not None else None
+        t = np.ascontiguousarray(term) if term is not None else None
+        smp = np.ascontiguousarray(samples) if samples is not None else None
+        self._check(lib().okb_window_add_frame(self._h, int(win), _p(pose), _p(sb), _p(t), _p(smp), 0 if smp is None else len(smp)))
+
+    def remove_frame(self, win, pose_idx, sb_idx=None):
+        self._check(lib().okb_window_remove_frame(self._h, int(win), C.c_uint32(int(pose_idx)),
+                                                  C.c_uint32(0xffffffff if sb_idx is None else int(sb_idx))))
+
+    def set_landmarks(self, win, idx, xyzw):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        x = _f64(xyzw)
+        self._check(lib().okb_window_set_landmarks(self._h, int(win), len(idx), _p(idx), _p(x)))
+
+    def remove_landmarks(self, win, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        self._check(lib().okb_window_remove_landmarks(self._h, int(win), len(idx), _p(idx)))
+
+    def add_observations(self, win, obs):
+        obs = np.ascontiguousarray(obs, dtype=abi.observation_dtype)
+        self._check(lib().okb_window_add_observations(self._h, int(win), len(obs), _p(obs)))
+
+    def remove_observations(self, win, keys):
+        k = np.zeros((len(keys), 4), np.uint32)
+        k[:, :3] = np.asarray(keys, dtype=np.uint32).reshape(-1, 3)
+        self._check(lib().okb_window_remove_observations(self._h, int(win), len(k), _p(k)))
+
+    def set_states(self, win, pose_idx=(), poses=None, sb_idx=(), speed_bias=None):
+        pi = np.ascontiguousarray(pose_idx, dtype=np.uint32)
+        si = np.ascontiguousarray(sb_idx, dtype=np.uint32)
+        self._check(lib().okb_window_set_states(self._h, int(win), len(pi), _p(pi) if len(pi) else None,
+                                                _p(_f64(poses)) if len(pi) else None, len(si), _p(si) if len(si) else None,
+                                                _p(_f64(speed_bias)) if len(si) else None))
+
+    def set_priors(self, win, pose_priors, sb_priors, marg=None):
+        pp = np.ascontiguousarray(pose_priors, dtype=abi.pose_prior_dtype)
+        sp = np.ascontiguousarray(sb_priors, dtype=abi.sb_prior_dtype)
+        m = None
+        if marg is not None:
+            m = abi.MargPrior()
+            m.n, m.n_blocks = int(marg["J"].shape[0]), len(marg["block_kind"])
+            m.block_kind = marg["block_kind"].ctypes.data_as(C.POINTER(C.c_int32))
+            m.block_idx = marg["block_idx"].ctypes.data_as(C.POINTER(C.c_uint32))
+            m.x0, m.J, m.e0 = abi.dptr(marg["x0"]), abi.dptr(marg["J"]), abi.dptr(marg["e0"])
+        self._check(lib().okb_window_set_priors(self._h, int(win), len(pp), _p(pp) if len(pp) else None, len(sp),
+                                                _p(sp) if len(sp) else None, C.byref(m) if m is not None else None))
+
+    def commit(self, first=0, count=1):
+        self._check(lib().okb_window_commit(self._h, int(first), int(count)))
+
     def debug_phase_us(self, win):
         out = np.zeros(16)
         self._check(lib().okb_debug_phase_ns(self._h, int(win), _p(out)))
@@ -140,10 +197,13 @@ class Context:
         self._check(lib().okb_optimize_finish(self._h, int(first), int(count), out))
         return [s.as_dict() for s in out]
 
-    def download(self, win, with_quality=True):
-        w = self._windows[win]
-        poses, sb, lms = np.zeros_like(w.poses), np.zeros_like(w.speed_bias), np.zeros_like(w.landmarks)
-        q = np.zeros(len(w.landmarks)) if with_quality else None
+    def download(self, win, with_quality=True, dims=None):
+        """dims = (n_poses, n_speed_bias, n_landmarks) when the window was changed incrementally since its upload."""
+        if dims is None:
+            w = self._windows[win]
+            dims = (len(w.poses), len(w.speed_bias), len(w.landmarks))
+        poses, sb, lms = np.zeros((dims[0], 7)), np.zeros((dims[1], 9)), np.zeros((dims[2], 4))
+        q = np.zeros(dims[2]) if with_quality else None
         self._check(lib().okb_window_download(self._h, int(win), _p(poses), _p(sb), _p(lms), _p(q)))
         return dict(poses=poses, speed_bias=sb, landmarks=lms, quality=q)
 

@@ -9,18 +9,31 @@
 #include "../../include/okvis_b200.h"
 #include "okb_estimator.cuh"
 
+// Capacities an arena is planned for: frames, landmarks, observations, IMU samples / terms, extrinsics, cameras,
+// priors per kind, marginalisation prior dimension.
+struct WinCaps { int K = 0, L = 0, O = 0, S = 0, T = 0, NE = 0, NC = 0, PP = 0, MN = 0; };
+
 struct WinStore {
   unsigned char* arena = nullptr;     // device
   size_t arena_bytes = 0;
-  unsigned char* staging = nullptr;   // pinned host mirror of the arena's input region
+  WinCaps caps, reserve;              // what the arena holds / the minimum asked for by okb_window_reserve
+  unsigned char* staging = nullptr;   // pinned: the pending command stream of the slot (okb_graph.cuh)
   size_t staging_bytes = 0;
+  size_t cmd_used = 0;                // bytes of commands not yet committed
+  size_t cmd_cap_dev = 0;             // size of the device-side command buffer
+  bool staging_busy = false;          // an H2D copy of `staging` may still be in flight (wait on `copied` before rewriting)
+  bool full_pending = false;          // the pending stream is a full upload
+  bool committed = false;
+  int obs_bound = 0;                  // upper bound of the device-side observation list length
+  int K_init = 0, NSB_init = 0, L_init = 0;   // shape at the last full upload (okb_window_reset)
+  std::vector<okb_imu_term> terms;    // host mirror of the IMU terms / prior indices (dimension bookkeeping of remove_frame)
+  std::vector<uint32_t> pp_idx, sbp_idx;
   size_t h2d_bytes = 0;
   bool uploaded = false;
-  cudaEvent_t copied = nullptr;       // recorded after the H2D copy of `staging`; the next upload of the slot waits on it
+  cudaEvent_t copied = nullptr;       // recorded after the H2D copy of `staging`
   unsigned char* out_staging = nullptr;  // pinned host buffer the estimates are downloaded into
   size_t out_bytes = 0;
   cudaEvent_t down = nullptr;         // recorded after the D2H copies of a download
-  std::vector<uint32_t> perm;         // internal (sorted) landmark index -> caller's index
   okb_solve_options opt{};            // options of the last okb_optimize_async on this slot
   int done_idx = -1;                  // index into okb_ctx::done_ring of the last solver work launched on this slot
 };

@@ -11,6 +11,7 @@
 
 #include "okb_ctx.h"
 #include "okb_hostpack.hpp"
+#include "okb_graph.cuh"
 #include "okb_kernels.cuh"
 
 using namespace okb;
@@ -129,7 +130,7 @@ extern "C" int64_t okb_kernel_launches(const okb_ctx* c) { return c ? c->launche
 extern "C" void* okb_stream(const okb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 // ---------------------------------------------------------------------------------------------
-// window packing
+// window graph: capacities, arena, command staging, commit (device side: okb_graph.cuh)
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct ArenaPlan {
@@ -140,14 +141,6 @@ struct ArenaPlan {
     return o;
   }
 };
-// Landmark estimates / qualities come back in the internal (sorted) order: scatter to the caller's order.
-void unpermute_landmarks(const WinStore& S, int L, const double* lm_sorted, const double* q_sorted, double* landmarks, double* quality) {
-  for (int j = 0; j < L; ++j) {
-    const uint32_t l = S.perm[j];
-    if (landmarks) std::memcpy(landmarks + 4 * (size_t)l, lm_sorted + 4 * (size_t)j, sizeof(double) * 4);
-    if (quality) quality[l] = q_sorted[j];
-  }
-}
 
 // Orders the solver stream after every transfer issued so far.
 int join_transfers(okb_ctx* c) {
@@ -161,122 +154,260 @@ void mark_work(okb_ctx* c, int first, int count) {
   cudaEventRecord(c->done_ring[k], c->stream);
   for (int i = first; i < first + count; ++i) c->wins[i].done_idx = k;
 }
-}  // namespace
 
-// Device-side epilogue of uploads of slots [first, first+count): two kernels for the whole range.
-static int upload_finish(okb_ctx* c, int first, int count) {
-  int max_work = 1;
-  for (int i = first; i < first + count; ++i) {
-    const WinDev& W = c->host[i];
-    max_work = std::max(max_work, std::max(std::max(W.n_obs, 4 * W.L), std::max(7 * W.K, 9 * W.NSB)));
+inline bool caps_cover(const WinCaps& a, const WinCaps& b) {
+  return a.K >= b.K && a.L >= b.L && a.O >= b.O && a.S >= b.S && a.T >= b.T && a.NE >= b.NE && a.NC >= b.NC && a.PP >= b.PP && a.MN >= b.MN;
+}
+inline WinCaps caps_max(const WinCaps& a, const WinCaps& b) {
+  return WinCaps{std::max(a.K, b.K), std::max(a.L, b.L), std::max(a.O, b.O), std::max(a.S, b.S), std::max(a.T, b.T),
+                 std::max(a.NE, b.NE), std::max(a.NC, b.NC), std::max(a.PP, b.PP), std::max(a.MN, b.MN)};
+}
+inline size_t full_upload_bytes(const WinCaps& q) {      // command stream of a full upload at these sizes
+  return 12 * sizeof(CmdHeader) + 8 * ((size_t)7 * q.NE + 16 * (size_t)q.K + 4 * (size_t)q.L + 2 * kMaxMargBlocks + 16 * kMaxMargBlocks +
+                                        (size_t)q.MN * q.MN + q.MN) +
+         sizeof(okb_camera) * q.NC + sizeof(okb_observation) * (size_t)q.O + sizeof(okb_imu_term) * q.T + sizeof(okb_imu_sample) * (size_t)q.S +
+         (sizeof(okb_pose_prior) + sizeof(okb_sb_prior)) * q.PP + 4096;
+}
+
+// Dimensions that follow from the current K / L / NC ... of the host mirror.
+void derive_dims(WinDev& W) {
+  int CP = 1;
+  while (CP < W.NC) CP <<= 1;
+  W.CP = CP;
+  W.NS = W.K * CP; W.NG = (W.NS + 31) / 32; W.NSP = W.NG * 32;
+  W.dc = 6 * W.K; W.d = W.dc + 9 * W.NSB; W.dcp = 4 * ((W.dc + 1 + 3) / 4);
+  W.Lp = (W.L + 31) & ~31;
+  W.partA_stride = W.dcp * W.dcp;
+  W.zero_bytes[0] = align_up(sizeof(double2) * (size_t)W.L * W.NS, 256);
+  W.zero_bytes[1] = align_up(sizeof(double) * (size_t)W.L * W.NS, 256);
+  W.zero_bytes[2] = align_up(sizeof(double) * 6 * (size_t)W.Lp * W.K, 256);
+}
+
+// (Re)plans the slot's arena for `q` and points the host mirror at it.  Contents are lost (callers follow up with a
+// full upload).
+int plan_arena(okb_ctx* c, int win, const WinCaps& q) {
+  WinStore& S = c->wins[win];
+  ArenaPlan P;
+  int CPc = 1;
+  while (CPc < q.NC) CPc <<= 1;
+  const int Kc = q.K, Lc = q.L, Lpc = (Lc + 31) & ~31;
+  const int NSc = Kc * CPc, NSPc = (NSc + 31) / 32 * 32;
+  const int dcc = 6 * Kc, dcap = 15 * Kc, dcpc = 4 * ((dcc + 1 + 3) / 4);
+  const int MN = std::max(q.MN, 1), MB = kMaxMargBlocks;
+  const size_t o_pose = P.take(8 * 7 * Kc), o_sb = P.take(8 * 9 * Kc), o_ext = P.take(8 * 7 * q.NE), o_mlm = P.take(8 * 4 * (size_t)Lpc);
+  const size_t o_out = P.take(8 * (16 * (size_t)Kc + 5 * (size_t)Lc));
+  const size_t o_cams = P.take(sizeof(okb_camera) * q.NC), o_obs = P.take(sizeof(okb_observation) * (size_t)std::max(q.O, 1));
+  const size_t o_imut = P.take(sizeof(okb_imu_term) * std::max(q.T, 1)), o_samp = P.take(sizeof(okb_imu_sample) * (size_t)std::max(q.S, 1));
+  const size_t o_pp = P.take(sizeof(okb_pose_prior) * std::max(q.PP, 1)), o_sbp = P.take(sizeof(okb_sb_prior) * std::max(q.PP, 1));
+  const size_t o_mkind = P.take(4 * MB), o_midx = P.take(4 * MB), o_mcol = P.take(4 * MB), o_moff = P.take(4 * MB);
+  const size_t o_mx0 = P.take(8 * 9 * MB), o_mJ = P.take(8 * (size_t)MN * MN), o_me0 = P.take(8 * MN), o_mH0 = P.take(8 * (size_t)MN * MN);
+  const size_t o_mlmi = P.take(8 * 4 * (size_t)Lpc), o_mark = P.take(Lpc), o_mvis = P.take(4 * (size_t)Lpc);
+  const size_t o_bitmap = P.take(4 * (((size_t)NSc * Lc + 31) / 32 + 1));
+  const size_t o_perm = P.take(4 * (size_t)Lpc), o_inv = P.take(4 * (size_t)Lpc), o_trange = P.take(4 * (size_t)(Lpc / 32 + 1)), o_vis = P.take(4 * (size_t)Lpc);
+  const size_t o_slots = P.take(sizeof(SlotInfo) * NSPc);
+  const size_t cmd_cap = align_up(full_upload_bytes(q) + 65536, 256);
+  const size_t o_cmd = P.take(cmd_cap);
+  // working state / scratch
+  const size_t o_lm = P.take(8 * 4 * (size_t)Lpc), o_pose_i = P.take(8 * 7 * Kc), o_sb_i = P.take(8 * 9 * Kc);
+  const size_t o_pose_c = P.take(8 * 7 * Kc), o_sb_c = P.take(8 * 9 * Kc), o_lm_c = P.take(8 * 4 * (size_t)Lpc);
+  size_t o_lmg[2], o_lmE[2], o_gd[2], o_Ed[2];
+  for (int b = 0; b < 2; ++b) { o_lmg[b] = P.take(8 * 3 * (size_t)Lc); o_lmE[b] = P.take(8 * 3 * (size_t)Lc); }
+  const size_t o_Rinv = P.take(8 * 6 * (size_t)Lc), o_slotctx = P.take(sizeof(SlotCtx) * NSPc), o_mf = P.take(8 * 3 * (size_t)Lpc * Kc);
+  const size_t o_gn = P.take(8 * 3 * (size_t)Lc), o_Li = P.take(8 * 9 * (size_t)Lpc), o_scale = P.take(8 * 3 * (size_t)Lc);
+  const int n_cx = (Lc + L1_THREADS - 1) / L1_THREADS;
+  const size_t o_partH = P.take(8 * (size_t)n_cx * Kc * kPartH), o_part = P.take(8 * (size_t)dcpc * dcpc * c->chunk_cap);
+  const size_t o_Hd = P.take(8 * (size_t)dcap * dcap);
+  for (int b = 0; b < 2; ++b) { o_gd[b] = P.take(8 * dcap); o_Ed[b] = P.take(8 * dcap); }
+  const size_t o_ud = P.take(8 * dcap), o_scd = P.take(8 * dcap), o_chol = P.take(8 * (size_t)(dcap + 1) * (dcap + 1));
+  const size_t o_obsz = P.take(sizeof(double2) * (size_t)Lc * NSc), o_obsw = P.take(8 * (size_t)Lc * NSc), o_M = P.take(8 * 6 * (size_t)Lpc * Kc);
+  const size_t o_quality = P.take(8 * (size_t)Lc);
+  const size_t o_cache = P.take(sizeof(ImuCache) * std::max(q.T, 1)), o_imu_out = P.take(8 * kImuOut * std::max(q.T, 1));
+
+  if (S.arena_bytes < P.total) {
+    if (S.arena) cudaFree(S.arena);
+    S.arena = nullptr; S.arena_bytes = 0;
+    OKB_CUDA(c, cudaMalloc(&S.arena, P.total));
+    S.arena_bytes = P.total;
   }
-  const int gx = std::max(1, std::min((max_work + 255) / 256, std::max(4, (8 * c->sm_count + count - 1) / count)));
-  k_zero<<<dim3(gx, count), 256, 0, c->stream_xfer>>>(c->d_wins, first);
-  k_prepare<<<dim3(gx, count), 256, 0, c->stream_xfer>>>(c->d_wins, first);
-  OKB_CUDA(c, cudaGetLastError());
+  const size_t out_bytes = 8 * (16 * (size_t)Kc + 5 * (size_t)Lc);
+  if (S.out_bytes < out_bytes) {
+    if (S.out_staging) cudaFreeHost(S.out_staging);
+    S.out_staging = nullptr; S.out_bytes = 0;
+    OKB_CUDA(c, cudaMallocHost(&S.out_staging, out_bytes));
+    S.out_bytes = out_bytes;
+  }
+  if (!S.down) OKB_CUDA(c, cudaEventCreateWithFlags(&S.down, cudaEventDisableTiming));
+  if (!S.copied) OKB_CUDA(c, cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
+  // the m_mark scratch must be all zero between commands; dead landmark slots must hold finite values
+  OKB_CUDA(c, cudaMemsetAsync(S.arena + o_mark, 0, Lpc, c->stream_xfer));
+  OKB_CUDA(c, cudaMemsetAsync(S.arena + o_mlm, 0, 8 * 4 * (size_t)Lpc, c->stream_xfer));
+  S.caps = q;
+  S.cmd_cap_dev = cmd_cap;
+
+  unsigned char* A = S.arena;
+  WinDev W;
+  std::memset(&W, 0, sizeof W);
+  auto dp = [&](size_t o) { return reinterpret_cast<double*>(A + o); };
+  auto up = [&](size_t o) { return reinterpret_cast<uint32_t*>(A + o); };
+  W.Kcap = q.K; W.Lcap = q.L; W.Ocap = q.O; W.Scap = q.S; W.Tcap = q.T; W.NEcap = q.NE; W.NCcap = q.NC; W.PPcap = q.PP;
+  W.pose = dp(o_pose); W.sb = dp(o_sb); W.ext = dp(o_ext); W.m_lm = dp(o_mlm); W.out = dp(o_out);
+  W.cams = reinterpret_cast<okb_camera*>(A + o_cams);
+  W.m_obs = reinterpret_cast<okb_observation*>(A + o_obs);
+  W.imu_terms = reinterpret_cast<okb_imu_term*>(A + o_imut);
+  W.samples = reinterpret_cast<okb_imu_sample*>(A + o_samp);
+  W.pp = reinterpret_cast<okb_pose_prior*>(A + o_pp);
+  W.sbp = reinterpret_cast<okb_sb_prior*>(A + o_sbp);
+  W.marg_kind = reinterpret_cast<int32_t*>(A + o_mkind); W.marg_idx = up(o_midx);
+  W.marg_col = reinterpret_cast<int32_t*>(A + o_mcol); W.marg_off = reinterpret_cast<int32_t*>(A + o_moff);
+  W.marg_x0 = dp(o_mx0); W.marg_J = dp(o_mJ); W.marg_e0 = dp(o_me0); W.marg_H0 = dp(o_mH0);
+  W.m_lm_init = dp(o_mlmi); W.m_mark = A + o_mark; W.m_vis = up(o_mvis); W.m_bitmap = up(o_bitmap);
+  W.perm = up(o_perm); W.lm_inv = up(o_inv); W.tile_range = up(o_trange); W.lm_vis = up(o_vis);
+  W.slots = reinterpret_cast<SlotInfo*>(A + o_slots);
+  W.cmd = A + o_cmd;
+  W.lm = dp(o_lm); W.pose_init = dp(o_pose_i); W.sb_init = dp(o_sb_i);
+  W.pose_c = dp(o_pose_c); W.sb_c = dp(o_sb_c); W.lm_c = dp(o_lm_c);
+  for (int b = 0; b < 2; ++b) { W.lm_g[b] = dp(o_lmg[b]); W.lm_E[b] = dp(o_lmE[b]); W.gd[b] = dp(o_gd[b]); W.Ed[b] = dp(o_Ed[b]); }
+  W.lm_Rinv = dp(o_Rinv); W.slot_ctx = reinterpret_cast<SlotCtx*>(A + o_slotctx); W.lm_mf = dp(o_mf); W.lm_gn = dp(o_gn);
+  W.lm_Li = dp(o_Li); W.lm_scale = dp(o_scale); W.partH = dp(o_partH); W.partA = dp(o_part);
+  W.Hd = dp(o_Hd); W.ud = dp(o_ud); W.scale_d = dp(o_scd); W.chol = dp(o_chol);
+  W.obs_z = reinterpret_cast<double2*>(A + o_obsz); W.obs_w = dp(o_obsw); W.lm_M = dp(o_M); W.quality = dp(o_quality);
+  W.zero_ptr[0] = A + o_obsz; W.zero_ptr[1] = A + o_obsw; W.zero_ptr[2] = A + o_M;
+  W.imu_cache = reinterpret_cast<ImuCache*>(A + o_cache); W.imu_out = dp(o_imu_out);
+  W.st = c->d_states + win;
+  W.n_chunks = 1; W.use_cauchy = 1;
+  c->host[win] = W;
   return OKB_OK;
 }
 
-static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finish);
+// ---- command staging (pinned, per slot)
+int cmd_reserve(okb_ctx* c, WinStore& S, size_t extra) {
+  if (S.staging_busy) {          // the previous commit's H2D copy reads the buffer: wait before it is rewritten
+    OKB_CUDA(c, cudaEventSynchronize(S.copied));
+    S.staging_busy = false;
+  }
+  const size_t need = S.cmd_used + extra;
+  if (need <= S.staging_bytes) return OKB_OK;
+  const size_t cap = align_up(std::max(need, 2 * S.staging_bytes), 4096);
+  unsigned char* nb = nullptr;
+  OKB_CUDA(c, cudaMallocHost(&nb, cap));
+  if (S.cmd_used) std::memcpy(nb, S.staging, S.cmd_used);
+  if (S.staging) cudaFreeHost(S.staging);
+  S.staging = nb; S.staging_bytes = cap;
+  return OKB_OK;
+}
+// Appends a command header and returns the payload pointer (8-byte aligned); payload_bytes is rounded up to 8.
+unsigned char* cmd_put(WinStore& S, uint32_t op, uint32_t n, uint32_t a, uint32_t b, size_t payload_bytes) {
+  payload_bytes = align_up(payload_bytes, 8);
+  CmdHeader h{op, n, a, b, payload_bytes};
+  std::memcpy(S.staging + S.cmd_used, &h, sizeof h);
+  unsigned char* pay = S.staging + S.cmd_used + sizeof h;
+  S.cmd_used += sizeof h + payload_bytes;
+  return pay;
+}
+}  // namespace
 
-extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) { return upload_pack(c, win, D, true); }
+static const char* graph_error_text(int e) {
+  switch (e) {
+    case GERR_INDEX: return "window graph: index out of range";
+    case GERR_DUPLICATE: return "window graph: duplicate observation of a landmark in one (frame,camera)";
+    case GERR_SLOT_EXT: return "window graph: inconsistent extrinsics block for a (frame,camera) slot";
+    case GERR_CAPACITY: return "window graph: capacity exceeded (okb_window_reserve)";
+    case GERR_SQRT_INFO: return "window graph: observation with non-positive sqrt information";
+    case GERR_DIMS: return "window graph: host / device dimension mismatch";
+    case GERR_MARG_REF: return "window graph: a removed frame is still referenced by the marginalisation prior";
+    default: return "window graph: unknown error";
+  }
+}
+static int graph_error_status(int e) {
+  return e == GERR_DUPLICATE ? OKB_ERR_UNSUPPORTED : e == GERR_CAPACITY ? OKB_ERR_CAPACITY : OKB_ERR_INVALID_ARG;
+}
 
-// Host packing + H2D copies of one window (transfer stream); `finish` also launches the device epilogue.
-static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finish) {
+extern "C" int okb_window_reserve(okb_ctx* c, int win, int max_frames, int max_landmarks, int max_observations, int max_imu_samples,
+                                  int max_marg_dim) {
+  if (!c || win < 0 || win >= c->max_windows || max_frames < 0 || max_landmarks < 0 || max_observations < 0 || max_imu_samples < 0 ||
+      max_marg_dim < 0) return OKB_ERR_INVALID_ARG;
+  if (max_frames > kMaxFrames || max_marg_dim > kMaxMarg) { c->set_error("okb_window_reserve: beyond the compiled-in limits"); return OKB_ERR_CAPACITY; }
+  WinCaps& r = c->wins[win].reserve;
+  r.K = max_frames; r.L = max_landmarks; r.O = max_observations; r.S = max_imu_samples; r.T = max_frames; r.MN = max_marg_dim;
+  r.PP = std::max(r.PP, 4);
+  return OKB_OK;
+}
+
+// Commits the pending commands of slots [first, first+count): H2D copies + interpreter + compile on the transfer stream.
+static int commit_range(okb_ctx* c, int first, int count) {
+  cudaSetDevice(c->device);
+  cudaStream_t xs = c->stream_xfer;
+  bool any = false;
+  int max_work = 1;
+  for (int i = first; i < first + count; ++i) {
+    WinStore& S = c->wins[i];
+    WinDev& W = c->host[i];
+    W.cmd_bytes = 0; W.dirty = 0; W.full = 0;
+    if (!S.cmd_used) continue;
+    if (S.cmd_used > S.cmd_cap_dev) { c->set_error("pending window commands exceed the device command buffer (commit more often)"); return OKB_ERR_CAPACITY; }
+    any = true;
+    if (S.done_idx >= 0) OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));   // solver work on this slot finishes first
+    OKB_CUDA(c, cudaMemcpyAsync(const_cast<unsigned char*>(W.cmd), S.staging, S.cmd_used, cudaMemcpyHostToDevice, xs));
+    OKB_CUDA(c, cudaEventRecord(S.copied, xs));
+    S.staging_busy = true;
+    S.h2d_bytes = S.cmd_used;
+    W.cmd_bytes = (int)S.cmd_used; W.dirty = 1; W.full = S.full_pending ? 1 : 0;
+    W.n_obs = S.obs_bound;
+    S.cmd_used = 0; S.full_pending = false; S.committed = true;
+    max_work = std::max(max_work, std::max(std::max(W.n_obs, 4 * W.L), std::max(7 * W.K, 9 * W.NSB)));
+  }
+  if (!any) return OKB_OK;
+  OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + first, &c->host[first], sizeof(WinDev) * count, cudaMemcpyHostToDevice, xs));
+  const int gx = std::max(1, std::min((max_work + 255) / 256, std::max(4, (8 * c->sm_count + count - 1) / count)));
+  k_apply_commands<<<count, 1024, 0, xs>>>(c->d_wins, first);
+  k_compile_obs<<<count, 1024, 0, xs>>>(c->d_wins, first);
+  k_compile_sort<<<count, 1024, 0, xs>>>(c->d_wins, first);
+  k_zero<<<dim3(gx, count), 256, 0, xs>>>(c->d_wins, first);
+  k_prepare<<<dim3(gx, count), 256, 0, xs>>>(c->d_wins, first);
+  c->launches += 5;
+  OKB_CUDA(c, cudaGetLastError());
+  for (int i = first; i < first + count; ++i) { c->host[i].cmd_bytes = 0; c->host[i].dirty = 0; c->host[i].full = 0; }
+  return OKB_OK;
+}
+
+extern "C" int okb_window_commit(okb_ctx* c, int first, int count) {
+  if (!c || first < 0 || count < 1 || first + count > c->max_windows) return OKB_ERR_INVALID_ARG;
+  return commit_range(c, first, count);
+}
+
+// Full upload = a command stream that rebuilds the whole graph (host side: validation of what only the host can
+// reject synchronously + one pass of memcpy into the pinned command buffer; sorting / slot tables / duplicate
+// detection happen on the device).
+static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D) {
   if (!c || !D || win < 0 || win >= c->max_windows) return OKB_ERR_INVALID_ARG;
   cudaSetDevice(c->device);
   const int K = D->n_poses, NSB = D->n_speed_bias, NE = D->n_extrinsics, L = D->n_landmarks, NC = D->n_cameras;
   if (K < 1 || L < 1 || NC < 1 || NE < 1) { c->set_error("empty window"); return OKB_ERR_INVALID_ARG; }
-  if (K > kMaxFrames) { c->set_error("more than 32 frames per window"); return OKB_ERR_CAPACITY; }
+  if (K > kMaxFrames || NSB > kMaxFrames) { c->set_error("more than 32 frames per window"); return OKB_ERR_CAPACITY; }
   for (int e = 0; e < NE; ++e)
     if (!D->extrinsics_fixed || !D->extrinsics_fixed[e]) {
       c->set_error("device solver requires fixed extrinsics (sigma_absolute_* = 0 as in the shipped configs)");
       return OKB_ERR_UNSUPPORTED;
     }
   if (D->n_relpose_terms > 0) { c->set_error("relative-pose terms need free extrinsics"); return OKB_ERR_UNSUPPORTED; }
-  int CP = 1;
-  while (CP < NC) CP <<= 1;
-  if (CP > 32) { c->set_error("more than 32 cameras"); return OKB_ERR_CAPACITY; }
-  const int NS = K * CP, NG = (NS + 31) / 32, NSP = NG * 32;
-  const int dc = 6 * K, d = dc + 9 * NSB, dcp = 4 * ((dc + 1 + 3) / 4);
-  if (d > kMaxDense) { c->set_error("reduced system too large"); return OKB_ERR_CAPACITY; }
+  if (NC > 32) { c->set_error("more than 32 cameras"); return OKB_ERR_CAPACITY; }
+  if (6 * K + 9 * NSB > kMaxDense) { c->set_error("reduced system too large"); return OKB_ERR_CAPACITY; }
   int marg_n = 0, marg_nb = 0, marg_xdim = 0;
   if (D->marg && D->marg->n > 0) {
     marg_n = D->marg->n; marg_nb = D->marg->n_blocks;
-    if (marg_n > kMaxMarg) { c->set_error("marginalisation prior too large"); return OKB_ERR_CAPACITY; }
-    for (int b = 0; b < marg_nb; ++b) marg_xdim += (D->marg->block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
+    if (marg_n > kMaxMarg || marg_nb > kMaxMargBlocks) { c->set_error("marginalisation prior too large"); return OKB_ERR_CAPACITY; }
+    int col = 0;
+    for (int b = 0; b < marg_nb; ++b) {
+      const int kind = D->marg->block_kind[b];
+      const uint32_t idx = D->marg->block_idx[b];
+      const int lim = kind == OKB_BLOCK_POSE ? K : kind == OKB_BLOCK_SPEED_BIAS ? NSB : kind == OKB_BLOCK_EXTRINSICS ? NE : -1;
+      if (lim < 0) { c->set_error("marginalisation prior: unknown block kind"); return OKB_ERR_INVALID_ARG; }
+      if ((int)idx >= lim) { c->set_error("marginalisation prior: block index out of range"); return OKB_ERR_INVALID_ARG; }
+      if (kind != OKB_BLOCK_EXTRINSICS) col += (kind == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
+      marg_xdim += (kind == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
+    }
+    if (col != marg_n) { c->set_error("marginalisation prior dimension mismatch"); return OKB_ERR_INVALID_ARG; }
   }
-  const size_t smA = smemA2_bytes(K, dcp, 0);
-  if (smA > (size_t)c->smem_optin) { c->set_error("window does not fit kernel A shared memory"); return OKB_ERR_CAPACITY; }
-
-  // ---- arena plan: [inputs (copied from the staging buffer)] [scratch]
-  ArenaPlan P;
-  WinDev W;
-  std::memset(&W, 0, sizeof W);
-  W.K = K; W.NSB = NSB; W.NE = NE; W.L = L; W.NC = NC; W.CP = CP; W.NS = NS; W.NG = NG; W.NSP = NSP;
-  W.d = d; W.dc = dc; W.dcp = dcp;
-  W.n_imu = D->n_imu_terms; W.n_samples = D->n_imu_samples; W.n_pp = D->n_pose_priors; W.n_sbp = D->n_sb_priors;
-  W.marg_n = marg_n; W.marg_nb = marg_nb; W.marg_xdim = marg_xdim;
-  W.n_chunks = 1; W.lm_per_chunk = L; W.use_cauchy = 1;
-  W.imu_params = D->imu_params;
-  const size_t o_pose = P.take(sizeof(double) * 7 * K);
-  const size_t o_sb = P.take(sizeof(double) * 9 * std::max(NSB, 1));
-  const size_t o_ext = P.take(sizeof(double) * 7 * NE);
-  const size_t o_lm = P.take(sizeof(double) * 4 * L);
-  const size_t o_slots = P.take(sizeof(SlotInfo) * NSP);
-  const size_t o_cams = P.take(sizeof(okb_camera) * NC);
-  const size_t o_vis = P.take(sizeof(uint32_t) * L);
-  const size_t o_inv = P.take(sizeof(uint32_t) * L);
-  const int n_tiles = (L + 31) / 32;
-  const size_t o_trange = P.take(sizeof(uint32_t) * n_tiles);
-  const size_t o_obsl = P.take(sizeof(okb_observation) * std::max(D->n_obs, 1));
-  const size_t o_imut = P.take(sizeof(okb_imu_term) * std::max(W.n_imu, 1));
-  const size_t o_samp = P.take(sizeof(okb_imu_sample) * std::max(W.n_samples, 1));
-  const size_t o_pp = P.take(sizeof(okb_pose_prior) * std::max(W.n_pp, 1));
-  const size_t o_sbp = P.take(sizeof(okb_sb_prior) * std::max(W.n_sbp, 1));
-  const size_t o_mkind = P.take(sizeof(int32_t) * std::max(marg_nb, 1));
-  const size_t o_midx = P.take(sizeof(uint32_t) * std::max(marg_nb, 1));
-  const size_t o_mcol = P.take(sizeof(int32_t) * std::max(marg_nb, 1));
-  const size_t o_moff = P.take(sizeof(int32_t) * std::max(marg_nb, 1));
-  const size_t o_mx0 = P.take(sizeof(double) * std::max(marg_xdim, 1));
-  const size_t o_mJ = P.take(sizeof(double) * std::max(marg_n * marg_n, 1));
-  const size_t o_me0 = P.take(sizeof(double) * std::max(marg_n, 1));
-  const size_t o_mH0 = P.take(sizeof(double) * std::max(marg_n * marg_n, 1));
-  const size_t input_bytes = P.total;
-  // scratch / state
-  const size_t o_pose_i = P.take(sizeof(double) * 7 * K), o_sb_i = P.take(sizeof(double) * 9 * std::max(NSB, 1));
-  const size_t o_lm_i = P.take(sizeof(double) * 4 * L);
-  const size_t o_pose_c = P.take(sizeof(double) * 7 * K), o_sb_c = P.take(sizeof(double) * 9 * std::max(NSB, 1));
-  const int Lp = (L + 31) & ~31;
-  const size_t o_lm_c = P.take(sizeof(double) * 4 * Lp);
-  size_t o_lmg[2], o_lmE[2], o_gd[2], o_Ed[2];
-  for (int b = 0; b < 2; ++b) { o_lmg[b] = P.take(sizeof(double) * 3 * L); o_lmE[b] = P.take(sizeof(double) * 3 * L); }
-  const size_t o_Rinv = P.take(sizeof(double) * 6 * L);
-  const size_t o_slotctx = P.take(sizeof(SlotCtx) * NSP);
-  const size_t o_mf = P.take(sizeof(double) * 3 * (size_t)Lp * K);
-  const size_t o_gn = P.take(sizeof(double) * 3 * L);
-  const size_t o_Li = P.take(sizeof(double) * 9 * Lp);
-  const size_t o_scale = P.take(sizeof(double) * 3 * L);
-  const int pstride = dcp * dcp;
-  const int n_cx = (L + L1_THREADS - 1) / L1_THREADS;
-  const size_t o_partH = P.take(sizeof(double) * (size_t)n_cx * K * kPartH);
-  const size_t o_part = P.take(sizeof(double) * (size_t)pstride * c->chunk_cap);
-  const size_t o_Hd = P.take(sizeof(double) * (size_t)d * d);
-  for (int b = 0; b < 2; ++b) { o_gd[b] = P.take(sizeof(double) * d); o_Ed[b] = P.take(sizeof(double) * d); }
-  const size_t o_ud = P.take(sizeof(double) * d), o_scd = P.take(sizeof(double) * d);
-  const size_t o_chol = P.take(sizeof(double) * (size_t)(d + 1) * (d + 1));
-  // one contiguous region zeroed by a single memset per upload
-  const size_t o_zero = P.total;
-  const size_t o_obsz = P.take(sizeof(double2) * (size_t)L * NS);
-  const size_t o_obsw = P.take(sizeof(double) * (size_t)L * NS);
-  const size_t o_M = P.take(sizeof(double) * 6 * (size_t)Lp * K);
-  const size_t o_quality = P.take(sizeof(double) * L);
-  const size_t o_cache = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
-  const size_t o_cache_i = P.take(sizeof(ImuCache) * std::max(W.n_imu, 1));
-  const size_t zero_bytes = P.total - o_zero;
-  const size_t o_imu_out = P.take(sizeof(double) * kImuOut * std::max(W.n_imu, 1));
-
-  // ---- validation of everything that is copied to the device unchecked, BEFORE the slot is touched
   for (int i = 0; i < D->n_pose_priors; ++i)
     if ((int)D->pose_priors[i].pose_idx >= K) { c->set_error("pose prior index out of range"); return OKB_ERR_INVALID_ARG; }
   for (int i = 0; i < D->n_sb_priors; ++i)
@@ -289,179 +420,91 @@ static int upload_pack(okb_ctx* c, int win, const okb_window_desc* D, bool finis
       return OKB_ERR_INVALID_ARG;
     }
   }
-  if (marg_n) {
-    int col = 0;
-    for (int b = 0; b < marg_nb; ++b) {
-      const int kind = D->marg->block_kind[b];
-      const uint32_t idx = D->marg->block_idx[b];
-      const int lim = kind == OKB_BLOCK_POSE ? K : kind == OKB_BLOCK_SPEED_BIAS ? NSB : kind == OKB_BLOCK_EXTRINSICS ? NE : -1;
-      if (lim < 0) { c->set_error("marginalisation prior: unknown block kind"); return OKB_ERR_INVALID_ARG; }
-      if ((int)idx >= lim) { c->set_error("marginalisation prior: block index out of range"); return OKB_ERR_INVALID_ARG; }
-      if (kind != OKB_BLOCK_EXTRINSICS) col += (kind == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
-    }
-    if (col != marg_n) { c->set_error("marginalisation prior dimension mismatch"); return OKB_ERR_INVALID_ARG; }
-  }
-
-  WinStore& S = c->wins[win];
-  S.uploaded = false;        // true again only when the whole upload has been issued successfully
-  if (S.arena_bytes < P.total) {
-    if (S.arena) cudaFree(S.arena);
-    S.arena = nullptr; S.arena_bytes = 0;
-    OKB_CUDA(c, cudaMalloc(&S.arena, P.total));
-    S.arena_bytes = P.total;
-  }
-  if (S.staging_bytes < input_bytes) {
-    if (S.staging) cudaFreeHost(S.staging);
-    S.staging = nullptr; S.staging_bytes = 0;
-    OKB_CUDA(c, cudaMallocHost(&S.staging, input_bytes));
-    S.staging_bytes = input_bytes;
-  }
-  const size_t out_bytes = (o_lm + sizeof(double) * 4 * L - o_pose) + sizeof(double) * L;
-  if (S.out_bytes < out_bytes) {
-    if (S.out_staging) cudaFreeHost(S.out_staging);
-    S.out_staging = nullptr; S.out_bytes = 0;
-    OKB_CUDA(c, cudaMallocHost(&S.out_staging, out_bytes));
-    S.out_bytes = out_bytes;
-  }
-  if (!S.down) OKB_CUDA(c, cudaEventCreateWithFlags(&S.down, cudaEventDisableTiming));
-  if (!S.copied) OKB_CUDA(c, cudaEventCreateWithFlags(&S.copied, cudaEventDisableTiming));
-  else OKB_CUDA(c, cudaEventSynchronize(S.copied));
-  unsigned char* H = S.staging;
-  std::memcpy(H + o_pose, D->poses, sizeof(double) * 7 * K);
-  if (NSB) std::memcpy(H + o_sb, D->speed_bias, sizeof(double) * 9 * NSB);
-  std::memcpy(H + o_ext, D->extrinsics, sizeof(double) * 7 * NE);
-  std::memcpy(H + o_cams, D->cameras, sizeof(okb_camera) * NC);
-  if (W.n_imu) std::memcpy(H + o_imut, D->imu_terms, sizeof(okb_imu_term) * W.n_imu);
-  if (W.n_samples) std::memcpy(H + o_samp, D->imu_samples, sizeof(okb_imu_sample) * W.n_samples);
-  if (W.n_pp) std::memcpy(H + o_pp, D->pose_priors, sizeof(okb_pose_prior) * W.n_pp);
-  if (W.n_sbp) std::memcpy(H + o_sbp, D->sb_priors, sizeof(okb_sb_prior) * W.n_sbp);
-  // Observations travel as the compact list; the device scatters them into the slot-major grid
-  // (k_prepare).  The host pass validates indices, finds the (frame,camera) slots, rejects duplicates with a
-  // bitmap over the grid cells and builds the per-landmark frame-visibility masks.
-  SlotInfo* slots = reinterpret_cast<SlotInfo*>(H + o_slots);
-  for (int s = 0; s < NSP; ++s) slots[s] = SlotInfo{0, 0, 0, 0};
-  std::vector<uint32_t> vis(L, 0u);       // frame-visibility mask per landmark (caller's indexing)
-  std::vector<uint64_t> seen(((size_t)NS * L + 63) / 64, 0);
   for (int i = 0; i < D->n_obs; ++i) {
     const okb_observation& ob = D->obs[i];
     if ((int)ob.pose_idx >= K || (int)ob.lm_idx >= L || (int)ob.ext_idx >= NE || (int)ob.cam_idx >= NC) {
       c->set_error("observation index out of range");
       return OKB_ERR_INVALID_ARG;
     }
-    const int s = (int)ob.pose_idx * CP + (int)ob.cam_idx;
-    SlotInfo& si = slots[s];
-    if (!si.valid) si = SlotInfo{(int)ob.pose_idx, (int)ob.ext_idx, (int)ob.cam_idx, 1};
-    else if (si.ext_idx != (int)ob.ext_idx) { c->set_error("inconsistent extrinsics block for a (frame,camera) slot"); return OKB_ERR_INVALID_ARG; }
-    const size_t g = (size_t)s * L + ob.lm_idx;
-    uint64_t& word = seen[g >> 6];
-    const uint64_t bit = 1ull << (g & 63);
-    if (word & bit) { c->set_error("duplicate observation of a landmark in one (frame,camera)"); return OKB_ERR_UNSUPPORTED; }
-    word |= bit;
     if (!(ob.sqrt_info > 0.0)) { c->set_error("observation with non-positive sqrt information"); return OKB_ERR_INVALID_ARG; }
-    vis[ob.lm_idx] |= (1u << ob.pose_idx);
   }
-  // Internal landmark order: sorted by (first, last) observing frame, stable (counting sort); landmarks
-  // without observations go last.  The device works in this order only; downloads map back.
-  {
-    S.perm.resize(L);
-    uint32_t* inv = reinterpret_cast<uint32_t*>(H + o_inv);
-    uint32_t* trange = reinterpret_cast<uint32_t*>(H + o_trange);
-    sort_landmarks_by_frame_range(vis.data(), L, S.perm.data(), inv, trange);     // okb_hostpack.hpp
-    uint32_t* vis_s = reinterpret_cast<uint32_t*>(H + o_vis);
-    double* lm_s = reinterpret_cast<double*>(H + o_lm);
-    for (int j = 0; j < L; ++j) {
-      const uint32_t l = S.perm[j];
-      vis_s[j] = vis[l];
-      std::memcpy(lm_s + 4 * (size_t)j, D->landmarks + 4 * (size_t)l, sizeof(double) * 4);
-    }
-  }
-  if (D->n_obs) std::memcpy(H + o_obsl, D->obs, sizeof(okb_observation) * D->n_obs);
-  if (marg_n) {
-    const okb_marg_prior& M = *D->marg;
-    int32_t* mk = reinterpret_cast<int32_t*>(H + o_mkind);
-    uint32_t* mi = reinterpret_cast<uint32_t*>(H + o_midx);
-    int32_t* mc = reinterpret_cast<int32_t*>(H + o_mcol);
-    int32_t* mo = reinterpret_cast<int32_t*>(H + o_moff);
-    int col = 0, xo = 0;
-    for (int b = 0; b < marg_nb; ++b) {
-      mk[b] = M.block_kind[b]; mi[b] = M.block_idx[b]; mo[b] = xo;
-      const bool fixed = (M.block_kind[b] == OKB_BLOCK_EXTRINSICS);   // extrinsics are fixed in the device solver
-      mc[b] = fixed ? -1 : col;
-      if (!fixed) col += (M.block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
-      xo += (M.block_kind[b] == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
-    }
-    std::memcpy(H + o_mx0, M.x0, sizeof(double) * marg_xdim);
-    std::memcpy(H + o_mJ, M.J, sizeof(double) * marg_n * marg_n);
-    std::memcpy(H + o_me0, M.e0, sizeof(double) * marg_n);
-    double* H0 = reinterpret_cast<double*>(H + o_mH0);
-    for (int i = 0; i < marg_n; ++i)
-      for (int j = 0; j <= i; ++j) {
-        double s = 0;
-        for (int r = 0; r < marg_n; ++r) s += M.J[(size_t)r * marg_n + i] * M.J[(size_t)r * marg_n + j];
-        H0[(size_t)i * marg_n + j] = s; H0[(size_t)j * marg_n + i] = s;
-      }
-  }
-  unsigned char* A = S.arena;
-  cudaStream_t xs = c->stream_xfer;
-  // solver work launched earlier on this slot must have finished before its arena is overwritten
-  if (S.done_idx >= 0) OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
-  OKB_CUDA(c, cudaMemcpyAsync(A, H, input_bytes, cudaMemcpyHostToDevice, xs));
-  OKB_CUDA(c, cudaEventRecord(S.copied, xs));
+  if (smemA2_bytes(K, 4 * ((6 * K + 1 + 3) / 4), 0) > (size_t)c->smem_optin) { c->set_error("window does not fit kernel A shared memory"); return OKB_ERR_CAPACITY; }
 
-  auto dp = [&](size_t o) { return reinterpret_cast<double*>(A + o); };
-  W.pose = dp(o_pose); W.sb = dp(o_sb); W.ext = dp(o_ext); W.lm = dp(o_lm);
-  W.pose_init = dp(o_pose_i); W.sb_init = dp(o_sb_i); W.lm_init = dp(o_lm_i);
-  W.pose_c = dp(o_pose_c); W.sb_c = dp(o_sb_c); W.lm_c = dp(o_lm_c);
-  W.slots = reinterpret_cast<SlotInfo*>(A + o_slots);
-  W.cams = reinterpret_cast<okb_camera*>(A + o_cams);
-  W.obs_z = reinterpret_cast<double2*>(A + o_obsz);
-  W.obs_w = dp(o_obsw);
-  W.lm_vis = reinterpret_cast<uint32_t*>(A + o_vis);
-  W.Lp = Lp;
-  W.zero_ptr = A + o_zero; W.zero_bytes = zero_bytes;
-  W.lm_inv = reinterpret_cast<const uint32_t*>(A + o_inv);
-  W.tile_range = reinterpret_cast<const uint32_t*>(A + o_trange);
-  W.obs_list = reinterpret_cast<const okb_observation*>(A + o_obsl);
-  W.n_obs = D->n_obs;
-  for (int b = 0; b < 2; ++b) { W.lm_g[b] = dp(o_lmg[b]); W.lm_E[b] = dp(o_lmE[b]); W.gd[b] = dp(o_gd[b]); W.Ed[b] = dp(o_Ed[b]); }
-  W.slot_ctx = reinterpret_cast<SlotCtx*>(A + o_slotctx);
-  W.lm_Rinv = dp(o_Rinv); W.lm_M = dp(o_M); W.lm_mf = dp(o_mf); W.partH = dp(o_partH); W.lm_gn = dp(o_gn); W.lm_Li = dp(o_Li); W.lm_scale = dp(o_scale); W.quality = dp(o_quality);
-  W.partA = dp(o_part); W.partA_stride = pstride;
-  W.Hd = dp(o_Hd); W.ud = dp(o_ud); W.scale_d = dp(o_scd); W.chol = dp(o_chol);
-  W.imu_terms = reinterpret_cast<okb_imu_term*>(A + o_imut);
-  W.samples = reinterpret_cast<okb_imu_sample*>(A + o_samp);
-  W.imu_cache = reinterpret_cast<ImuCache*>(A + o_cache);
-  W.imu_cache_init = reinterpret_cast<ImuCache*>(A + o_cache_i);
-  W.imu_out = dp(o_imu_out);
-  W.pp = reinterpret_cast<okb_pose_prior*>(A + o_pp);
-  W.sbp = reinterpret_cast<okb_sb_prior*>(A + o_sbp);
-  W.marg_kind = reinterpret_cast<int32_t*>(A + o_mkind);
-  W.marg_idx = reinterpret_cast<uint32_t*>(A + o_midx);
-  W.marg_col = reinterpret_cast<int32_t*>(A + o_mcol);
-  W.marg_off = reinterpret_cast<int32_t*>(A + o_moff);
-  W.marg_x0 = dp(o_mx0); W.marg_J = dp(o_mJ); W.marg_e0 = dp(o_me0); W.marg_H0 = dp(o_mH0);
-  W.st = c->d_states + win;
+  WinStore& S = c->wins[win];
+  S.uploaded = false;        // true again only when the whole upload has been issued successfully
+  WinCaps need{K, L, D->n_obs, D->n_imu_samples, D->n_imu_terms, NE, NC, std::max(D->n_pose_priors, D->n_sb_priors), marg_n};
+  need = caps_max(need, S.reserve);
+  need.T = std::max(need.T, need.K);
+  if (!S.arena || !caps_cover(S.caps, need)) {
+    if (S.done_idx >= 0) OKB_CUDA(c, cudaEventSynchronize(c->done_ring[S.done_idx]));    // the old arena may still be in use
+    int rc = plan_arena(c, win, S.arena ? caps_max(S.caps, need) : need);
+    if (rc) return rc;
+  }
+  S.cmd_used = 0;            // a full upload supersedes anything still pending
+  int rc = cmd_reserve(c, S, full_upload_bytes(need));
+  if (rc) return rc;
+  unsigned char* q;
+  q = cmd_put(S, CMD_RESET_GRAPH, 0, (uint32_t)NE, (uint32_t)NC, 8 * 7 * (size_t)NE + sizeof(okb_camera) * NC);
+  std::memcpy(q, D->extrinsics, 8 * 7 * (size_t)NE);
+  std::memcpy(q + 8 * 7 * (size_t)NE, D->cameras, sizeof(okb_camera) * NC);
+  q = cmd_put(S, CMD_SET_FRAMES, 0, (uint32_t)K, (uint32_t)NSB, 8 * (7 * (size_t)K + 9 * (size_t)NSB));
+  std::memcpy(q, D->poses, 8 * 7 * (size_t)K);
+  if (NSB) std::memcpy(q + 8 * 7 * (size_t)K, D->speed_bias, 8 * 9 * (size_t)NSB);
+  q = cmd_put(S, CMD_SET_LANDMARKS, (uint32_t)L, 0, 1, 8 * 4 * (size_t)L);
+  std::memcpy(q, D->landmarks, 8 * 4 * (size_t)L);
+  if (D->n_obs) {
+    q = cmd_put(S, CMD_ADD_OBS, (uint32_t)D->n_obs, 0, 0, sizeof(okb_observation) * (size_t)D->n_obs);
+    std::memcpy(q, D->obs, sizeof(okb_observation) * (size_t)D->n_obs);
+  }
+  q = cmd_put(S, CMD_SET_IMU, 0, (uint32_t)D->n_imu_terms, (uint32_t)D->n_imu_samples,
+              sizeof(okb_imu_term) * D->n_imu_terms + sizeof(okb_imu_sample) * (size_t)D->n_imu_samples);
+  if (D->n_imu_terms) std::memcpy(q, D->imu_terms, sizeof(okb_imu_term) * D->n_imu_terms);
+  if (D->n_imu_samples) std::memcpy(q + sizeof(okb_imu_term) * D->n_imu_terms, D->imu_samples, sizeof(okb_imu_sample) * (size_t)D->n_imu_samples);
+  q = cmd_put(S, CMD_SET_POSE_PRIORS, (uint32_t)D->n_pose_priors, 0, 0, sizeof(okb_pose_prior) * D->n_pose_priors);
+  if (D->n_pose_priors) std::memcpy(q, D->pose_priors, sizeof(okb_pose_prior) * D->n_pose_priors);
+  q = cmd_put(S, CMD_SET_SB_PRIORS, (uint32_t)D->n_sb_priors, 0, 0, sizeof(okb_sb_prior) * D->n_sb_priors);
+  if (D->n_sb_priors) std::memcpy(q, D->sb_priors, sizeof(okb_sb_prior) * D->n_sb_priors);
+  if (marg_n) {
+    const size_t kb = align_up(4 * (size_t)marg_nb, 8);
+    q = cmd_put(S, CMD_SET_MARG, 0, (uint32_t)marg_n, (uint32_t)marg_nb, 2 * kb + 8 * ((size_t)marg_xdim + (size_t)marg_n * marg_n + marg_n));
+    std::memset(q, 0, 2 * kb);
+    std::memcpy(q, D->marg->block_kind, 4 * (size_t)marg_nb);
+    std::memcpy(q + kb, D->marg->block_idx, 4 * (size_t)marg_nb);
+    double* x = reinterpret_cast<double*>(q + 2 * kb);
+    std::memcpy(x, D->marg->x0, 8 * (size_t)marg_xdim);
+    std::memcpy(x + marg_xdim, D->marg->J, 8 * (size_t)marg_n * marg_n);
+    std::memcpy(x + marg_xdim + (size_t)marg_n * marg_n, D->marg->e0, 8 * (size_t)marg_n);
+  }
+  // host mirror of the dimensions
+  WinDev& W = c->host[win];
+  W.K = K; W.NSB = NSB; W.NE = NE; W.L = L; W.NC = NC;
+  W.n_imu = D->n_imu_terms; W.n_samples = D->n_imu_samples; W.n_pp = D->n_pose_priors; W.n_sbp = D->n_sb_priors;
+  W.marg_n = marg_n; W.marg_nb = marg_nb; W.marg_xdim = marg_xdim;
+  W.imu_params = D->imu_params;
+  derive_dims(W);
   W.shard_rank = c->shard_rank; W.shard_world = c->shard_world; W.shard_box_cap = c->shard_box_cap;
   if (c->shard_world > 1) {
-    if (shard_box_doubles(K, dcp) > (size_t)c->shard_box_cap) { c->set_error("window exceeds the shard mailbox (max_frames of okb_shard_export)"); return OKB_ERR_CAPACITY; }
+    if (shard_box_doubles(K, W.dcp) > (size_t)c->shard_box_cap) { c->set_error("window exceeds the shard mailbox (max_frames of okb_shard_export)"); return OKB_ERR_CAPACITY; }
     for (int r = 0; r < c->shard_world; ++r) {
       if (!c->shard_peer[r]) { c->set_error("landmark sharding: okb_shard_connect has not been called"); return OKB_ERR_INVALID_ARG; }
       W.shard_mail[r] = c->shard_peer[r] + (size_t)win * c->shard_win_bytes;
     }
   }
-  c->host[win] = W;
+  S.terms.assign(D->imu_terms, D->imu_terms + D->n_imu_terms);
+  S.pp_idx.clear(); S.sbp_idx.clear();
+  for (int i = 0; i < D->n_pose_priors; ++i) S.pp_idx.push_back(D->pose_priors[i].pose_idx);
+  for (int i = 0; i < D->n_sb_priors; ++i) S.sbp_idx.push_back(D->sb_priors[i].sb_idx);
+  S.obs_bound = D->n_obs;
+  S.full_pending = true;
+  S.K_init = K; S.NSB_init = NSB; S.L_init = L;
   S.uploaded = true;
-  S.h2d_bytes = input_bytes;
-  OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + win, &c->host[win], sizeof(WinDev), cudaMemcpyHostToDevice, xs));
-  if (finish) {
-    const int rc = upload_finish(c, win, 1);
-    if (rc) return rc;
-  }
-  // No synchronisation here: uploads of different slots pipeline behind each other on the transfer stream
-  // and overlap solver kernels of other windows.  The staging buffer belongs to this slot; its next upload
-  // waits on `copied` before touching it.  okb_optimize* / okb_window_reset order themselves after all
-  // uploads issued before them (join_transfers).
   return OKB_OK;
+}
+
+extern "C" int okb_window_upload(okb_ctx* c, int win, const okb_window_desc* D) {
+  int rc = upload_pack(c, win, D);
+  if (rc) return rc;
+  return commit_range(c, win, 1);
 }
 
 extern "C" int okb_window_upload_batch(okb_ctx* c, int first, int count, const okb_window_desc* descs, int host_threads) {
@@ -470,14 +513,14 @@ extern "C" int okb_window_upload_batch(okb_ctx* c, int first, int count, const o
   T = std::max(1, std::min(T, count));
   std::vector<int> rcs(T, OKB_OK);
   if (T == 1) {
-    for (int i = 0; i < count && !rcs[0]; ++i) rcs[0] = upload_pack(c, first + i, descs + i, false);
+    for (int i = 0; i < count && !rcs[0]; ++i) rcs[0] = upload_pack(c, first + i, descs + i);
   } else {
     std::vector<std::thread> th;
     th.reserve(T);
     for (int t = 0; t < T; ++t)
       th.emplace_back([=, &rcs]() {
         for (int i = t; i < count; i += T) {
-          const int rc = upload_pack(c, first + i, descs + i, false);
+          const int rc = upload_pack(c, first + i, descs + i);
           if (rc) { rcs[t] = rc; return; }
         }
       });
@@ -485,8 +528,212 @@ extern "C" int okb_window_upload_batch(okb_ctx* c, int first, int count, const o
   }
   for (int t = 0; t < T; ++t)
     if (rcs[t]) return rcs[t];
+  return commit_range(c, first, count);
+}
+
+// ---------------------------------------------------------------------------------------------
+// incremental graph updates (Estimator::addStates / addLandmark / addObservation / removeObservation / set_*,
+// okvis_ceres/src/Estimator.cpp:110-413, implementation/Estimator.hpp:43-90): commands appended to the slot's
+// pending stream; nothing touches the device until okb_window_commit / okb_optimize*.
+// ---------------------------------------------------------------------------------------------
+static int delta_begin(okb_ctx* c, int win, size_t extra, WinStore** S, WinDev** W) {
+  if (!c || win < 0 || win >= c->max_windows) return OKB_ERR_INVALID_ARG;
+  if (!c->wins[win].uploaded) { c->set_error("window slot not uploaded"); return OKB_ERR_INVALID_ARG; }
   cudaSetDevice(c->device);
-  return upload_finish(c, first, count);      // one k_zero + one k_prepare for the whole range
+  *S = &c->wins[win];
+  *W = &c->host[win];
+  return cmd_reserve(c, **S, extra + sizeof(CmdHeader) + 64);
+}
+
+extern "C" int okb_window_add_frame(okb_ctx* c, int win, const double* pose, const double* speed_bias, const okb_imu_term* term,
+                                    const okb_imu_sample* samples, int n_samples) {
+  WinStore* S; WinDev* W;
+  if (!pose || (term && (!samples || n_samples < 2))) return OKB_ERR_INVALID_ARG;
+  int rc = delta_begin(c, win, 16 * 8 + sizeof(okb_imu_term) + sizeof(okb_imu_sample) * (size_t)std::max(n_samples, 0) + sizeof(CmdHeader), &S, &W);
+  if (rc) return rc;
+  const int K1 = W->K + 1, NSB1 = W->NSB + (speed_bias ? 1 : 0);
+  if (K1 > S->caps.K || NSB1 > S->caps.K || 6 * K1 + 9 * NSB1 > kMaxDense) { c->set_error("okb_window_add_frame: frame capacity exceeded (okb_window_reserve)"); return OKB_ERR_CAPACITY; }
+  if (smemA2_bytes(K1, 4 * ((6 * K1 + 1 + 3) / 4), 0) > (size_t)c->smem_optin) { c->set_error("window does not fit kernel A shared memory"); return OKB_ERR_CAPACITY; }
+  if (term) {
+    if ((int)term->pose0 >= K1 || (int)term->pose1 >= K1 || (int)term->sb0 >= NSB1 || (int)term->sb1 >= NSB1 ||
+        (uint64_t)term->sample_offset + term->sample_count > (uint64_t)n_samples || term->sample_count < 2) {
+      c->set_error("IMU term index out of range");
+      return OKB_ERR_INVALID_ARG;
+    }
+    if (W->n_imu + 1 > S->caps.T || W->n_samples + n_samples > S->caps.S) { c->set_error("okb_window_add_frame: IMU capacity exceeded (okb_window_reserve)"); return OKB_ERR_CAPACITY; }
+  }
+  if (c->shard_world > 1 && shard_box_doubles(K1, 4 * ((6 * K1 + 1 + 3) / 4)) > (size_t)c->shard_box_cap) { c->set_error("window exceeds the shard mailbox"); return OKB_ERR_CAPACITY; }
+  unsigned char* q = cmd_put(*S, CMD_ADD_FRAME, 0, 0, speed_bias ? 1u : 0u, 8 * 16);
+  std::memcpy(q, pose, 56);
+  if (speed_bias) std::memcpy(q + 56, speed_bias, 72); else std::memset(q + 56, 0, 72);
+  W->K = K1; W->NSB = NSB1;
+  if (term) {
+    q = cmd_put(*S, CMD_ADD_IMU_TERM, (uint32_t)n_samples, 0, 0, sizeof(okb_imu_term) + sizeof(okb_imu_sample) * (size_t)n_samples);
+    std::memcpy(q, term, sizeof(okb_imu_term));
+    std::memcpy(q + sizeof(okb_imu_term), samples, sizeof(okb_imu_sample) * (size_t)n_samples);
+    okb_imu_term mirror = *term;
+    mirror.sample_offset += (uint32_t)W->n_samples;
+    S->terms.push_back(mirror);
+    W->n_imu += 1; W->n_samples += n_samples;
+  }
+  derive_dims(*W);
+  return OKB_OK;
+}
+
+extern "C" int okb_window_remove_frame(okb_ctx* c, int win, uint32_t pose_idx, uint32_t sb_idx) {
+  WinStore* S; WinDev* W;
+  int rc = delta_begin(c, win, 0, &S, &W);
+  if (rc) return rc;
+  const bool has_sb = sb_idx != 0xffffffffu;
+  if ((int)pose_idx >= W->K || (has_sb && (int)sb_idx >= W->NSB) || W->K < 2) { c->set_error("okb_window_remove_frame: index out of range"); return OKB_ERR_INVALID_ARG; }
+  // the host mirror of the IMU term / prior counts needs the terms that touch the frame: it keeps a light copy
+  cmd_put(*S, CMD_REMOVE_FRAME, 0, pose_idx, sb_idx, 0);
+  int kept = 0, s_lo = 0x7fffffff, s_hi = 0;
+  for (auto& T : S->terms) {
+    const bool drop = T.pose0 == pose_idx || T.pose1 == pose_idx || (has_sb && (T.sb0 == sb_idx || T.sb1 == sb_idx));
+    if (drop) continue;
+    if (T.pose0 > pose_idx) T.pose0--;
+    if (T.pose1 > pose_idx) T.pose1--;
+    if (has_sb && T.sb0 > sb_idx) T.sb0--;
+    if (has_sb && T.sb1 > sb_idx) T.sb1--;
+    s_lo = std::min(s_lo, (int)T.sample_offset); s_hi = std::max(s_hi, (int)(T.sample_offset + T.sample_count));
+    S->terms[kept++] = T;
+  }
+  S->terms.resize(kept);
+  if (!kept) { s_lo = 0; s_hi = 0; }
+  for (auto& T : S->terms) T.sample_offset -= (uint32_t)s_lo;
+  W->n_imu = kept; W->n_samples = s_hi - s_lo;
+  auto drop_priors = [](std::vector<uint32_t>& v, uint32_t idx) {
+    size_t o = 0;
+    for (size_t i = 0; i < v.size(); ++i) { if (v[i] == idx) continue; v[o++] = v[i] > idx ? v[i] - 1 : v[i]; }
+    v.resize(o);
+  };
+  drop_priors(S->pp_idx, pose_idx);
+  if (has_sb) drop_priors(S->sbp_idx, sb_idx);
+  W->n_pp = (int)S->pp_idx.size(); W->n_sbp = (int)S->sbp_idx.size();
+  W->K -= 1;
+  if (has_sb) W->NSB -= 1;
+  derive_dims(*W);
+  return OKB_OK;
+}
+
+extern "C" int okb_window_set_landmarks(okb_ctx* c, int win, int n, const uint32_t* idx, const double* xyzw) {
+  WinStore* S; WinDev* W;
+  if (n < 1 || !idx || !xyzw) return OKB_ERR_INVALID_ARG;
+  int rc = delta_begin(c, win, align_up(4 * (size_t)n, 8) + 32 * (size_t)n, &S, &W);
+  if (rc) return rc;
+  int L = W->L;
+  for (int i = 0; i < n; ++i) {
+    if ((int)idx[i] >= S->caps.L) { c->set_error("okb_window_set_landmarks: landmark capacity exceeded (okb_window_reserve)"); return OKB_ERR_CAPACITY; }
+    L = std::max(L, (int)idx[i] + 1);
+  }
+  const size_t ib = align_up(4 * (size_t)n, 8);
+  unsigned char* q = cmd_put(*S, CMD_SET_LANDMARKS, (uint32_t)n, 0, 0, ib + 32 * (size_t)n);
+  std::memset(q, 0, ib);
+  std::memcpy(q, idx, 4 * (size_t)n);
+  std::memcpy(q + ib, xyzw, 32 * (size_t)n);
+  W->L = L;
+  derive_dims(*W);
+  return OKB_OK;
+}
+
+extern "C" int okb_window_remove_landmarks(okb_ctx* c, int win, int n, const uint32_t* idx) {
+  WinStore* S; WinDev* W;
+  if (n < 1 || !idx) return OKB_ERR_INVALID_ARG;
+  int rc = delta_begin(c, win, 4 * (size_t)n + 8, &S, &W);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i)
+    if ((int)idx[i] >= W->L) { c->set_error("okb_window_remove_landmarks: index out of range"); return OKB_ERR_INVALID_ARG; }
+  unsigned char* q = cmd_put(*S, CMD_REMOVE_LANDMARKS, (uint32_t)n, 0, 0, 4 * (size_t)n);
+  std::memcpy(q, idx, 4 * (size_t)n);
+  return OKB_OK;
+}
+
+extern "C" int okb_window_add_observations(okb_ctx* c, int win, int n, const okb_observation* obs) {
+  WinStore* S; WinDev* W;
+  if (n < 1 || !obs) return OKB_ERR_INVALID_ARG;
+  int rc = delta_begin(c, win, sizeof(okb_observation) * (size_t)n, &S, &W);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    const okb_observation& ob = obs[i];
+    if ((int)ob.pose_idx >= W->K || (int)ob.lm_idx >= W->L || (int)ob.ext_idx >= W->NE || (int)ob.cam_idx >= W->NC) { c->set_error("observation index out of range"); return OKB_ERR_INVALID_ARG; }
+    if (!(ob.sqrt_info > 0.0)) { c->set_error("observation with non-positive sqrt information"); return OKB_ERR_INVALID_ARG; }
+  }
+  if (S->obs_bound + n > S->caps.O) { c->set_error("okb_window_add_observations: observation capacity exceeded (okb_window_reserve)"); return OKB_ERR_CAPACITY; }
+  unsigned char* q = cmd_put(*S, CMD_ADD_OBS, (uint32_t)n, 0, 0, sizeof(okb_observation) * (size_t)n);
+  std::memcpy(q, obs, sizeof(okb_observation) * (size_t)n);
+  S->obs_bound += n;
+  return OKB_OK;
+}
+
+extern "C" int okb_window_remove_observations(okb_ctx* c, int win, int n, const okb_obs_key* keys) {
+  WinStore* S; WinDev* W;
+  if (n < 1 || !keys) return OKB_ERR_INVALID_ARG;
+  int rc = delta_begin(c, win, sizeof(okb_obs_key) * (size_t)n, &S, &W);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i)
+    if ((int)keys[i].pose_idx >= W->K || (int)keys[i].lm_idx >= W->L || (int)keys[i].cam_idx >= W->NC) { c->set_error("observation key out of range"); return OKB_ERR_INVALID_ARG; }
+  unsigned char* q = cmd_put(*S, CMD_REMOVE_OBS, (uint32_t)n, 0, 0, sizeof(okb_obs_key) * (size_t)n);
+  std::memcpy(q, keys, sizeof(okb_obs_key) * (size_t)n);
+  return OKB_OK;
+}
+
+extern "C" int okb_window_set_states(okb_ctx* c, int win, int n_poses, const uint32_t* pose_idx, const double* poses, int n_sb,
+                                     const uint32_t* sb_idx, const double* speed_bias) {
+  WinStore* S; WinDev* W;
+  if (n_poses < 0 || n_sb < 0 || (n_poses && (!pose_idx || !poses)) || (n_sb && (!sb_idx || !speed_bias))) return OKB_ERR_INVALID_ARG;
+  int rc = delta_begin(c, win, (sizeof(CmdHeader) + 72) * (size_t)(n_poses + n_sb), &S, &W);
+  if (rc) return rc;
+  for (int i = 0; i < n_poses; ++i) if ((int)pose_idx[i] >= W->K) { c->set_error("okb_window_set_states: pose index out of range"); return OKB_ERR_INVALID_ARG; }
+  for (int i = 0; i < n_sb; ++i) if ((int)sb_idx[i] >= W->NSB) { c->set_error("okb_window_set_states: speed/bias index out of range"); return OKB_ERR_INVALID_ARG; }
+  for (int i = 0; i < n_poses; ++i) std::memcpy(cmd_put(*S, CMD_SET_POSE, 0, pose_idx[i], 0, 56), poses + 7 * (size_t)i, 56);
+  for (int i = 0; i < n_sb; ++i) std::memcpy(cmd_put(*S, CMD_SET_SB, 0, sb_idx[i], 0, 72), speed_bias + 9 * (size_t)i, 72);
+  return OKB_OK;
+}
+
+extern "C" int okb_window_set_priors(okb_ctx* c, int win, int n_pose_priors, const okb_pose_prior* pose_priors, int n_sb_priors,
+                                     const okb_sb_prior* sb_priors, const okb_marg_prior* marg) {
+  WinStore* S; WinDev* W;
+  if (n_pose_priors < 0 || n_sb_priors < 0) return OKB_ERR_INVALID_ARG;
+  const int mn = marg ? marg->n : 0, mnb = marg ? marg->n_blocks : 0;
+  int rc = delta_begin(c, win, sizeof(okb_pose_prior) * (size_t)n_pose_priors + sizeof(okb_sb_prior) * (size_t)n_sb_priors + 3 * sizeof(CmdHeader) +
+                                   8 * ((size_t)mn * mn + mn + 11 * (size_t)mnb + 8), &S, &W);
+  if (rc) return rc;
+  if (n_pose_priors > S->caps.PP || n_sb_priors > S->caps.PP) { c->set_error("okb_window_set_priors: more priors than reserved"); return OKB_ERR_CAPACITY; }
+  for (int i = 0; i < n_pose_priors; ++i) if ((int)pose_priors[i].pose_idx >= W->K) { c->set_error("pose prior index out of range"); return OKB_ERR_INVALID_ARG; }
+  for (int i = 0; i < n_sb_priors; ++i) if ((int)sb_priors[i].sb_idx >= W->NSB) { c->set_error("speed/bias prior index out of range"); return OKB_ERR_INVALID_ARG; }
+  int xdim = 0;
+  if (marg) {
+    if (mn > S->caps.MN || mn > kMaxMarg || mnb > kMaxMargBlocks || mn < 0) { c->set_error("okb_window_set_priors: marginalisation prior larger than reserved"); return OKB_ERR_CAPACITY; }
+    int col = 0;
+    for (int b = 0; b < mnb; ++b) {
+      const int kind = marg->block_kind[b];
+      const int lim = kind == OKB_BLOCK_POSE ? W->K : kind == OKB_BLOCK_SPEED_BIAS ? W->NSB : kind == OKB_BLOCK_EXTRINSICS ? W->NE : -1;
+      if (lim < 0 || (int)marg->block_idx[b] >= lim) { c->set_error("marginalisation prior: bad block"); return OKB_ERR_INVALID_ARG; }
+      if (kind != OKB_BLOCK_EXTRINSICS) col += (kind == OKB_BLOCK_SPEED_BIAS) ? 9 : 6;
+      xdim += (kind == OKB_BLOCK_SPEED_BIAS) ? 9 : 7;
+    }
+    if (col != mn) { c->set_error("marginalisation prior dimension mismatch"); return OKB_ERR_INVALID_ARG; }
+  }
+  unsigned char* q = cmd_put(*S, CMD_SET_POSE_PRIORS, (uint32_t)n_pose_priors, 0, 0, sizeof(okb_pose_prior) * (size_t)n_pose_priors);
+  if (n_pose_priors) std::memcpy(q, pose_priors, sizeof(okb_pose_prior) * (size_t)n_pose_priors);
+  q = cmd_put(*S, CMD_SET_SB_PRIORS, (uint32_t)n_sb_priors, 0, 0, sizeof(okb_sb_prior) * (size_t)n_sb_priors);
+  if (n_sb_priors) std::memcpy(q, sb_priors, sizeof(okb_sb_prior) * (size_t)n_sb_priors);
+  S->pp_idx.clear(); S->sbp_idx.clear();
+  for (int i = 0; i < n_pose_priors; ++i) S->pp_idx.push_back(pose_priors[i].pose_idx);
+  for (int i = 0; i < n_sb_priors; ++i) S->sbp_idx.push_back(sb_priors[i].sb_idx);
+  W->n_pp = n_pose_priors; W->n_sbp = n_sb_priors;
+  if (marg) {
+    const size_t kb = align_up(4 * (size_t)mnb, 8);
+    q = cmd_put(*S, CMD_SET_MARG, 0, (uint32_t)mn, (uint32_t)mnb, 2 * kb + 8 * ((size_t)xdim + (size_t)mn * mn + mn));
+    std::memset(q, 0, 2 * kb);
+    if (mnb) { std::memcpy(q, marg->block_kind, 4 * (size_t)mnb); std::memcpy(q + kb, marg->block_idx, 4 * (size_t)mnb); }
+    double* x = reinterpret_cast<double*>(q + 2 * kb);
+    if (xdim) std::memcpy(x, marg->x0, 8 * (size_t)xdim);
+    if (mn) { std::memcpy(x + xdim, marg->J, 8 * (size_t)mn * mn); std::memcpy(x + xdim + (size_t)mn * mn, marg->e0, 8 * (size_t)mn); }
+    W->marg_n = mn; W->marg_nb = mnb; W->marg_xdim = xdim;
+  }
+  return OKB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -616,13 +863,20 @@ static int check_range(okb_ctx* c, int first, int count) {
 
 extern "C" int64_t okb_window_h2d_bytes(const okb_ctx* c, int win) {
   if (!c || win < 0 || win >= c->max_windows || !c->wins[win].uploaded) return 0;
-  return (int64_t)(c->wins[win].h2d_bytes + sizeof(WinDev));
+  return (int64_t)(c->wins[win].h2d_bytes + sizeof(WinDev));     // the last commit's command stream + the window descriptor
 }
 
 extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
   int rc = check_range(c, first, count);
   if (rc) return rc;
   cudaSetDevice(c->device);
+  for (int i = first; i < first + count; ++i) {
+    const WinStore& S = c->wins[i];
+    const WinDev& W = c->host[i];
+    if (W.K != S.K_init || W.NSB != S.NSB_init || W.L != S.L_init) { c->set_error("okb_window_reset: the window changed shape since its last full upload"); return OKB_ERR_INVALID_ARG; }
+  }
+  rc = commit_range(c, first, count);
+  if (rc) return rc;
   if (join_transfers(c)) { c->set_error("stream ordering failed"); return OKB_ERR_CUDA; }
   k_reset<<<count, 128, 0, c->stream>>>(c->d_wins, first, 1);
   c->launches += 1;
@@ -711,6 +965,8 @@ extern "C" int okb_optimize_async(okb_ctx* c, int first, int count, const okb_so
   if (rc) return rc;
   if (!opt || opt->max_iterations < 0) return OKB_ERR_INVALID_ARG;
   cudaSetDevice(c->device);
+  rc = commit_range(c, first, count);       // pending graph commands of these slots (no-op when there are none)
+  if (rc) return rc;
   // chunking: enough CTAs for ~2 waves when the batch is small
   for (int i = first; i < first + count; ++i) {
     WinDev& W = c->host[i];
@@ -754,6 +1010,12 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
     OKB_CUDA(c, cudaMemcpyAsync(c->h_states + first, c->d_states + first, sizeof(SolverState) * count, cudaMemcpyDeviceToHost, c->stream));
     mark_work(c, first, count);
   }
+  for (int i = first; i < first + count; ++i) {
+    const SolverState& s = c->h_states[i];
+    if (s.g.err) { c->set_error(graph_error_text(s.g.err)); return graph_error_status(s.g.err); }
+    WinStore& S = c->wins[i];
+    if (!S.cmd_used) S.obs_bound = s.g.n_obs;      // exact length of the compacted observation list
+  }
   if (out) {
     for (int i = 0; i < count; ++i) {
       const SolverState& s = c->h_states[first + i];
@@ -779,28 +1041,31 @@ extern "C" int okb_optimize(okb_ctx* c, int first, int count, const okb_solve_op
   return okb_optimize_finish(c, first, count, out);
 }
 
+// The estimates come back from the packed output block (pose | speed/bias | landmarks | quality, caller's order) that
+// k_quality / k_prepare / k_reset keep current: one D2H copy per window, plain memcpy on the host.
+static size_t out_doubles(const WinDev& W) { return 7 * (size_t)W.K + 9 * (size_t)W.NSB + 5 * (size_t)W.L; }
+static void copy_out_window(const WinDev& W, const WinStore& S, double* poses, double* speed_bias, double* landmarks, double* quality) {
+  const double* o = reinterpret_cast<const double*>(S.out_staging);
+  if (poses) std::memcpy(poses, o, sizeof(double) * 7 * W.K);
+  if (speed_bias && W.NSB) std::memcpy(speed_bias, o + 7 * W.K, sizeof(double) * 9 * W.NSB);
+  if (landmarks) std::memcpy(landmarks, o + 7 * W.K + 9 * W.NSB, sizeof(double) * 4 * (size_t)W.L);
+  if (quality) std::memcpy(quality, o + 7 * W.K + 9 * W.NSB + 4 * (size_t)W.L, sizeof(double) * (size_t)W.L);
+}
+
 extern "C" int okb_window_download(okb_ctx* c, int win, double* poses, double* speed_bias, double* landmarks, double* quality) {
   int rc = check_range(c, win, 1);
   if (rc) return rc;
   cudaSetDevice(c->device);
+  rc = commit_range(c, win, 1);
+  if (rc) return rc;
   const WinDev& W = c->host[win];
   WinStore& S = c->wins[win];
-  if (!S.uploaded) { c->set_error("window not uploaded"); return OKB_ERR_INVALID_ARG; }
-  // Estimates live contiguously in the arena ([poses | speed/bias | extrinsics | landmarks]); they and the
-  // quality vector are copied into the slot's pinned buffer on the transfer stream, after the solver work
-  // last launched on this slot.
   cudaStream_t xs = c->stream_xfer;
   if (S.done_idx >= 0) OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
-  const unsigned char* base = reinterpret_cast<const unsigned char*>(W.pose);
-  const size_t span = (reinterpret_cast<const unsigned char*>(W.lm) - base) + sizeof(double) * 4 * W.L;
-  OKB_CUDA(c, cudaMemcpyAsync(S.out_staging, base, span, cudaMemcpyDeviceToHost, xs));
-  if (quality) OKB_CUDA(c, cudaMemcpyAsync(S.out_staging + span, W.quality, sizeof(double) * W.L, cudaMemcpyDeviceToHost, xs));
+  OKB_CUDA(c, cudaMemcpyAsync(S.out_staging, W.out, sizeof(double) * out_doubles(W), cudaMemcpyDeviceToHost, xs));
   OKB_CUDA(c, cudaEventRecord(S.down, xs));
   OKB_CUDA(c, cudaEventSynchronize(S.down));
-  if (poses) std::memcpy(poses, S.out_staging, sizeof(double) * 7 * W.K);
-  if (speed_bias && W.NSB) std::memcpy(speed_bias, S.out_staging + (reinterpret_cast<const unsigned char*>(W.sb) - base), sizeof(double) * 9 * W.NSB);
-  unpermute_landmarks(S, W.L, reinterpret_cast<const double*>(S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base)),
-                      reinterpret_cast<const double*>(S.out_staging + span), landmarks, quality);
+  copy_out_window(W, S, poses, speed_bias, landmarks, quality);
   return OKB_OK;
 }
 
@@ -809,44 +1074,28 @@ extern "C" int okb_window_download_batch(okb_ctx* c, int first, int count, doubl
   int rc = check_range(c, first, count);
   if (rc) return rc;
   cudaSetDevice(c->device);
+  rc = commit_range(c, first, count);
+  if (rc) return rc;
   cudaStream_t xs = c->stream_xfer;
   bool waited[okb_ctx::kDoneRing] = {};
   for (int i = first; i < first + count; ++i) {
     WinStore& S = c->wins[i];
-    if (!S.uploaded) { c->set_error("window not uploaded"); return OKB_ERR_INVALID_ARG; }
     if (S.done_idx >= 0 && !waited[S.done_idx]) {
       OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
       waited[S.done_idx] = true;
     }
   }
-  for (int i = first; i < first + count; ++i) {
-    const WinDev& W = c->host[i];
-    WinStore& S = c->wins[i];
-    const unsigned char* base = reinterpret_cast<const unsigned char*>(W.pose);
-    const size_t span = (reinterpret_cast<const unsigned char*>(W.lm) - base) + sizeof(double) * 4 * W.L;
-    OKB_CUDA(c, cudaMemcpyAsync(S.out_staging, base, span, cudaMemcpyDeviceToHost, xs));
-    if (quality && quality[i - first])
-      OKB_CUDA(c, cudaMemcpyAsync(S.out_staging + span, W.quality, sizeof(double) * W.L, cudaMemcpyDeviceToHost, xs));
-  }
+  for (int i = first; i < first + count; ++i)
+    OKB_CUDA(c, cudaMemcpyAsync(c->wins[i].out_staging, c->host[i].out, sizeof(double) * out_doubles(c->host[i]), cudaMemcpyDeviceToHost, xs));
   WinStore& S0 = c->wins[first];
   OKB_CUDA(c, cudaEventRecord(S0.down, xs));
   OKB_CUDA(c, cudaEventSynchronize(S0.down));
-  // pinned staging -> caller's buffers (landmarks / qualities scattered back to the caller's order); a few host
-  // threads share the slots of a large batch
   auto copy_out = [&](int i) {
-    const WinDev& W = c->host[i];
-    const WinStore& S = c->wins[i];
     const int k = i - first;
-    const unsigned char* base = reinterpret_cast<const unsigned char*>(W.pose);
-    const size_t span = (reinterpret_cast<const unsigned char*>(W.lm) - base) + sizeof(double) * 4 * W.L;
-    if (poses && poses[k]) std::memcpy(poses[k], S.out_staging, sizeof(double) * 7 * W.K);
-    if (speed_bias && speed_bias[k] && W.NSB)
-      std::memcpy(speed_bias[k], S.out_staging + (reinterpret_cast<const unsigned char*>(W.sb) - base), sizeof(double) * 9 * W.NSB);
-    unpermute_landmarks(S, W.L, reinterpret_cast<const double*>(S.out_staging + (reinterpret_cast<const unsigned char*>(W.lm) - base)),
-                        reinterpret_cast<const double*>(S.out_staging + span), landmarks ? landmarks[k] : nullptr,
-                        quality ? quality[k] : nullptr);
+    copy_out_window(c->host[i], c->wins[i], poses ? poses[k] : nullptr, speed_bias ? speed_bias[k] : nullptr,
+                    landmarks ? landmarks[k] : nullptr, quality ? quality[k] : nullptr);
   };
-  const int T = std::max(1, std::min(8, count / 16));
+  const int T = std::max(1, std::min(8, count / 32));
   if (T == 1) {
     for (int i = first; i < first + count; ++i) copy_out(i);
   } else {

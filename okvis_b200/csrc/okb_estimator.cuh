@@ -13,6 +13,7 @@ constexpr int kMaxFrames = 32;        // frame visibility mask is one u32
 constexpr int kMaxChunks = 64;        // landmark chunks (CTAs) per window in kernel A
 constexpr int kMaxDense = 512;        // reduced-system dimension limit
 constexpr int kMaxMarg = 160;         // marginalisation prior dimension limit
+constexpr int kMaxMargBlocks = 64;    // parameter blocks connected to the marginalisation prior
 constexpr int kMaxShard = 8;          // ranks of a landmark-sharded window (one NVSwitch domain)
 
 // Ceres 1.9 defaults used by Estimator::optimize
@@ -32,6 +33,10 @@ constexpr int kMaxConsecutiveInvalid = 5;
 enum Mode { MODE_INIT = 0, MODE_STEP = 1, MODE_REBUILD = 2 };
 
 struct SlotInfo { int pose_idx, ext_idx, cam_idx, valid; };
+
+// Dimensions of the device-resident window graph as the command interpreter left them (okb_graph.cuh); the host
+// mirrors the same arithmetic, k_compile_obs cross-checks.  err: first GERR_* raised by a command or by the compile.
+struct GraphState { int K, NSB, L, n_obs, n_imu, n_samples, n_pp, n_sbp, marg_n, marg_nb, marg_xdim, NE, NC, err; };
 
 // Per-window solver state (device resident, one per window; also read back as the summary).
 struct SolverState {
@@ -60,6 +65,7 @@ struct SolverState {
   unsigned long long shard_epoch;
   unsigned long long shard_wait_ns, shard_rounds;
   int shard_fault;     // 1 = a peer did not arrive within the time-out (the window terminates with FAILURE)
+  GraphState g;
 };
 
 // ---- landmark-sharded single window: per-window mailbox in every rank's device memory.
@@ -87,6 +93,22 @@ __host__ __device__ inline size_t lm_mf_index(int l, int f, int K) { return ((si
 struct SlotCtx;   // per (frame, camera) transform + intrinsics at the candidate state (okb_kernels_lm.cuh)
 
 struct WinDev {
+  // capacities the arena was planned for (okb_window_reserve / the largest upload); the current dimensions below
+  // change with the graph commands
+  int Kcap, Lcap, Ocap, Scap, Tcap, NEcap, NCcap, PPcap;
+  // master graph in the caller's index space (okb_graph.cuh); pose / sb / ext below are master and working copy at once
+  double* m_lm;                                // [Lcap][4] landmark estimates, caller's order (written back after every optimize)
+  double* m_lm_init;                           // [Lcap][4] as of the last full upload (okb_window_reset)
+  unsigned char* m_mark;                       // [Lcap] scratch marks of the command interpreter (all zero between commands)
+  okb_observation* m_obs;                      // [Ocap] observation list; sqrt_info == 0: removed, compacted by k_compile_obs
+  uint32_t* m_vis;                             // [Lcap] frame-visibility masks, caller's order (compile scratch)
+  uint32_t* m_bitmap;                          // one bit per observation-grid cell (duplicate detection)
+  uint32_t* perm;                              // [Lcap] internal (sorted) landmark index -> caller's index
+  double* out;                                 // packed estimates for the download: pose [K][7] | sb [NSB][9] | landmarks [L][4] | quality [L]
+  const unsigned char* cmd;                    // command buffer of the pending commit
+  int cmd_bytes;
+  int dirty;                                   // 1 = the graph changed: compile before the next optimize
+  int full;                                    // 1 = the pending commit is a full upload: snapshot the initial state
   int K, NSB, NE, L, NC;
   int Lp;              // L rounded up to whole tiles of 32: leading dimension of lm_M / lm_mf, rows of lm_Li / lm_c (bulk copies stay aligned)
   int CP;              // cameras per frame padded to a power of two
@@ -100,7 +122,7 @@ struct WinDev {
   int use_cauchy;
   // state
   double *pose, *sb, *ext, *lm;                // committed  [K][7] [NSB][9] [NE][7] [L][4]
-  double *pose_init, *sb_init, *lm_init;       // as uploaded (okb_window_reset)
+  double *pose_init, *sb_init;                 // as of the last full upload (okb_window_reset); landmarks: m_lm_init
   double *pose_c, *sb_c, *lm_c;                // candidate
   // graph
   SlotInfo* slots;                             // [NSP]
@@ -108,15 +130,14 @@ struct WinDev {
   double2* obs_z;                              // [NS][L]  slot-major: coalesced for thread-per-landmark kernels
   double* obs_w;                               // [NS][L] sqrt information, 0 = no observation
   uint32_t* lm_vis;                            // [L] bit f set = observed in frame f
-  const okb_observation* obs_list;             // [n_obs] as uploaded; k_prepare scatters it into the grid
-  int n_obs;
+  int n_obs;                                   // host's upper bound of the list length (launch sizing); exact: st->g.n_obs
   // Landmarks are stored sorted by (first, last) observing frame (okb_window_upload): tracks are runs of
   // consecutive frames, so neighbouring landmarks see nearly the same frames -> warp-coherent visibility
   // in k_linearize and block-sparse Schur tiles in k_schur.
-  unsigned char* zero_ptr;                     // region cleared by k_zero at upload
-  size_t zero_bytes;
-  const uint32_t* lm_inv;                      // [L] caller's landmark index -> internal (sorted) index
-  const uint32_t* tile_range;                  // [ceil(L/32)] frames seen by the tile: first | last << 8 (first > last: none)
+  unsigned char* zero_ptr[3];                  // regions cleared by k_zero at every compile: observation grid (z, w), M blocks
+  size_t zero_bytes[3];
+  uint32_t* lm_inv;                            // [L] caller's landmark index -> internal (sorted) index
+  uint32_t* tile_range;                  // [ceil(L/32)] frames seen by the tile: first | last << 8 (first > last: none)
   // per-landmark solver data
   double* lm_g[2];                             // [L][3] gradient block (double buffered: cur / speculative)
   double* lm_E[2];                             // [L][3] metric (Ceres diagonal^2 / scale^2)
@@ -143,8 +164,7 @@ struct WinDev {
   okb_imu_term* imu_terms;
   okb_imu_sample* samples;
   okb_imu_params imu_params;
-  ImuCache* imu_cache;
-  ImuCache* imu_cache_init;
+  ImuCache* imu_cache;                         // all zero (valid = 0) after an upload / okb_window_reset
   double* imu_out;                             // [n_imu][kImuOut] written by k_imu, consumed by k_solve
   int *sb_off;                                 // unused placeholder for alignment
   // priors

@@ -782,46 +782,61 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
 #undef PHASE_MARK
 }
 
-// resets the solver state (and optionally the parameter state) of a range of windows
-// Upload epilogue on the transfer stream, batched over windows (blockIdx.y): k_zero clears each window's
-// zero region (observation grid, M blocks, caches, quality); k_prepare then scatters the compact
-// observation list into the slot-major grid and keeps the uploaded state for okb_window_reset.
+// Compile epilogue on the transfer stream, batched over windows (blockIdx.y), for windows whose graph changed
+// (W.dirty): k_zero clears the observation grid and the M blocks; k_prepare scatters the compacted observation
+// list (k_compile_obs) into the slot-major grid through the landmark permutation (k_compile_sort), refreshes the packed
+// output block and, after a full upload, keeps the initial state for okb_window_reset.
 __global__ void __launch_bounds__(256) k_zero(const WinDev* __restrict__ wins, int win_first) {
   const WinDev& W = wins[win_first + blockIdx.y];
-  uint4* p = reinterpret_cast<uint4*>(W.zero_ptr);
-  const size_t n = W.zero_bytes / sizeof(uint4);          // regions are 256-byte multiples
+  if (!W.dirty) return;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    uint4* p = reinterpret_cast<uint4*>(W.zero_ptr[r]);
+    const size_t n = W.zero_bytes[r] / sizeof(uint4);         // regions are 256-byte multiples
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = z;
+  }
 }
+// packed estimates for the download: pose [K][7] | sb [NSB][9] | landmarks [L][4] | quality [L] (caller's order)
+__device__ __forceinline__ double* out_lm(const WinDev& W) { return W.out + 7 * W.K + 9 * W.NSB; }
+__device__ __forceinline__ double* out_quality(const WinDev& W) { return W.out + 7 * W.K + 9 * W.NSB + 4 * (size_t)W.L; }
+
 __global__ void __launch_bounds__(256) k_prepare(const WinDev* __restrict__ wins, int win_first) {
   const WinDev& W = wins[win_first + blockIdx.y];
-  const int work = max(max(W.n_obs, 4 * W.L), max(7 * W.K, 9 * W.NSB));
+  if (!W.dirty) return;
+  const int n_obs = W.st->g.n_obs;
+  const int work = max(max(n_obs, 4 * W.L), max(7 * W.K, 9 * W.NSB));
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < work; i += gridDim.x * blockDim.x) {
-    if (i < W.n_obs) {
-      const okb_observation ob = W.obs_list[i];
+    if (i < n_obs) {
+      const okb_observation ob = W.m_obs[i];
       const size_t g = (size_t)((int)ob.pose_idx * W.CP + (int)ob.cam_idx) * W.L + W.lm_inv[ob.lm_idx];
       W.obs_z[g] = make_double2(ob.z[0], ob.z[1]);
       W.obs_w[g] = ob.sqrt_info;
     }
-    if (i < 7 * W.K) W.pose_init[i] = W.pose[i];
-    if (i < 9 * W.NSB) W.sb_init[i] = W.sb[i];
-    if (i < 4 * W.L) W.lm_init[i] = W.lm[i];
+    if (i < 7 * W.K) { W.out[i] = W.pose[i]; if (W.full) W.pose_init[i] = W.pose[i]; }
+    if (i < 9 * W.NSB) { W.out[7 * W.K + i] = W.sb[i]; if (W.full) W.sb_init[i] = W.sb[i]; }
+    if (i < 4 * W.L) { out_lm(W)[i] = W.m_lm[i]; if (W.full) W.m_lm_init[i] = W.m_lm[i]; }
+    if (i < W.L) out_quality(W)[i] = 0.0;
   }
 }
 
+// resets the solver state (and optionally the parameter state: the one of the last full upload) of a range of windows
 __global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int restore_params) {
   const WinDev& W = wins[win_first + blockIdx.x];
   const int tid = threadIdx.x;
   if (restore_params) {
-    for (int i = tid; i < 7 * W.K; i += blockDim.x) W.pose[i] = W.pose_init[i];
-    for (int i = tid; i < 9 * W.NSB; i += blockDim.x) W.sb[i] = W.sb_init[i];
-    for (int i = tid; i < 4 * W.L; i += blockDim.x) W.lm[i] = W.lm_init[i];
-    const int nb = (int)(sizeof(ImuCache) / sizeof(double));
-    for (int t = 0; t < W.n_imu; ++t) {
-      double* dst = reinterpret_cast<double*>(W.imu_cache + t);
-      const double* src = reinterpret_cast<const double*>(W.imu_cache_init + t);
-      for (int i = tid; i < nb; i += blockDim.x) dst[i] = src[i];
+    for (int i = tid; i < 7 * W.K; i += blockDim.x) { W.pose[i] = W.pose_init[i]; W.out[i] = W.pose_init[i]; }
+    for (int i = tid; i < 9 * W.NSB; i += blockDim.x) { W.sb[i] = W.sb_init[i]; W.out[7 * W.K + i] = W.sb_init[i]; }
+    for (int j = tid; j < W.L; j += blockDim.x) {
+      const uint32_t l = W.perm[j];
+      const double4 x = *reinterpret_cast<const double4*>(W.m_lm_init + 4 * (size_t)l);
+      *reinterpret_cast<double4*>(W.m_lm + 4 * (size_t)l) = x;
+      *reinterpret_cast<double4*>(W.lm + 4 * (size_t)j) = x;
+      *reinterpret_cast<double4*>(out_lm(W) + 4 * (size_t)l) = x;
+      out_quality(W)[l] = 0.0;
     }
+    const int nb = (int)(sizeof(ImuCache) / sizeof(double));
+    for (int i = tid; i < nb * W.n_imu; i += blockDim.x) reinterpret_cast<double*>(W.imu_cache)[i] = 0.0;   // valid = 0, as uploaded
   }
   __syncthreads();
   for (int i = tid; i < 7 * W.K; i += blockDim.x) W.pose_c[i] = W.pose[i];
@@ -832,6 +847,7 @@ __global__ void k_reset(const WinDev* __restrict__ wins, int win_first, int rest
     SolverState* st = W.st;
     st->mode = MODE_INIT; st->done = 0; st->cur = 0;
     st->iteration = 0; st->num_successful = 0; st->num_invalid = 0; st->termination = OKB_TERM_NO_CONVERGENCE;
+    if (st->g.err) { st->done = 1; st->termination = OKB_TERM_FAILURE; }    // a rejected graph is never solved
     st->reuse = 0; st->numeric_fail = 0;
     st->radius = kInitialRadius; st->mu = kMinMu; st->mu_spec = kMinMu;
     st->cost = 0; st->initial_cost = 0; st->x_norm2 = 0;

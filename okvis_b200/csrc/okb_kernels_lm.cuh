@@ -722,7 +722,18 @@ __global__ void __launch_bounds__(128) k_quality(const WinDev* __restrict__ wins
     }
     double ev[3];
     eig3sym_closed(H, ev);
-    W.quality[l] = (ev[0] < 1.0e-12) ? 0.0 : sqrt(ev[0]) / sqrt(ev[2]);
+    const double q = (ev[0] < 1.0e-12) ? 0.0 : sqrt(ev[0]) / sqrt(ev[2]);
+    W.quality[l] = q;
+    // write-back in the caller's order: the master copy (next compile) and the packed download block
+    const uint32_t lc = W.perm[l];
+    *reinterpret_cast<double4*>(W.m_lm + 4 * (size_t)lc) = x4;
+    double* o = W.out + 7 * W.K + 9 * W.NSB;
+    *reinterpret_cast<double4*>(o + 4 * (size_t)lc) = x4;
+    o[4 * (size_t)L + lc] = q;
+  }
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < 7 * W.K; i += blockDim.x) W.out[i] = W.pose[i];
+    for (int i = tid; i < 9 * W.NSB; i += blockDim.x) W.out[7 * W.K + i] = W.sb[i];
   }
 }
 

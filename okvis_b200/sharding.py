@@ -63,3 +63,13 @@ def merge_shard_results(n_landmarks, parts):
         if d.get("quality") is not None:
             out["quality"][idx] = d["quality"]
     return out
+
+
+def connect_shards(ctx, dist, device, rank, world, max_frames):
+    """Multi-process mailbox set-up of a landmark-sharded context: export this rank's cudaIpc handle, all-gather the
+    handles with torch.distributed (64 bytes per rank; plumbing only), map the peers."""
+    import torch
+    handle = torch.from_numpy(ctx.shard_export(rank, world, max_frames)).to(device)
+    gathered = [torch.zeros_like(handle) for _ in range(world)]
+    dist.all_gather(gathered, handle)
+    ctx.shard_connect(np.stack([g.cpu().numpy() for g in gathered]))

@@ -13,13 +13,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def connect_shards(ctx, dist, torch, rank, world, local_rank, max_frames):
-    handle = torch.from_numpy(ctx.shard_export(rank, world, max_frames)).to("cuda:%d" % local_rank)
-    gathered = [torch.zeros_like(handle) for _ in range(world)]
-    dist.all_gather(gathered, handle)
-    ctx.shard_connect(np.stack([g.cpu().numpy() for g in gathered]))
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=5)
@@ -38,7 +31,7 @@ def main():
         cfg = dataclasses.replace(cfg, n_landmarks=a.landmarks)
     w = synthetic.make_window(a.config, 0, cfg=cfg)
     ctx = capi.Context(local_rank, 1)
-    connect_shards(ctx, dist, torch, rank, world, local_rank, len(w.poses))
+    sharding.connect_shards(ctx, dist, torch.device('cuda', local_rank), rank, world, len(w.poses))
     sw, idx = sharding.shard_window(w, rank, world)
     ctx.upload(0, sw)
     dist.barrier()
