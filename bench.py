@@ -203,6 +203,60 @@ def frontend_leg(ctx, cam):
             "note": "host buffers in/out, host clock; sequential DenseMatcher semantics (assignbest on the device)"}
 
 
+def pin_to_gpu_numa(gpu_index):
+    """Pins this process (and the host threads it starts later) to the CPUs of the NUMA node the GPU hangs off, so that
+    the command packing and the pinned staging buffers of a rank stay local to its GPU.  Returns the node or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        dom, rest = bus.split(":", 1)
+        node = int(open("/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:], rest)).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
+def latency_leg(torch, dev, local_rank, window, reps=20):
+    """B = 1 latency: ONE resident cfg-2 window, reset + optimize(10) + quality pass, CUDA events on the
+    library stream, plus the host wall time of the blocking okb_optimize call (launch + sync + summary read-back)."""
+    from okvis_b200 import capi
+    c1 = capi.Context(local_rank, 1)
+    try:
+        c1.upload(0, window)
+        stream = torch.cuda.ExternalStream(c1.stream, device=dev)
+        dev_ms, wall_ms, iters = [], [], 0
+        for rep in range(reps + 3):
+            c1.reset(0, 1)
+            torch.cuda.synchronize(dev)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            with torch.cuda.stream(stream):
+                ev0.record(stream)
+                c1.optimize_async(0, 1, max_iterations=ITERS)
+                ev1.record(stream)
+            s = c1.optimize_finish(0, 1)[0]
+            t1 = time.perf_counter()
+            torch.cuda.synchronize(dev)
+            if rep >= 3:
+                dev_ms.append(ev0.elapsed_time(ev1))
+                wall_ms.append((t1 - t0) * 1e3)
+                iters = s["iterations"]
+        return {"latency_b1_ms": float(np.median(dev_ms)), "latency_b1_wall_ms": float(np.median(wall_ms)),
+                "latency_b1_min_ms": float(min(dev_ms)), "iterations": int(iters), "reps": reps,
+                "what": "one resident cfg-2 window: optimize(%d) + landmark-quality pass, device time (CUDA events) and host wall time of the blocking call" % ITERS}
+    finally:
+        c1.close()
+
+
 def cfg5_leg(torch, dist, dev, rank, world, local_rank, reps=5):
     """BASELINE.json configs[4]: ONE 20-keyframe / 4-camera / 8000-landmark window, landmarks sharded lm_idx % world over
     the ranks, partial reduced systems all-reduced through NVLink peer-memory mailboxes inside the solver kernels
@@ -271,8 +325,10 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = pin_to_gpu_numa(local_rank)
     B = args.batch
-    ctx = capi.Context(local_rank, B)
+    Be = max(1, min(B, args.e2e_batch))                 # windows per slot range of the e2e leg (two ranges alternate)
+    ctx = capi.Context(local_rank, max(B, 2 * Be))
     # independent windows: global window w runs on rank w mod world, no data-path collective
     from okvis_b200 import sharding, synthetic
     windows = [synthetic.make_window(2, w) for w in sharding.shard_indices(world * args.distinct, world, rank)]
@@ -311,24 +367,33 @@ def run_b200(args):
     launches = ctx.kernel_launches - launches0
     clocks = sampler.result() if rank == 0 else None
 
-    # ---- e2e through the C-ABI with HOST buffers: every step uploads its windows (host -> device), optimizes
-    # and downloads the estimates (device -> host).  Two window ranges are used alternately so that the host
-    # packing / copies of step i+1 overlap the device work of step i (what a streaming caller does); uploads
-    # and downloads of different windows run on a few host threads (the C calls release the GIL).
-    Be = min(B // 2, args.e2e_batch)
+    # ---- e2e through the C-ABI with HOST buffers, resident windows: the windows live on the device; every
+    # step the host restores a slot to its uploaded estimates (okb_window_reset, device side), drops the newest frame
+    # and adds it again -- pose, speed/bias, the ImuError term with its samples and that frame's observations, i.e. what
+    # Estimator::addStates + addObservation send per camera frame -- then optimizes and downloads ALL estimates
+    # (poses, speed/bias, landmarks, quality).  Each step therefore solves the same graph as the resident leg from the
+    # same initial estimates.  Two slot ranges alternate so that the host-side command packing, the H2D copy, the
+    # device-side graph compile and the D2H copy of one range overlap the solve of the other (transfer stream).
     e2e_steps = max(2, args.steps)
     range_windows = [windows[i % len(windows)] for i in range(Be)]
     descs = ctx.make_descs(range_windows)              # descriptors only point at the host arrays
     for base in (0, Be):
+        for i, w_ in enumerate(range_windows):
+            ctx.reserve(base + i, len(w_.poses), len(w_.landmarks), len(w_.obs) + 4096, len(w_.imu_samples) + 256)
         ctx.upload_batch(base, range_windows, args.host_threads, descs)
+    full_upload_bytes = sum(ctx.h2d_bytes(i) for i in range(Be))
     host_out = {base: ctx.alloc_outputs(base, Be) for base in (0, Be)}   # host result buffers, reused every step
-
-    h2d_range = sum(ctx.h2d_bytes(i) for i in range(Be))                # counted by the library per upload
+    prepared = {base: [ctx.prepare_readd_newest(base + i, w_) for i, w_ in enumerate(range_windows)] for base in (0, Be)}
     d2h_range = sum(v.nbytes for o in host_out[0][0] for v in o.values()) + Be * 48   # estimates + summaries
+    h2d_seen = []
 
     def upload_range(base):
-        ctx.upload_batch(base, range_windows, args.host_threads, descs)
-        return h2d_range
+        ctx.reset(base, Be)                 # device side: estimates as uploaded (no host traffic)
+        ctx.readd_newest(prepared[base])    # host side: command appends into the pinned per-slot buffers
+        ctx.commit(base, Be)                # one H2D copy per slot + device-side interpreter / compile
+        if not h2d_seen:
+            h2d_seen.append(sum(ctx.h2d_bytes(base + i) for i in range(Be)))   # counted by the library per commit
+        return h2d_seen[0]
 
     def download_range(base):
         ctx.download_batch(base, Be, host_out[base])
@@ -336,7 +401,7 @@ def run_b200(args):
 
     def e2e_run(n_steps):
         # software pipeline over two window ranges: while the device optimizes range `cur`, the host downloads
-        # the estimates of the previous step and uploads the next step's windows (transfer stream)
+        # the estimates of the previous step and sends the next step's frame (transfer stream)
         it = 0
         h2d = d2h = 0
         h2d += upload_range(0)
@@ -369,6 +434,12 @@ def run_b200(args):
     except Exception as e:
         cfg5_res = {"error": repr(e)}
 
+    lat = None
+    if rank == 0:
+        try:
+            lat = latency_leg(torch, dev, local_rank, windows[0])
+        except Exception as e:
+            lat = {"error": repr(e)}
     if rank == 0:
         peak, peak_kind = load_peaks()
         w = windows[0]
@@ -413,7 +484,9 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (%.0f MB resident per GPU)" % (B * 3.0)},
             "e2e": {"value": e_iters_all / (e2e_ms * 1e-3), "unit": "iterations/s", "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(d2h) * world, "windows_per_gpu": Be, "steps": e2e_steps,
-                    "note": "upload+optimize+download per step; step i+1 uploads overlap step i compute; %d host threads" % args.host_threads},
+                    "full_window_upload_bytes": int(full_upload_bytes) * world,
+                    "note": "resident windows: per step reset (device) + re-add of the newest frame with its IMU term and observations (H2D) "
+                            "+ optimize(10) + download of all estimates (D2H); two slot ranges alternate so transfers overlap the solve"},
             "gpu_launches": launches_all,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_linearize + k_lmblock + k_schur (residuals, Jacobian factors, J^T J, Schur complement)",
@@ -425,6 +498,8 @@ def run_b200(args):
                          "k_solve_avg_launch_ms": sv_ms, "k_solve_share": prof["solve_ms"] / max(total_k, 1e-9)},
             "cpu_baseline": {"value": cpu_iters / cpu_dt, "unit": "iterations/s", "cores": cores, "kind": "port",
                              "sample": "%d windows x optimize(%d) + quality pass, one oracle thread per window, %d threads" % (n_cpu, ITERS, cores)},
+            "latency": lat,
+            "host": {"numa_node": numa_node, "usable_cpus": host_cpus()},
             "frontend": frontend,
             "cfg5_sharded_window": cfg5,
         }
@@ -441,7 +516,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=592, help="resident windows per GPU (4 per SM)")
-    ap.add_argument("--e2e-batch", type=int, default=296)
+    ap.add_argument("--e2e-batch", type=int, default=592, help="windows per step of the e2e leg (two slot ranges of this size alternate)")
     ap.add_argument("--skip-cpu", action="store_true", help="tuning runs only: shrink the cpu_baseline sample to one window")
     ap.add_argument("--host-threads", type=int, default=12, help="host threads packing/uploading windows in the e2e leg")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic windows per rank (replicated to fill the batch)")

@@ -159,6 +159,29 @@ class Context:
     def commit(self, first=0, count=1):
         self._check(lib().okb_window_commit(self._h, int(first), int(count)))
 
+    def prepare_readd_newest(self, win, w):
+        """Pre-marshalled arguments of the streaming pattern `drop the newest frame, add it again with its IMU term and
+        observations` (what a VIO host does once per camera frame: Estimator::addStates + addObservation of that frame,
+        okvis_ceres/src/Estimator.cpp:110-343, implementation/Estimator.hpp:43-90) for slot `win` holding window `w`."""
+        K = len(w.poses)
+        t = w.imu_terms[K - 2:K - 1].copy()
+        lo, n = int(t["sample_offset"][0]), int(t["sample_count"][0])
+        t["sample_offset"] = 0
+        smp = np.ascontiguousarray(w.imu_samples[lo:lo + n])
+        obs = np.ascontiguousarray(w.obs[w.obs["pose_idx"] == K - 1])
+        pose, sb = _f64(w.poses[K - 1]).copy(), _f64(w.speed_bias[K - 1]).copy()
+        keep = (pose, sb, t, smp, obs)
+        return (C.c_int(int(win)), C.c_uint32(K - 1), _p(pose), _p(sb), _p(t), _p(smp), C.c_int(n), C.c_int(len(obs)), _p(obs), keep)
+
+    def readd_newest(self, prepared):
+        """Issues remove_frame / add_frame / add_observations for every prepared slot (host-side command appends only)."""
+        L_, h = lib(), self._h
+        rm, af, ao = L_.okb_window_remove_frame, L_.okb_window_add_frame, L_.okb_window_add_observations
+        for win, last, pose, sb, t, smp, n, n_obs, obs, _ in prepared:
+            rc = rm(h, win, last, last) or af(h, win, pose, sb, t, smp, n) or ao(h, win, n_obs, obs)
+            if rc:
+                self._check(rc)
+
     def debug_phase_us(self, win):
         out = np.zeros(16)
         self._check(lib().okb_debug_phase_ns(self._h, int(win), _p(out)))

@@ -877,11 +877,21 @@ extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
   }
   rc = commit_range(c, first, count);
   if (rc) return rc;
-  if (join_transfers(c)) { c->set_error("stream ordering failed"); return OKB_ERR_CUDA; }
-  k_reset<<<count, 128, 0, c->stream>>>(c->d_wins, first, 1);
+  // Runs on the TRANSFER stream (after the solver work already launched on these slots): restoring a slot is part of
+  // preparing it, so it overlaps a solve that is running on other slots; the next okb_optimize* of the slot joins the
+  // transfer stream as it does for uploads.
+  cudaStream_t xs = c->stream_xfer;
+  bool waited[okb_ctx::kDoneRing] = {};
+  for (int i = first; i < first + count; ++i) {
+    const WinStore& S = c->wins[i];
+    if (S.done_idx >= 0 && !waited[S.done_idx]) {
+      OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
+      waited[S.done_idx] = true;
+    }
+  }
+  k_reset<<<count, 128, 0, xs>>>(c->d_wins, first, 1);
   c->launches += 1;
   OKB_CUDA(c, cudaGetLastError());
-  mark_work(c, first, count);
   return OKB_OK;
 }
 
