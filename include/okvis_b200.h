@@ -18,6 +18,8 @@
  *   okb_eval_speed_bias_error <- SpeedAndBiasError::EvaluateWithMinimalJacobians okvis_ceres/src/SpeedAndBiasError.cpp:89-116
  *   okb_eval_relative_pose    <- RelativePoseError::EvaluateWithMinimalJacobians okvis_ceres/src/RelativePoseError.cpp:84-162
  *   okb_eval_marginalization  <- MarginalizationError::EvaluateWithMinimalJacobians okvis_ceres/src/MarginalizationError.cpp:893-946
+ *   okb_window_marginalize    <- MarginalizationError::addResidualBlock / marginalizeOut / updateErrorComputation
+ *                                okvis_ceres/src/MarginalizationError.cpp:127-435, 507-846 (driven by Estimator.cpp:434-773)
  *   okb_hamming_match         <- okvis::DenseMatcher::match            okvis_matcher/include/okvis/implementation/DenseMatcher.hpp:48-225
  *                                + assignbest                          okvis_matcher/src/DenseMatcher.cpp:69-110
  *   okb_hamming_candidates    <- VioKeyframeWindowMatchingAlgorithm::specificDescriptorDistance
@@ -256,6 +258,44 @@ int okb_window_set_priors(okb_ctx* ctx, int win, int n_pose_priors, const okb_po
  * work on other slots).  Optional: the calls that need the result do it themselves. */
 int okb_window_commit(okb_ctx* ctx, int win_first, int count);
 
+/* Removes speed/bias block sb_idx together with the ImuError terms and SpeedAndBiasError priors attached to it; the
+ * pose of that frame stays (the "removeAllButPose" frames of Estimator::applyMarginalizationStrategy,
+ * Estimator.cpp:483-554).  Later speed/bias blocks move down one position. */
+int okb_window_remove_speed_bias(okb_ctx* ctx, int win, uint32_t sb_idx);
+
+/* ---- device-side marginalisation -----------------------------------------------------------------------------
+ * The numeric half of Estimator::applyMarginalizationStrategy (okvis_ceres/src/Estimator.cpp:434-773):
+ * MarginalizationError::addResidualBlock (okvis_ceres/src/MarginalizationError.cpp:127-435) for the listed residual
+ * blocks -- evaluated at the first-estimate linearisation points, reprojection errors with the Cauchy correction --
+ * marginalizeOut (:507-802) of the marked blocks and of the listed landmarks, and updateErrorComputation (:806-846).
+ * The window's marginalisation prior is replaced on the device by the result (kept blocks in job order; their
+ * linearisation points are kept when block_prev >= 0, else the current estimates become x0).  The bookkeeping half
+ * stays with the caller, exactly like the reference: after this call it removes the linearised terms / blocks with
+ * okb_window_remove_frame / okb_window_remove_speed_bias / okb_window_remove_landmarks and re-fixes the first pose
+ * with okb_window_set_priors (Estimator.cpp:761-770).  H and b0 persist on the device between calls as the
+ * reference's H_ / b0_ members do (a prior supplied by the host through okb_window_upload / okb_window_set_priors
+ * starts from H = J^T J, b0 = -J^T e0).  Errors found by the device (a residual whose parameter blocks are not all
+ * listed, inconsistent block_prev) surface at the next okb_optimize* / okb_window_download_marg. */
+typedef struct okb_marg_job {
+  int32_t n_blocks;                 /* dense parameter blocks of the linear system, in H order (<= 64) */
+  int32_t n_imu_terms, n_sb_priors, n_landmarks;
+  const int32_t* block_kind;        /* [n_blocks] OKB_BLOCK_POSE / OKB_BLOCK_SPEED_BIAS */
+  const uint32_t* block_idx;        /* [n_blocks] position in the window NOW */
+  const int32_t* block_prev;        /* [n_blocks] position in the current prior's block list, -1 = newly connected; every
+                                       block of the current prior must appear exactly once */
+  const uint8_t* block_marginalize; /* [n_blocks] 1 = marginalise this block out */
+  const uint32_t* imu_terms;        /* ImuError terms to linearise (positions in the window's term list) */
+  const uint32_t* sb_priors;        /* SpeedAndBiasError terms to linearise */
+  const uint32_t* landmarks;        /* landmarks to marginalise: every observation they still have is linearised */
+} okb_marg_job;
+int okb_window_marginalize(okb_ctx* ctx, int win, const okb_marg_job* job);
+/* Reads the window's current marginalisation prior back (tests, host-side persistence): J [n][n], e0 [n], the
+ * H / b0 it was factored from, block list, linearisation points.  Any pointer may be NULL; arrays must hold the
+ * compiled-in maxima (n <= 160, 64 blocks).  status[4] = {device error code of the last okb_window_marginalize,
+ * rank of H, rank of the dense marginalised block, Jacobi sweeps}. */
+int okb_window_download_marg(okb_ctx* ctx, int win, int32_t* n, int32_t* n_blocks, int32_t* block_kind, uint32_t* block_idx,
+                             double* x0, double* J, double* e0, double* H, double* b0, int32_t* status);
+
 /* Bytes the last commit (full upload or incremental commands) of this slot copied host -> device (0 if the slot is empty). */
 int64_t okb_window_h2d_bytes(const okb_ctx* ctx, int win);
 /* Restores the state of the last FULL upload of the slot on the device (no host traffic); used to repeat a solve
@@ -311,6 +351,9 @@ int okb_profile_read(okb_ctx* ctx, double out[6]);
 /* Diagnostics: nanoseconds the reduced-solve kernel spent per internal phase during the last optimize of
  * `win` (dense terms, partial gather, assembly, Cholesky, substitution, back-substitution, dogleg). */
 int okb_debug_phase_ns(okb_ctx* ctx, int win, double out[16]);
+/* Diagnostics: the mutable preintegration cache of ImuError term `term` (ImuError.hpp:251-276): the bias the
+ * preintegration was done at, whether it is valid (0 = redo_), and how often it was redone. */
+int okb_debug_imu_cache(okb_ctx* ctx, int win, int term, double sb_ref[9], int32_t* valid, int32_t* redo_count);
 
 /* ------------------------------------------------- single-block test hooks
  * Mirror ErrorInterface::EvaluateWithMinimalJacobians (okvis_ceres/include/okvis/ceres/ErrorInterface.hpp:93-95).

@@ -41,6 +41,32 @@ class MargPrior(C.Structure):
                 ("block_idx", C.POINTER(C.c_uint32)), ("x0", c_double_p), ("J", c_double_p), ("e0", c_double_p)]
 
 
+class MargJob(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("n_imu_terms", C.c_int32), ("n_sb_priors", C.c_int32), ("n_landmarks", C.c_int32),
+                ("block_kind", C.POINTER(C.c_int32)), ("block_idx", C.POINTER(C.c_uint32)), ("block_prev", C.POINTER(C.c_int32)),
+                ("block_marginalize", C.POINTER(C.c_uint8)), ("imu_terms", C.POINTER(C.c_uint32)),
+                ("sb_priors", C.POINTER(C.c_uint32)), ("landmarks", C.POINTER(C.c_uint32))]
+
+
+def make_marg_job(block_kind, block_idx, block_prev, block_marginalize, imu_terms=(), sb_priors=(), landmarks=()):
+    """okb_marg_job over numpy arrays (kept alive on the returned object)."""
+    a = [np.ascontiguousarray(block_kind, np.int32), np.ascontiguousarray(block_idx, np.uint32),
+         np.ascontiguousarray(block_prev, np.int32), np.ascontiguousarray(block_marginalize, np.uint8),
+         np.ascontiguousarray(imu_terms, np.uint32), np.ascontiguousarray(sb_priors, np.uint32),
+         np.ascontiguousarray(landmarks, np.uint32)]
+    j = MargJob()
+    j.n_blocks, j.n_imu_terms, j.n_sb_priors, j.n_landmarks = len(a[0]), len(a[4]), len(a[5]), len(a[6])
+    j.block_kind = a[0].ctypes.data_as(C.POINTER(C.c_int32))
+    j.block_idx = a[1].ctypes.data_as(C.POINTER(C.c_uint32))
+    j.block_prev = a[2].ctypes.data_as(C.POINTER(C.c_int32))
+    j.block_marginalize = a[3].ctypes.data_as(C.POINTER(C.c_uint8))
+    j.imu_terms = a[4].ctypes.data_as(C.POINTER(C.c_uint32))
+    j.sb_priors = a[5].ctypes.data_as(C.POINTER(C.c_uint32))
+    j.landmarks = a[6].ctypes.data_as(C.POINTER(C.c_uint32))
+    j._keep = a
+    return j
+
+
 class WindowDesc(C.Structure):
     _fields_ = [("n_poses", C.c_int32), ("n_speed_bias", C.c_int32), ("n_extrinsics", C.c_int32),
                 ("n_landmarks", C.c_int32), ("n_cameras", C.c_int32), ("n_obs", C.c_int32),

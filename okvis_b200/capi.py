@@ -156,6 +156,26 @@ class Context:
         self._check(lib().okb_window_set_priors(self._h, int(win), len(pp), _p(pp) if len(pp) else None, len(sp),
                                                 _p(sp) if len(sp) else None, C.byref(m) if m is not None else None))
 
+    def remove_speed_bias(self, win, sb_idx):
+        self._check(lib().okb_window_remove_speed_bias(self._h, int(win), C.c_uint32(int(sb_idx))))
+
+    def marginalize(self, win, job):
+        """okb_window_marginalize; job from abi.make_marg_job."""
+        self._check(lib().okb_window_marginalize(self._h, int(win), C.byref(job)))
+
+    def download_marg(self, win):
+        n, nb = C.c_int32(0), C.c_int32(0)
+        kind, idx = np.zeros(64, np.int32), np.zeros(64, np.uint32)
+        x0, J, e0, H, b0 = np.zeros(9 * 64), np.zeros(160 * 160), np.zeros(160), np.zeros(160 * 160), np.zeros(160)
+        st = np.zeros(4, np.int32)
+        self._check(lib().okb_window_download_marg(self._h, int(win), C.byref(n), C.byref(nb), _p(kind), _p(idx), _p(x0), _p(J),
+                                                   _p(e0), _p(H), _p(b0), _p(st)))
+        n, nb = n.value, nb.value
+        kind, idx = kind[:nb].copy(), idx[:nb].copy()
+        xdim = int(sum(9 if k == abi.BLOCK_SPEED_BIAS else 7 for k in kind))
+        return dict(n=n, block_kind=kind, block_idx=idx, x0=x0[:xdim].copy(), J=J[:n * n].reshape(n, n).copy(), e0=e0[:n].copy(),
+                    H=H[:n * n].reshape(n, n).copy(), b0=b0[:n].copy(), status=st.copy())
+
     def commit(self, first=0, count=1):
         self._check(lib().okb_window_commit(self._h, int(first), int(count)))
 
@@ -188,6 +208,12 @@ class Context:
         names = ["dense_terms", "gather", "assemble", "cholesky", "substitution", "backsub", "dogleg", "_",
                  "p8", "p9", "p10", "p11", "p12", "p13", "p14", "p15"]   # OKB_SCHUR_PROF / OKB_CHOL_PROF builds: cycles
         return {n: v * 1e-3 for n, v in zip(names, out)}
+
+    def debug_imu_cache(self, win, term):
+        ref = np.zeros(9)
+        v, r = C.c_int32(0), C.c_int32(0)
+        self._check(lib().okb_debug_imu_cache(self._h, int(win), int(term), _p(ref), C.byref(v), C.byref(r)))
+        return ref, v.value, r.value
 
     def h2d_bytes(self, win):
         f = lib().okb_window_h2d_bytes

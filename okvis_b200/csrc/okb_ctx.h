@@ -36,6 +36,9 @@ struct WinStore {
   cudaEvent_t down = nullptr;         // recorded after the D2H copies of a download
   okb_solve_options opt{};            // options of the last okb_optimize_async on this slot
   int done_idx = -1;                  // index into okb_ctx::done_ring of the last solver work launched on this slot
+  unsigned char* marg_scratch = nullptr;   // device scratch of okb_window_marginalize (okb_marg.cuh), allocated on first use
+  size_t marg_scratch_bytes = 0;
+  int marg_lm_cap = 0, marg_K_cap = 0, marg_L_cap = 0, marg_O_cap = 0;
 };
 
 struct okb_frontend_state;

@@ -13,6 +13,7 @@
 #include "okb_hostpack.hpp"
 #include "okb_graph.cuh"
 #include "okb_kernels.cuh"
+#include "okb_marg.cuh"
 
 using namespace okb;
 
@@ -101,6 +102,7 @@ extern "C" void okb_ctx_destroy(okb_ctx* c) {
   if (c->stream_xfer) cudaStreamSynchronize(c->stream_xfer);
   for (auto& w : c->wins) {
     if (w.arena) cudaFree(w.arena);
+    if (w.marg_scratch) cudaFree(w.marg_scratch);
     if (w.staging) cudaFreeHost(w.staging);
     if (w.out_staging) cudaFreeHost(w.out_staging);
     if (w.copied) cudaEventDestroy(w.copied);
@@ -195,12 +197,13 @@ int plan_arena(okb_ctx* c, int win, const WinCaps& q) {
   const int dcc = 6 * Kc, dcap = 15 * Kc, dcpc = 4 * ((dcc + 1 + 3) / 4);
   const int MN = std::max(q.MN, 1), MB = kMaxMargBlocks;
   const size_t o_pose = P.take(8 * 7 * Kc), o_sb = P.take(8 * 9 * Kc), o_ext = P.take(8 * 7 * q.NE), o_mlm = P.take(8 * 4 * (size_t)Lpc);
-  const size_t o_out = P.take(8 * (16 * (size_t)Kc + 5 * (size_t)Lc));
+  const size_t o_out = P.take(8 * (16 * (size_t)Kc + 4 + 5 * (size_t)Lc));
   const size_t o_cams = P.take(sizeof(okb_camera) * q.NC), o_obs = P.take(sizeof(okb_observation) * (size_t)std::max(q.O, 1));
   const size_t o_imut = P.take(sizeof(okb_imu_term) * std::max(q.T, 1)), o_samp = P.take(sizeof(okb_imu_sample) * (size_t)std::max(q.S, 1));
   const size_t o_pp = P.take(sizeof(okb_pose_prior) * std::max(q.PP, 1)), o_sbp = P.take(sizeof(okb_sb_prior) * std::max(q.PP, 1));
   const size_t o_mkind = P.take(4 * MB), o_midx = P.take(4 * MB), o_mcol = P.take(4 * MB), o_moff = P.take(4 * MB);
   const size_t o_mx0 = P.take(8 * 9 * MB), o_mJ = P.take(8 * (size_t)MN * MN), o_me0 = P.take(8 * MN), o_mH0 = P.take(8 * (size_t)MN * MN);
+  const size_t o_mHs = P.take(8 * (size_t)MN * MN), o_mb0 = P.take(8 * MN);
   const size_t o_mlmi = P.take(8 * 4 * (size_t)Lpc), o_mark = P.take(Lpc), o_mvis = P.take(4 * (size_t)Lpc);
   const size_t o_bitmap = P.take(4 * (((size_t)NSc * Lc + 31) / 32 + 1));
   const size_t o_perm = P.take(4 * (size_t)Lpc), o_inv = P.take(4 * (size_t)Lpc), o_trange = P.take(4 * (size_t)(Lpc / 32 + 1)), o_vis = P.take(4 * (size_t)Lpc);
@@ -229,7 +232,7 @@ int plan_arena(okb_ctx* c, int win, const WinCaps& q) {
     OKB_CUDA(c, cudaMalloc(&S.arena, P.total));
     S.arena_bytes = P.total;
   }
-  const size_t out_bytes = 8 * (16 * (size_t)Kc + 5 * (size_t)Lc);
+  const size_t out_bytes = 8 * (16 * (size_t)Kc + 4 + 5 * (size_t)Lc);
   if (S.out_bytes < out_bytes) {
     if (S.out_staging) cudaFreeHost(S.out_staging);
     S.out_staging = nullptr; S.out_bytes = 0;
@@ -259,7 +262,7 @@ int plan_arena(okb_ctx* c, int win, const WinCaps& q) {
   W.sbp = reinterpret_cast<okb_sb_prior*>(A + o_sbp);
   W.marg_kind = reinterpret_cast<int32_t*>(A + o_mkind); W.marg_idx = up(o_midx);
   W.marg_col = reinterpret_cast<int32_t*>(A + o_mcol); W.marg_off = reinterpret_cast<int32_t*>(A + o_moff);
-  W.marg_x0 = dp(o_mx0); W.marg_J = dp(o_mJ); W.marg_e0 = dp(o_me0); W.marg_H0 = dp(o_mH0);
+  W.marg_x0 = dp(o_mx0); W.marg_J = dp(o_mJ); W.marg_e0 = dp(o_me0); W.marg_H0 = dp(o_mH0); W.marg_Hs = dp(o_mHs); W.marg_b0 = dp(o_mb0);
   W.m_lm_init = dp(o_mlmi); W.m_mark = A + o_mark; W.m_vis = up(o_mvis); W.m_bitmap = up(o_bitmap);
   W.perm = up(o_perm); W.lm_inv = up(o_inv); W.tile_range = up(o_trange); W.lm_vis = up(o_vis);
   W.slots = reinterpret_cast<SlotInfo*>(A + o_slots);
@@ -736,6 +739,178 @@ extern "C" int okb_window_set_priors(okb_ctx* c, int win, int n_pose_priors, con
   return OKB_OK;
 }
 
+extern "C" int okb_window_remove_speed_bias(okb_ctx* c, int win, uint32_t sb_idx) {
+  WinStore* S; WinDev* W;
+  int rc = delta_begin(c, win, 0, &S, &W);
+  if (rc) return rc;
+  if ((int)sb_idx >= W->NSB) { c->set_error("okb_window_remove_speed_bias: index out of range"); return OKB_ERR_INVALID_ARG; }
+  cmd_put(*S, CMD_REMOVE_SB, 0, sb_idx, 0, 0);
+  int kept = 0, s_lo = 0x7fffffff, s_hi = 0;
+  for (auto& T : S->terms) {
+    if (T.sb0 == sb_idx || T.sb1 == sb_idx) continue;
+    if (T.sb0 > sb_idx) T.sb0--;
+    if (T.sb1 > sb_idx) T.sb1--;
+    s_lo = std::min(s_lo, (int)T.sample_offset); s_hi = std::max(s_hi, (int)(T.sample_offset + T.sample_count));
+    S->terms[kept++] = T;
+  }
+  S->terms.resize(kept);
+  if (!kept) { s_lo = 0; s_hi = 0; }
+  for (auto& T : S->terms) T.sample_offset -= (uint32_t)s_lo;
+  W->n_imu = kept; W->n_samples = s_hi - s_lo;
+  size_t o = 0;
+  for (size_t i = 0; i < S->sbp_idx.size(); ++i) { if (S->sbp_idx[i] == sb_idx) continue; S->sbp_idx[o++] = S->sbp_idx[i] > sb_idx ? S->sbp_idx[i] - 1 : S->sbp_idx[i]; }
+  S->sbp_idx.resize(o);
+  W->n_sbp = (int)o;
+  W->NSB -= 1;
+  derive_dims(*W);
+  return OKB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side marginalisation (okb_marg.cuh): MarginalizationError::addResidualBlock / marginalizeOut /
+// updateErrorComputation (okvis_ceres/src/MarginalizationError.cpp:127-435, 507-846)
+// ---------------------------------------------------------------------------------------------
+static int hook_alloc_fwd(okb_ctx* c, size_t bytes);
+static int check_range(okb_ctx* c, int first, int count);
+namespace {
+constexpr int kMargImuCap = 32, kMargSbpCap = 8;
+struct MargLayout { size_t kind, idx, prev, marg, imu, sbp, lms, payload_end, H, b, A, Q, T, Hn, bn, xlin, lmrec, lmV, lmvis, lmslot, clist, status, total; };
+MargLayout marg_layout(int lm_cap, int K_cap, int L_cap, int O_cap) {
+  MargLayout m;
+  size_t o = sizeof(MargJobHeader);
+  auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + bytes, 16); return r; };
+  m.kind = take(4 * kMaxMargBlocks); m.idx = take(4 * kMaxMargBlocks); m.prev = take(4 * kMaxMargBlocks); m.marg = take(kMaxMargBlocks);
+  m.imu = take(4 * kMargImuCap); m.sbp = take(4 * kMargSbpCap); m.lms = take(4 * (size_t)lm_cap);
+  m.payload_end = o;
+  const size_t NN = (size_t)kMargWork * kMargWork * 8;
+  m.H = take(NN); m.b = take(8 * kMargWork); m.A = take(NN); m.Q = take(NN); m.T = take(NN); m.Hn = take(NN); m.bn = take(8 * kMargWork);
+  m.xlin = take(8 * 9 * kMaxMargBlocks);
+  m.lmrec = take(8 * (size_t)lm_cap * K_cap * kMargRec); m.lmV = take(8 * 16 * (size_t)lm_cap); m.lmvis = take(4 * (size_t)lm_cap);
+  m.lmslot = take(4 * (size_t)std::max(L_cap, 1)); m.clist = take(4 * (size_t)std::max(O_cap, 1)); m.status = take(16);
+  m.total = o;
+  return m;
+}
+MargScratch marg_pointers(unsigned char* base, const MargLayout& m) {
+  MargScratch sc;
+  sc.hdr = reinterpret_cast<MargJobHeader*>(base);
+  sc.kind = reinterpret_cast<int32_t*>(base + m.kind); sc.idx = reinterpret_cast<uint32_t*>(base + m.idx);
+  sc.prev = reinterpret_cast<int32_t*>(base + m.prev); sc.marg = base + m.marg;
+  sc.imu_terms = reinterpret_cast<uint32_t*>(base + m.imu); sc.sb_priors = reinterpret_cast<uint32_t*>(base + m.sbp);
+  sc.landmarks = reinterpret_cast<uint32_t*>(base + m.lms);
+  auto dp = [&](size_t o) { return reinterpret_cast<double*>(base + o); };
+  sc.H = dp(m.H); sc.b = dp(m.b); sc.A = dp(m.A); sc.Q = dp(m.Q); sc.T = dp(m.T); sc.Hn = dp(m.Hn); sc.bn = dp(m.bn); sc.xlin = dp(m.xlin);
+  sc.lmrec = dp(m.lmrec); sc.lmV = dp(m.lmV); sc.lmvis = reinterpret_cast<uint32_t*>(base + m.lmvis);
+  sc.lmslot = reinterpret_cast<int32_t*>(base + m.lmslot); sc.clist = reinterpret_cast<int32_t*>(base + m.clist);
+  sc.status = reinterpret_cast<int32_t*>(base + m.status);
+  return sc;
+}
+}  // namespace
+
+extern "C" int okb_window_marginalize(okb_ctx* c, int win, const okb_marg_job* job) {
+  if (!c || !job || win < 0 || win >= c->max_windows) return OKB_ERR_INVALID_ARG;
+  if (!c->wins[win].uploaded) { c->set_error("window slot not uploaded"); return OKB_ERR_INVALID_ARG; }
+  cudaSetDevice(c->device);
+  int rc = commit_range(c, win, 1);            // pending graph edits first: the job indexes the window as it is now
+  if (rc) return rc;
+  WinStore& S = c->wins[win];
+  WinDev& W = c->host[win];
+  if (job->n_blocks < 1 || job->n_blocks > kMaxMargBlocks || job->n_imu_terms < 0 || job->n_imu_terms > kMargImuCap || job->n_sb_priors < 0 ||
+      job->n_sb_priors > kMargSbpCap || job->n_landmarks < 0 || !job->block_kind || !job->block_idx || !job->block_prev || !job->block_marginalize) {
+    c->set_error("okb_window_marginalize: malformed job");
+    return OKB_ERR_INVALID_ARG;
+  }
+  int N = 0, n_keep = 0, nb_keep = 0, xdim = 0;
+  for (int b = 0; b < job->n_blocks; ++b) {
+    const int kind = job->block_kind[b];
+    if (kind != OKB_BLOCK_POSE && kind != OKB_BLOCK_SPEED_BIAS) { c->set_error("okb_window_marginalize: block kind must be pose or speed/bias (extrinsics are fixed)"); return OKB_ERR_UNSUPPORTED; }
+    const int lim = kind == OKB_BLOCK_POSE ? W.K : W.NSB;
+    if ((int)job->block_idx[b] >= lim || job->block_prev[b] < -1 || job->block_prev[b] >= W.marg_nb) { c->set_error("okb_window_marginalize: block index out of range"); return OKB_ERR_INVALID_ARG; }
+    const int dim = kind == OKB_BLOCK_SPEED_BIAS ? 9 : 6;
+    N += dim;
+    if (!job->block_marginalize[b]) { n_keep += dim; nb_keep += 1; xdim += (kind == OKB_BLOCK_SPEED_BIAS) ? 9 : 7; }
+  }
+  for (int i = 0; i < job->n_imu_terms; ++i) if ((int)job->imu_terms[i] >= W.n_imu) { c->set_error("okb_window_marginalize: IMU term index out of range"); return OKB_ERR_INVALID_ARG; }
+  for (int i = 0; i < job->n_sb_priors; ++i) if ((int)job->sb_priors[i] >= W.n_sbp) { c->set_error("okb_window_marginalize: prior index out of range"); return OKB_ERR_INVALID_ARG; }
+  for (int i = 0; i < job->n_landmarks; ++i) if ((int)job->landmarks[i] >= W.L) { c->set_error("okb_window_marginalize: landmark index out of range"); return OKB_ERR_INVALID_ARG; }
+  if (N > kMargWork) { c->set_error("okb_window_marginalize: linear system larger than the compiled-in limit"); return OKB_ERR_CAPACITY; }
+  if (n_keep > kMaxMarg || n_keep > S.caps.MN) { c->set_error("okb_window_marginalize: resulting prior larger than reserved (okb_window_reserve max_marg_dim)"); return OKB_ERR_CAPACITY; }
+  // scratch
+  if (!S.marg_scratch || S.marg_lm_cap < job->n_landmarks || S.marg_K_cap < S.caps.K || S.marg_L_cap < S.caps.L || S.marg_O_cap < S.caps.O) {
+    if (S.marg_scratch) { OKB_CUDA(c, cudaStreamSynchronize(c->stream_xfer)); cudaFree(S.marg_scratch); S.marg_scratch = nullptr; }
+    S.marg_lm_cap = std::max(256, 2 * job->n_landmarks); S.marg_K_cap = S.caps.K; S.marg_L_cap = S.caps.L; S.marg_O_cap = S.caps.O;
+    const MargLayout m = marg_layout(S.marg_lm_cap, S.marg_K_cap, S.marg_L_cap, S.marg_O_cap);
+    OKB_CUDA(c, cudaMalloc(&S.marg_scratch, m.total));
+    S.marg_scratch_bytes = m.total;
+    OKB_CUDA(c, cudaMemsetAsync(S.marg_scratch, 0, m.total, c->stream_xfer));
+  }
+  const MargLayout m = marg_layout(S.marg_lm_cap, S.marg_K_cap, S.marg_L_cap, S.marg_O_cap);
+  rc = cmd_reserve(c, S, m.payload_end);
+  if (rc) return rc;
+  unsigned char* q = S.staging;
+  std::memset(q, 0, m.payload_end);
+  MargJobHeader h{job->n_blocks, job->n_imu_terms, job->n_sb_priors, job->n_landmarks, N, n_keep, S.marg_lm_cap, 0};
+  std::memcpy(q, &h, sizeof h);
+  std::memcpy(q + m.kind, job->block_kind, 4 * (size_t)job->n_blocks);
+  std::memcpy(q + m.idx, job->block_idx, 4 * (size_t)job->n_blocks);
+  std::memcpy(q + m.prev, job->block_prev, 4 * (size_t)job->n_blocks);
+  std::memcpy(q + m.marg, job->block_marginalize, (size_t)job->n_blocks);
+  if (job->n_imu_terms) std::memcpy(q + m.imu, job->imu_terms, 4 * (size_t)job->n_imu_terms);
+  if (job->n_sb_priors) std::memcpy(q + m.sbp, job->sb_priors, 4 * (size_t)job->n_sb_priors);
+  if (job->n_landmarks) std::memcpy(q + m.lms, job->landmarks, 4 * (size_t)job->n_landmarks);
+  cudaStream_t xs = c->stream_xfer;
+  if (S.done_idx >= 0) OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
+  OKB_CUDA(c, cudaMemcpyAsync(S.marg_scratch, q, m.payload_end, cudaMemcpyHostToDevice, xs));
+  OKB_CUDA(c, cudaEventRecord(S.copied, xs));
+  S.staging_busy = true;
+  OKB_CUDA(c, cudaMemsetAsync(S.marg_scratch + m.status, 0, 16, xs));
+  OKB_CUDA(c, cudaMemcpyAsync(c->d_wins + win, &W, sizeof(WinDev), cudaMemcpyHostToDevice, xs));
+  k_marginalize<<<1, M_THREADS, 0, xs>>>(c->d_wins, win, marg_pointers(S.marg_scratch, m));
+  c->launches += 1;
+  OKB_CUDA(c, cudaGetLastError());
+  W.marg_n = n_keep; W.marg_nb = nb_keep; W.marg_xdim = xdim;
+  return OKB_OK;
+}
+
+extern "C" int okb_window_download_marg(okb_ctx* c, int win, int32_t* n, int32_t* n_blocks, int32_t* block_kind, uint32_t* block_idx, double* x0,
+                                        double* J, double* e0, double* H, double* b0, int32_t* status) {
+  int rc = check_range(c, win, 1);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  rc = commit_range(c, win, 1);
+  if (rc) return rc;
+  const int cap = 8 + 2 * kMaxMargBlocks + 9 * kMaxMargBlocks + 2 * kMaxMarg * kMaxMarg + 2 * kMaxMarg;
+  rc = hook_alloc_fwd(c, sizeof(double) * cap);
+  if (rc) return rc;
+  WinStore& S = c->wins[win];
+  cudaStream_t xs = c->stream_xfer;
+  if (S.done_idx >= 0) OKB_CUDA(c, cudaStreamWaitEvent(xs, c->done_ring[S.done_idx], 0));
+  k_marg_export<<<1, 256, 0, xs>>>(c->d_wins, win, reinterpret_cast<double*>(c->hook_buf), cap);
+  c->launches += 1;
+  std::vector<double> host(cap);
+  OKB_CUDA(c, cudaMemcpyAsync(host.data(), c->hook_buf, sizeof(double) * cap, cudaMemcpyDeviceToHost, xs));
+  int32_t st[4] = {0, 0, 0, 0};
+  if (S.marg_scratch) {
+    const MargLayout m = marg_layout(S.marg_lm_cap, S.marg_K_cap, S.marg_L_cap, S.marg_O_cap);
+    OKB_CUDA(c, cudaMemcpyAsync(st, S.marg_scratch + m.status, 16, cudaMemcpyDeviceToHost, xs));
+  }
+  OKB_CUDA(c, cudaStreamSynchronize(xs));
+  const int nn = (int)host[0], nb = (int)host[1], xd = (int)host[2];
+  if (n) *n = nn;
+  if (n_blocks) *n_blocks = nb;
+  if (status) std::memcpy(status, st, 16);
+  if ((int)host[3] > cap) { c->set_error("okb_window_download_marg: prior larger than the export buffer"); return OKB_ERR_CAPACITY; }
+  const double* o = host.data() + 8;
+  for (int i = 0; i < nb; ++i) { if (block_kind) block_kind[i] = (int32_t)o[i]; if (block_idx) block_idx[i] = (uint32_t)o[nb + i]; }
+  o += 2 * nb;
+  if (x0) std::memcpy(x0, o, sizeof(double) * xd);
+  o += xd;
+  if (J) std::memcpy(J, o, sizeof(double) * (size_t)nn * nn);
+  if (e0) std::memcpy(e0, o + (size_t)nn * nn, sizeof(double) * nn);
+  if (H) std::memcpy(H, o + (size_t)nn * nn + nn, sizeof(double) * (size_t)nn * nn);
+  if (b0) std::memcpy(b0, o + 2 * (size_t)nn * nn + nn, sizeof(double) * nn);
+  return OKB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // landmark-sharded single window: mailbox set-up
 // ---------------------------------------------------------------------------------------------
@@ -1038,6 +1213,25 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
   return OKB_OK;
 }
 
+// diagnostics: the ImuError cache of term `term` (reference bias of the preintegration, valid flag, redo counter)
+extern "C" int okb_debug_imu_cache(okb_ctx* c, int win, int term, double sb_ref[9], int32_t* valid, int32_t* redo_count) {
+  int rc = check_range(c, win, 1);
+  if (rc) return rc;
+  cudaSetDevice(c->device);
+  rc = commit_range(c, win, 1);
+  if (rc) return rc;
+  const WinDev& W = c->host[win];
+  if (term < 0 || term >= W.n_imu) return OKB_ERR_INVALID_ARG;
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream));
+  OKB_CUDA(c, cudaStreamSynchronize(c->stream_xfer));
+  ImuCache h;
+  OKB_CUDA(c, cudaMemcpy(&h, W.imu_cache + term, sizeof(ImuCache), cudaMemcpyDeviceToHost));
+  if (sb_ref) std::memcpy(sb_ref, h.sb_ref, sizeof(double) * 9);
+  if (valid) *valid = h.valid;
+  if (redo_count) *redo_count = h.redo_count;
+  return OKB_OK;
+}
+
 // diagnostics: accumulated k_solve phase times (ns) of the last optimize of `win`
 extern "C" int okb_debug_phase_ns(okb_ctx* c, int win, double out[16]) {
   if (!c || win < 0 || win >= c->max_windows || !out) return OKB_ERR_INVALID_ARG;
@@ -1053,13 +1247,13 @@ extern "C" int okb_optimize(okb_ctx* c, int first, int count, const okb_solve_op
 
 // The estimates come back from the packed output block (pose | speed/bias | landmarks | quality, caller's order) that
 // k_quality / k_prepare / k_reset keep current: one D2H copy per window, plain memcpy on the host.
-static size_t out_doubles(const WinDev& W) { return 7 * (size_t)W.K + 9 * (size_t)W.NSB + 5 * (size_t)W.L; }
+static size_t out_doubles(const WinDev& W) { return out_lm_offset(W.K, W.NSB) + 5 * (size_t)W.L; }
 static void copy_out_window(const WinDev& W, const WinStore& S, double* poses, double* speed_bias, double* landmarks, double* quality) {
   const double* o = reinterpret_cast<const double*>(S.out_staging);
   if (poses) std::memcpy(poses, o, sizeof(double) * 7 * W.K);
   if (speed_bias && W.NSB) std::memcpy(speed_bias, o + 7 * W.K, sizeof(double) * 9 * W.NSB);
-  if (landmarks) std::memcpy(landmarks, o + 7 * W.K + 9 * W.NSB, sizeof(double) * 4 * (size_t)W.L);
-  if (quality) std::memcpy(quality, o + 7 * W.K + 9 * W.NSB + 4 * (size_t)W.L, sizeof(double) * (size_t)W.L);
+  if (landmarks) std::memcpy(landmarks, o + out_lm_offset(W.K, W.NSB), sizeof(double) * 4 * (size_t)W.L);
+  if (quality) std::memcpy(quality, o + out_lm_offset(W.K, W.NSB) + 4 * (size_t)W.L, sizeof(double) * (size_t)W.L);
 }
 
 extern "C" int okb_window_download(okb_ctx* c, int win, double* poses, double* speed_bias, double* landmarks, double* quality) {
@@ -1162,6 +1356,8 @@ __global__ void k_hook_relpose(const double* in /* S36 p0 p1 */, double* out /* 
 }
 }  // namespace
 
+static int hook_alloc(okb_ctx* c, size_t bytes);
+static int hook_alloc_fwd(okb_ctx* c, size_t bytes) { return hook_alloc(c, bytes); }
 static int hook_alloc(okb_ctx* c, size_t bytes) {
   if (c->hook_bytes >= bytes) return OKB_OK;
   if (c->hook_buf) cudaFree(c->hook_buf);

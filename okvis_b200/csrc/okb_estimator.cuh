@@ -90,6 +90,10 @@ __host__ __device__ inline size_t shard_win_bytes(int world, size_t box_cap) {
 __host__ __device__ inline size_t lm_M_index(int l, int f, int K) { return ((size_t)(l >> 5) * K + f) * 192 + (l & 31); }   // + 32 * element (0..5)
 __host__ __device__ inline size_t lm_mf_index(int l, int f, int K) { return ((size_t)(l >> 5) * K + f) * 96 + (l & 31); }    // + 32 * element (0..2)
 
+// packed download block: pose [K][7] | speed/bias [NSB][9] | pad to 4 doubles | landmarks [L][4] | quality [L]
+// (the landmark part is written with 32-byte vector stores)
+__host__ __device__ inline size_t out_lm_offset(int K, int NSB) { return ((size_t)7 * K + (size_t)9 * NSB + 3) & ~(size_t)3; }
+
 struct SlotCtx;   // per (frame, camera) transform + intrinsics at the candidate state (okb_kernels_lm.cuh)
 
 struct WinDev {
@@ -176,6 +180,7 @@ struct WinDev {
   int32_t* marg_col;                           // [marg_nb] first column of each block
   int32_t* marg_off;                           // [marg_nb] offset into x0
   double *marg_x0, *marg_J, *marg_e0, *marg_H0;  // H0 = J^T J
+  double *marg_Hs, *marg_b0;                   // H / b0 as MarginalizationError keeps them between calls (okb_marg.cuh); host-supplied priors: J^T J, -J^T e0
   // landmark sharding: this rank holds the landmarks / observations of its shard and all dense blocks
   int shard_rank, shard_world;                 // world <= 1: not sharded
   int shard_box_cap;                           // doubles per box

@@ -35,6 +35,7 @@ enum {
   CMD_ADD_IMU_TERM = 13,    // n = samples; payload okb_imu_term (sample_offset relative to the payload's samples), okb_imu_sample [n]
   CMD_SET_POSE_PRIORS = 14, // n; payload okb_pose_prior [n]
   CMD_SET_SB_PRIORS = 15,   // n; payload okb_sb_prior [n]
+  CMD_REMOVE_SB = 17,       // a = speed/bias index: the block, the IMU terms and SpeedAndBiasError priors attached to it
   CMD_SET_MARG = 16         // a = n, b = n_blocks; payload kind [b] i32, idx [b] u32 (each 8-byte padded), x0, J [n][n], e0 [n]
 };
 struct CmdHeader { uint32_t op, n, a, b; uint64_t payload_bytes; };   // payload follows, 8-byte aligned
@@ -363,6 +364,92 @@ __global__ void __launch_bounds__(1024) k_apply_commands(const WinDev* __restric
           double s = 0;
           for (int r = 0; r < n; ++r) s += J[(size_t)r * n + i] * J[(size_t)r * n + j];
           W.marg_H0[(size_t)i * n + j] = s; W.marg_H0[(size_t)j * n + i] = s;
+          W.marg_Hs[(size_t)i * n + j] = s; W.marg_Hs[(size_t)j * n + i] = s;
+        }
+        for (int i = tid; i < n; i += NT) {            // b0 = -J^T e0: what a later okb_window_marginalize starts from
+          double s = 0;
+          for (int r = 0; r < n; ++r) s += J[(size_t)r * n + i] * e0[r];
+          W.marg_b0[i] = -s;
+        }
+        break;
+      }
+      case CMD_REMOVE_SB: {
+        const int sbi = (int)h.a;
+        if (sbi >= NSB) { if (tid == 0) graph_error(g, GERR_INDEX); break; }
+        {
+          const int ns = 9 * (NSB - sbi - 1);
+          double vs = 0;
+          if (tid < ns) vs = W.sb[9 * (sbi + 1) + tid];
+          __syncthreads();
+          if (tid < ns) W.sb[9 * sbi + tid] = vs;
+        }
+        const int n_imu = g->n_imu;
+        if (tid == 0) {
+          int o = 0;
+          for (int t = 0; t < n_imu; ++t) {
+            okb_imu_term T = W.imu_terms[t];
+            const bool drop = (int)T.sb0 == sbi || (int)T.sb1 == sbi;
+            s_map[t] = drop ? -1 : o;
+            if (drop) continue;
+            if ((int)T.sb0 > sbi) T.sb0--;
+            if ((int)T.sb1 > sbi) T.sb1--;
+            W.imu_terms[o++] = T;
+          }
+          s_i[0] = o;
+        }
+        __syncthreads();
+        const int n_new = s_i[0];
+        constexpr int CW2 = (int)(sizeof(ImuCache) / sizeof(double));
+        for (int t = 0; t < n_imu; ++t) {
+          const int o = s_map[t];
+          if (o < 0 || o == t) continue;
+          double v[(CW2 + 1023) / 1024];
+#pragma unroll
+          for (int q = 0; q < (CW2 + 1023) / 1024; ++q) { const int i = tid + q * 1024; if (i < CW2) v[q] = reinterpret_cast<const double*>(W.imu_cache + t)[i]; }
+          __syncthreads();
+#pragma unroll
+          for (int q = 0; q < (CW2 + 1023) / 1024; ++q) { const int i = tid + q * 1024; if (i < CW2) reinterpret_cast<double*>(W.imu_cache + o)[i] = v[q]; }
+          __syncthreads();
+        }
+        if (tid == 0) {
+          uint32_t lo = 0xffffffffu, hi = 0;
+          for (int t = 0; t < n_new; ++t) { lo = min(lo, W.imu_terms[t].sample_offset); hi = max(hi, W.imu_terms[t].sample_offset + W.imu_terms[t].sample_count); }
+          if (n_new == 0) { lo = 0; hi = 0; }
+          s_i[1] = (int)lo; s_i[2] = (int)hi;
+          for (int t = 0; t < n_new; ++t) W.imu_terms[t].sample_offset -= lo;
+        }
+        __syncthreads();
+        {
+          const int lo = s_i[1], hi = s_i[2];
+          constexpr int SW2 = (int)(sizeof(okb_imu_sample) / 8);
+          const int words = (hi - lo) * SW2;
+          double* pool = reinterpret_cast<double*>(W.samples);
+          if (lo > 0)
+            for (int base = 0; base < words; base += NT) {
+              const int i = base + tid;
+              double v = 0;
+              if (i < words) v = pool[(size_t)lo * SW2 + i];
+              __syncthreads();
+              if (i < words) pool[i] = v;
+              __syncthreads();
+            }
+          if (tid == 0) { g->n_samples = hi - lo; g->n_imu = n_new; }
+        }
+        if (tid == 0) {
+          int o = 0;
+          for (int i = 0; i < g->n_sbp; ++i) {
+            okb_sb_prior P = W.sbp[i];
+            if ((int)P.sb_idx == sbi) continue;
+            if ((int)P.sb_idx > sbi) P.sb_idx--;
+            W.sbp[o++] = P;
+          }
+          g->n_sbp = o;
+          for (int b = 0; b < g->marg_nb; ++b) {
+            if (W.marg_kind[b] != OKB_BLOCK_SPEED_BIAS) continue;
+            if ((int)W.marg_idx[b] == sbi) graph_error(g, GERR_MARG_REF);
+            else if ((int)W.marg_idx[b] > sbi) W.marg_idx[b]--;
+          }
+          g->NSB = NSB - 1;
         }
         break;
       }

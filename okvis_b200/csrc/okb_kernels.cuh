@@ -798,8 +798,8 @@ __global__ void __launch_bounds__(256) k_zero(const WinDev* __restrict__ wins, i
   }
 }
 // packed estimates for the download: pose [K][7] | sb [NSB][9] | landmarks [L][4] | quality [L] (caller's order)
-__device__ __forceinline__ double* out_lm(const WinDev& W) { return W.out + 7 * W.K + 9 * W.NSB; }
-__device__ __forceinline__ double* out_quality(const WinDev& W) { return W.out + 7 * W.K + 9 * W.NSB + 4 * (size_t)W.L; }
+__device__ __forceinline__ double* out_lm(const WinDev& W) { return W.out + out_lm_offset(W.K, W.NSB); }
+__device__ __forceinline__ double* out_quality(const WinDev& W) { return W.out + out_lm_offset(W.K, W.NSB) + 4 * (size_t)W.L; }
 
 __global__ void __launch_bounds__(256) k_prepare(const WinDev* __restrict__ wins, int win_first) {
   const WinDev& W = wins[win_first + blockIdx.y];

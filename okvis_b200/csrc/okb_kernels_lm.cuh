@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(128) k_quality(const WinDev* __restrict__ wins
     // write-back in the caller's order: the master copy (next compile) and the packed download block
     const uint32_t lc = W.perm[l];
     *reinterpret_cast<double4*>(W.m_lm + 4 * (size_t)lc) = x4;
-    double* o = W.out + 7 * W.K + 9 * W.NSB;
+    double* o = W.out + out_lm_offset(W.K, W.NSB);
     *reinterpret_cast<double4*>(o + 4 * (size_t)lc) = x4;
     o[4 * (size_t)L + lc] = q;
   }

@@ -6,6 +6,7 @@
 #include "oracle_brisk.hpp"
 #include "oracle_errors.hpp"
 #include "oracle_marg.hpp"
+#include "oracle_marg_apply.hpp"
 #include "oracle_matcher.hpp"
 #include "oracle_solver.hpp"
 #ifdef _OPENMP
@@ -62,6 +63,24 @@ void oko_get_state(void* p, double* poses, double* sb, double* lms, double* qual
     pb->landmark_quality(q);
     std::memcpy(quality, q.data(), q.size() * 8);
   }
+}
+// Test plumbing for chained marginalisation checks: overwrite the estimates (caches untouched) and bring an ImuError
+// cache into the state "preintegrated at sb_ref" (what the device reports through okb_debug_imu_cache).
+void oko_set_state(void* p, const double* poses, const double* sb, const double* lms) {
+  Problem* pb = static_cast<Problem*>(p);
+  if (poses) std::memcpy(pb->poses.data(), poses, pb->poses.size() * 8);
+  if (sb) std::memcpy(pb->sb.data(), sb, pb->sb.size() * 8);
+  if (lms) std::memcpy(pb->lms.data(), lms, pb->lms.size() * 8);
+}
+int oko_set_imu_cache(void* p, int term, const double* sb_ref, int valid) {
+  Problem* pb = static_cast<Problem*>(p);
+  if (term < 0 || term >= (int)pb->imu_terms.size()) return -1;
+  ImuCache& c = pb->imu_cache[term];
+  if (!valid) { c.redo = true; return 0; }
+  const okb_imu_term& T = pb->imu_terms[term];
+  imu_redo_preintegration(pb->samples.data() + T.sample_offset, (int)T.sample_count, pb->imu_params, T.t0_ns, T.t1_ns, sb_ref, c);
+  c.redo = false;
+  return 0;
 }
 double oko_cost(void* p) { return static_cast<Problem*>(p)->cost_only(); }
 
@@ -185,6 +204,23 @@ int oko_marg_update_error_computation(const double* H, const double* b, int n, d
   std::memcpy(J, Jv.data(), sizeof(double) * (size_t)n * n);
   std::memcpy(e0, ev.data(), sizeof(double) * n);
   return rank;
+}
+// One marginalisation step on the problem's graph (oracle_marg_apply.hpp).  Outputs sized for n <= 160 / 64 blocks.
+// Returns the dimension of the new prior (-1: a residual's parameter block is missing from the job).
+int oko_marginalize(void* p, const okb_marg_job* job, const double* H_prev, const double* b0_prev, int32_t* kind, uint32_t* idx, double* x0,
+                    double* J, double* e0, double* H, double* b0, int* rank) {
+  Problem* pb = static_cast<Problem*>(p);
+  MargOut o;
+  const int n = marginalize_problem(*pb, *job, H_prev, b0_prev, o);
+  if (n < 0) return n;
+  for (size_t i = 0; i < o.kind.size(); ++i) { kind[i] = o.kind[i]; idx[i] = o.idx[i]; }
+  std::memcpy(x0, o.x0.data(), sizeof(double) * o.x0.size());
+  std::memcpy(J, o.J.data(), sizeof(double) * (size_t)n * n);
+  std::memcpy(e0, o.e0.data(), sizeof(double) * n);
+  std::memcpy(H, o.H.data(), sizeof(double) * (size_t)n * n);
+  std::memcpy(b0, o.b0.data(), sizeof(double) * n);
+  if (rank) *rank = o.rank;
+  return n;
 }
 int oko_sym_eig(const double* A, int n, double* evals, double* evecs) {
   std::vector<double> Av(A, A + (size_t)n * n), ev, V;

@@ -83,6 +83,36 @@ class OracleProblem:
                                        "quality", "other"], phases.tolist()))
         return out
 
+    def set_state(self, poses=None, speed_bias=None, landmarks=None):
+        a = [np.ascontiguousarray(x, np.float64) if x is not None else None for x in (poses, speed_bias, landmarks)]
+        f = lib().oko_set_state
+        f.restype = None
+        f(C.c_void_p(self._p), *[C.c_void_p(x.ctypes.data) if x is not None else None for x in a])
+
+    def set_imu_cache(self, term, sb_ref, valid=True):
+        r = np.ascontiguousarray(sb_ref, np.float64)
+        assert lib().oko_set_imu_cache(C.c_void_p(self._p), int(term), C.c_void_p(r.ctypes.data), int(bool(valid))) == 0
+
+    def marginalize(self, job, H_prev=None, b0_prev=None):
+        """One marginalisation step (oracle_marg_apply.hpp) on the problem's graph at its current estimates."""
+        kind, idx = np.zeros(64, np.int32), np.zeros(64, np.uint32)
+        x0, J, e0, H, b0 = np.zeros(9 * 64), np.zeros(160 * 160), np.zeros(160), np.zeros(160 * 160), np.zeros(160)
+        rank = C.c_int(0)
+        f = lib().oko_marginalize
+        f.restype = C.c_int
+        hp = np.ascontiguousarray(H_prev, np.float64) if H_prev is not None else None
+        bp = np.ascontiguousarray(b0_prev, np.float64) if b0_prev is not None else None
+        n = f(C.c_void_p(self._p), C.byref(job), C.c_void_p(hp.ctypes.data) if hp is not None else None,
+              C.c_void_p(bp.ctypes.data) if bp is not None else None, *[C.c_void_p(a.ctypes.data) for a in (kind, idx, x0, J, e0, H, b0)],
+              C.byref(rank))
+        if n < 0:
+            raise RuntimeError("oracle marginalize: a residual's parameter block is missing from the job")
+        nb = sum(1 for m in job._keep[3] if not m)
+        kind, idx = kind[:nb].copy(), idx[:nb].copy()
+        xdim = int(sum(9 if k == abi.BLOCK_SPEED_BIAS else 7 for k in kind))
+        return dict(n=n, block_kind=kind, block_idx=idx, x0=x0[:xdim].copy(), J=J[:n * n].reshape(n, n).copy(), e0=e0[:n].copy(),
+                    H=H[:n * n].reshape(n, n).copy(), b0=b0[:n].copy(), rank=rank.value)
+
     def state(self, with_quality=True):
         w = self.window
         poses = np.zeros_like(w.poses)
