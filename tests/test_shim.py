@@ -44,3 +44,36 @@ def test_shim_estimator_cycle_converges():
     assert abs(r["vy"] - 0.5) < 2e-2      # velocity recovered although the first-frame prior says 0
     assert 0.0 < r["lm_quality"] <= 1.0
     assert r["dup_obs"] == 0              # duplicate observation returns NULL like the reference
+
+
+@pytest.mark.gpu
+def test_shim_survives_the_threaded_kfvio_cycle_with_marginalisation():
+    """30 frames of addStates -> addObservation -> optimize -> applyMarginalizationStrategy(5, 3): the window holds
+    numKeyframes + numImuFrames frames, the estimate stays on the true trajectory (exact measurements) although
+    frames / landmarks are marginalised every step, and only a frame's worth of data is uploaded per optimize."""
+    build_shim()
+    out = subprocess.run([BIN, "--sliding", "30"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr + out.stdout
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert "error" not in r, r
+    assert r["marg_calls"] == 30 and r["max_frames"] <= 8 and r["frames"] == 8
+    assert r["imu_window_ok"] == 1
+    assert r["removed_landmarks"] > 50            # landmarks leave the field of view and are marginalised / dropped
+    # the first frames still carry the zero-velocity prior against 1.5 m/s; afterwards the estimate sits on the trajectory
+    assert r["max_pos_err"] < 5e-2 and r["pos_err"] < 2e-3
+    assert abs(r["vy"] - 1.5) < 2e-2
+    assert r["steady_upload_bytes"] * 4 < r["first_upload_bytes"] or r["steady_upload_bytes"] < 100000
+
+
+@pytest.mark.gpu
+def test_frontend_and_dense_matcher_shims():
+    """okvis_b200::Frontend (detectAndDescribe, propagation, parameter accessors) and okvis_b200::DenseMatcher
+    (match<ALGORITHM> with the reference's epilogue, candidate lists) on a stereo pair with 12 px disparity."""
+    build_shim()
+    out = subprocess.run([BIN, "--frontend"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert min(r["keypoints"]) > 100 and r["initialized"] == 1
+    assert r["matches"] > 60 and r["consistent"] >= 0.7 * r["matches"]     # the blocky texture repeats: some corners are ambiguous
+    assert r["candidates"] >= r["matches"]
+    assert r["propagation_ok"] == 1 and abs(r["propagated_x"] - 0.2 * 0.2) < 1e-6     # 0.2 m/s for 0.2 s
