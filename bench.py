@@ -161,46 +161,69 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def frontend_leg(ctx, cam):
-    """Secondary measurement (north_star rows S-V): keypoint detect/describe and the all-pairs Hamming matcher through
-    the C-ABI with host buffers, next to the CPU oracle on a bounded sample.  Reported inside the same JSON line."""
+def frontend_leg(ctx, cam, rank=0, world=1, with_cpu=True):
+    """Secondary measurement (north_star rows S-V, BASELINE.json configs[2]): keypoint detect/describe and the all-pairs
+    Hamming matcher through the C-ABI with host buffers (host clock, copies included), next to the CPU oracle on a
+    bounded sample.  Two parameter sets: cfg-3 (uniformity radius 15, <= 1000 keypoints on a dense texture, 1000 x 1000
+    match) and OKVIS' shipped yaml (radius 40, <= 400).  Images shard over ranks per image: every
+    rank works on its own seeded stereo pair; rank 0 reports its own timings, the caller sums images/s over ranks."""
     from okvis_b200 import images
     from oracle import oracle_py as op
-    left, right = images.stereo_pair()
     R = np.eye(3)
-    for s_, im in enumerate((left, right)):
-        ctx.detect_describe(im, cam, R, cam_slot=s_)
-    reps = 20
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        kl, dl = ctx.detect_describe(left, cam, R, cam_slot=0)
-        kr, dr = ctx.detect_describe(right, cam, R, cam_slot=1)
-    dd_ms = (time.perf_counter() - t0) * 1e3 / (2 * reps)
-    t0 = time.perf_counter()
-    op.detect_describe(left, cam, R)
-    dd_cpu_ms = (time.perf_counter() - t0) * 1e3
-    ctx.hamming_match(dl, dr)
+    out = {"note": "host buffers in/out, host clock; sequential DenseMatcher semantics (top-k lists and assignbest on the device)"}
+    seed = 0x0B200 + 3000 + 17 * rank
+    dense_l = images.textured_image(seed, n_shapes=2600)
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    dense_r = np.roll(dense_l, -12, axis=1).astype(np.float64) + rng.normal(0, 2.0, dense_l.shape)
+    dense_r = np.clip(np.rint(dense_r), 0, 255).astype(np.uint8)
+    left, right = images.stereo_pair()
+    for tag, (il, ir), kw in (("cfg3", (dense_l, dense_r), dict(uniformity_radius=15.0, max_keypoints=1000)),
+                              ("production", (left, right), dict(uniformity_radius=40.0, max_keypoints=400))):
+        for s_, im in enumerate((il, ir)):
+            ctx.detect_describe(im, cam, R, cam_slot=s_, **kw)
+        reps = 20
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            kl, dl = ctx.detect_describe(il, cam, R, cam_slot=0, **kw)
+            kr, dr = ctx.detect_describe(ir, cam, R, cam_slot=1, **kw)
+        dd_ms = (time.perf_counter() - t0) * 1e3 / (2 * reps)
+        ctx.hamming_match(dl, dr)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            ctx.hamming_match(dl, dr)
+        m_us = (time.perf_counter() - t0) * 1e6 / 50
+        o = {"detect_describe_ms_per_image": dd_ms, "keypoints": [int(len(kl)), int(len(kr))], "hamming_match_us": m_us,
+             "hamming_match_shape": [int(len(dl)), int(len(dr))],
+             "params": "uniformity radius %.0f px, absolute threshold 800, <= %d keypoints, 48-byte descriptors" % (kw["uniformity_radius"], kw["max_keypoints"]),
+             # SURVEY 8d algorithmic traffic: 3.3 MB per image (image + score planes + descriptors), (nA+nB)*48 + nA*32 B per match
+             "detect_describe_GBps": 3.3e-3 / (dd_ms * 1e-3), "hamming_Gpairs_per_s": len(dl) * len(dr) / (m_us * 1e-6) / 1e9}
+        if with_cpu:
+            t0 = time.perf_counter()
+            op.detect_describe(il, cam, R, **kw)
+            o["cpu_oracle_detect_describe_ms_per_image"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            for _ in range(3):
+                op.match_hamming(dl, dr)
+            o["cpu_oracle_hamming_match_us"] = (time.perf_counter() - t0) * 1e6 / 3
+        out[tag] = o
+    rng = np.random.Generator(np.random.PCG64(5))
+    A = rng.integers(0, 256, (1000, 48), dtype=np.uint8)
+    Bm = A[rng.permutation(1000)].copy()
+    Bm[:, :4] ^= rng.integers(0, 256, (1000, 4), dtype=np.uint8)
+    ctx.hamming_match(A, Bm)
     t0 = time.perf_counter()
     for _ in range(50):
-        ctx.hamming_match(dl, dr)
-    m_us = (time.perf_counter() - t0) * 1e6 / 50
-    t0 = time.perf_counter()
-    for _ in range(5):
-        op.match_hamming(dl, dr)
-    m_cpu_us = (time.perf_counter() - t0) * 1e6 / 5
-    rng = np.random.Generator(np.random.PCG64(5))
+        ctx.hamming_match(A, Bm)
+    out["hamming_1000x1000_us"] = (time.perf_counter() - t0) * 1e6 / 50
     A = rng.integers(0, 256, (8192, 48), dtype=np.uint8)
     Bm = rng.integers(0, 256, (8192, 48), dtype=np.uint8)
     ctx.hamming_match(A, Bm, threshold=200.0)
     t0 = time.perf_counter()
     for _ in range(5):
         ctx.hamming_match(A, Bm, threshold=200.0)
-    big_s = (time.perf_counter() - t0) / 5
-    return {"detect_describe_ms_per_image": dd_ms, "image": "752x480 u8, <=400 keypoints, 48-byte descriptors", "keypoints": [int(len(kl)), int(len(kr))],
-            "cpu_oracle_detect_describe_ms_per_image": dd_cpu_ms,
-            "hamming_match_us": m_us, "hamming_match_shape": [int(len(dl)), int(len(dr))], "cpu_oracle_hamming_match_us": m_cpu_us,
-            "hamming_8192x8192_gcmp_per_s": 8192.0 * 8192.0 / big_s / 1e9,
-            "note": "host buffers in/out, host clock; sequential DenseMatcher semantics (assignbest on the device)"}
+    out["hamming_8192x8192_gcmp_per_s"] = 8192.0 * 8192.0 / ((time.perf_counter() - t0) / 5) / 1e9
+    out["images_per_s_this_gpu"] = 1e3 / out["cfg3"]["detect_describe_ms_per_image"]
+    return out
 
 
 def pin_to_gpu_numa(gpu_index):
@@ -374,7 +397,7 @@ def run_b200(args):
     # (poses, speed/bias, landmarks, quality).  Each step therefore solves the same graph as the resident leg from the
     # same initial estimates.  Two slot ranges alternate so that the host-side command packing, the H2D copy, the
     # device-side graph compile and the D2H copy of one range overlap the solve of the other (transfer stream).
-    e2e_steps = max(2, args.steps)
+    e2e_steps = max(12, 2 * args.steps)     # the two-range pipeline needs a fill and a drain step: amortised like in a long stream
     range_windows = [windows[i % len(windows)] for i in range(Be)]
     descs = ctx.make_descs(range_windows)              # descriptors only point at the host arrays
     for base in (0, Be):
@@ -440,6 +463,14 @@ def run_b200(args):
             lat = latency_leg(torch, dev, local_rank, windows[0])
         except Exception as e:
             lat = {"error": repr(e)}
+    try:        # frontend leg on every rank: images shard per image, no collective
+        frontend = frontend_leg(ctx, windows[0].cameras[0], rank, world, with_cpu=(rank == 0))
+        ips = frontend["images_per_s_this_gpu"]
+    except Exception as e:       # the headline measurement must not depend on this leg
+        frontend, ips = {"error": repr(e)}, 0.0
+    (_,), (ips_all,) = sharding.reduce_measurement(dist, dev, [0.0], [ips])
+    if isinstance(frontend, dict):
+        frontend["images_per_s_all_gpus"] = ips_all
     if rank == 0:
         peak, peak_kind = load_peaks()
         w = windows[0]
@@ -470,10 +501,6 @@ def run_b200(args):
                 cpu_iters, cpu_dt, n_cpu = it_, dt_, t_
         cores = n_cpu
         cfg5 = cfg5_res
-        try:
-            frontend = frontend_leg(ctx, windows[0].cameras[0])
-        except Exception as e:       # the headline measurement must not depend on this leg
-            frontend = {"error": repr(e)}
         line = {
             "metric": METRIC, "value": iters_all / (elapsed_ms * 1e-3), "unit": "iterations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,

@@ -77,6 +77,17 @@ struct okb_ctx {
   unsigned char* shard_peer[okb::kMaxShard] = {};             // [rank]; own entry = shard_local
   bool shard_peer_ipc[okb::kMaxShard] = {};                   // opened with cudaIpcOpenMemHandle (closed at destroy)
   int64_t launches = 0;
+  // captured launch sequences of okb_optimize (run_rounds): key fields up to `exec`, compared bytewise
+  struct GraphEntry {
+    int first, count, rounds, with_quality, opt_iter, opt_min, opt_cauchy, _pad;
+    double opt_time;
+    unsigned char plan[96];
+    cudaGraphExec_t exec;
+    int64_t launches;
+    uint64_t stamp;
+  };
+  std::vector<GraphEntry> graphs;
+  uint64_t graph_clock = 0;
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
   std::vector<int> prof_kind;             // kernel id per pair

@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -87,8 +89,10 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
   }
   cudaMemset(c->d_states, 0, sizeof(SolverState) * max_windows);
   cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-  cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
-  cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_solve<S_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_solve<S_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_solve<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_solve<512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_schur, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_quality, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   *out = c;
@@ -119,6 +123,7 @@ extern "C" void okb_ctx_destroy(okb_ctx* c) {
   if (c->d_states) cudaFree(c->d_states);
   if (c->h_states) cudaFreeHost(c->h_states);
   if (c->hook_buf) cudaFree(c->hook_buf);
+  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto e : c->prof_events) cudaEventDestroy(e);
   if (c->ev_round) cudaEventDestroy(c->ev_round);
   if (c->ev_imu) cudaEventDestroy(c->ev_imu);
@@ -1073,9 +1078,14 @@ extern "C" int okb_window_reset(okb_ctx* c, int first, int count) {
 // ---------------------------------------------------------------------------------------------
 // optimize
 // ---------------------------------------------------------------------------------------------
-static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_options& opt, int rounds) {
-  int max_chunks = 1, max_imu = 0, max_cx = 1, max_K = 1;
-  size_t smA = 0, smS = 0;
+// Launch geometry of one optimize of windows [first, first+count): everything a captured CUDA graph depends on
+// besides the kernel arguments.
+struct RoundPlan {
+  int max_chunks = 1, max_imu = 0, max_cx = 1, max_K = 1, acc_copies = 1, chol_smem = 1, solve_threads = S_THREADS, gxQ = 1, shard = 0, push_gx = 1;
+  size_t smA = 0, smS = 0, smQ = 0;
+};
+static int plan_rounds(okb_ctx* c, int first, int count, RoundPlan& P) {
+  P = RoundPlan();
   bool chol_smem = true;
   // Schur accumulator in shared memory if two CTAs per SM still fit (else one CTA; else accumulate in global memory)
   int acc_copies = 1;
@@ -1085,63 +1095,125 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
         smemA2_bytes(c->host[i].K, c->host[i].dcp, 0) <= sm_two) acc_copies = 0;
   for (int i = first; i < first + count; ++i)
     if (smemA2_bytes(c->host[i].K, c->host[i].dcp, acc_copies) > (size_t)c->smem_optin) acc_copies = 0;
+  int maxL = 1;
   for (int i = first; i < first + count; ++i) {
     const WinDev& W = c->host[i];
-    max_chunks = std::max(max_chunks, W.n_chunks);
-    max_imu = std::max(max_imu, W.n_imu);
-    smA = std::max(smA, smemA2_bytes(W.K, W.dcp, acc_copies));
-    max_cx = std::max(max_cx, (W.L + L1_THREADS - 1) / L1_THREADS);
-    max_K = std::max(max_K, W.K);
+    P.max_chunks = std::max(P.max_chunks, W.n_chunks);
+    P.max_imu = std::max(P.max_imu, W.n_imu);
+    P.smA = std::max(P.smA, smemA2_bytes(W.K, W.dcp, acc_copies));
+    P.max_cx = std::max(P.max_cx, (W.L + L1_THREADS - 1) / L1_THREADS);
+    P.max_K = std::max(P.max_K, W.K);
     if (smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, true) > (size_t)c->smem_optin) chol_smem = false;
+    P.smQ = std::max(P.smQ, (size_t)W.NS * sizeof(SlotCtx));
+    maxL = std::max(maxL, W.L);
   }
   for (int i = first; i < first + count; ++i) {
     const WinDev& W = c->host[i];
-    smS = std::max(smS, smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, chol_smem));
+    P.smS = std::max(P.smS, smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, chol_smem));
   }
-  if (smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
+  if (P.smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
+  P.acc_copies = acc_copies; P.chol_smem = chol_smem ? 1 : 0;
+  // few windows: one wide CTA per SM (sharded windows keep the 256-thread CTA: every rank must run the same reduction tree)
+  P.solve_threads = (2 * count <= c->sm_count && c->shard_world <= 1) ? 512 : S_THREADS;
+  P.gxQ = std::max(1, std::min((maxL + 127) / 128, (4 * c->sm_count + count - 1) / count));
+  P.shard = c->shard_world > 1 ? 1 : 0;
+  P.push_gx = std::max(1, std::min(16, c->sm_count / std::max(1, count)));
+  return OKB_OK;
+}
+
+static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_options& opt, int rounds, const RoundPlan& P) {
   for (int r = 0; r < rounds; ++r) {
-    const dim3 gridA(max_chunks, count);
-    if (max_imu > 0) {   // IMU terms only depend on the previous round's candidate: run beside the landmark kernels
+    const dim3 gridA(P.max_chunks, count);
+    if (P.max_imu > 0) {   // IMU terms only depend on the previous round's candidate: run beside the landmark kernels
       cudaEventRecord(c->ev_round, c->stream);
       cudaStreamWaitEvent(c->stream_imu, c->ev_round, 0);
-      k_imu<<<dim3(max_imu, count), 32, 0, c->stream_imu>>>(c->d_wins, first);
+      k_imu<<<dim3(P.max_imu, count), 32, 0, c->stream_imu>>>(c->d_wins, first);
       cudaEventRecord(c->ev_imu, c->stream_imu);
       c->launches += 1;
     }
     prof_begin(c, 0);
-    k_linearize<<<dim3(max_cx, max_K, count), L1_THREADS, 0, c->stream>>>(c->d_wins, first);
-    k_lmblock<<<dim3(max_cx, count), 128, 0, c->stream>>>(c->d_wins, first);
-    k_schur<<<gridA, A2_THREADS, smA, c->stream>>>(c->d_wins, first, acc_copies, opt.max_iterations);
-    if (c->shard_world > 1) {    // chunk reduction fused with the push half of the all-reduce over peer memory
-      k_shard_push<<<dim3(std::max(1, std::min(16, c->sm_count / std::max(1, count))), count), 256, 0, c->stream>>>(c->d_wins, first);
+    k_linearize<<<dim3(P.max_cx, P.max_K, count), L1_THREADS, 0, c->stream>>>(c->d_wins, first);
+    k_lmblock<<<dim3(P.max_cx, count), 128, 0, c->stream>>>(c->d_wins, first);
+    k_schur<<<gridA, A2_THREADS, P.smA, c->stream>>>(c->d_wins, first, P.acc_copies, opt.max_iterations);
+    if (P.shard) {    // chunk reduction fused with the push half of the all-reduce over peer memory
+      k_shard_push<<<dim3(P.push_gx, count), 256, 0, c->stream>>>(c->d_wins, first);
       c->launches += 1;
-    } else if (max_chunks > 1) { k_reduce_partials<<<dim3(8, count), 256, 0, c->stream>>>(c->d_wins, first); c->launches += 1; }
+    } else if (P.max_chunks > 1) { k_reduce_partials<<<dim3(8, count), 256, 0, c->stream>>>(c->d_wins, first); c->launches += 1; }
     prof_end(c);
-    c->launches += 2;
-    if (max_imu > 0) cudaStreamWaitEvent(c->stream, c->ev_imu, 0);
+    c->launches += 3;
+    if (P.max_imu > 0) cudaStreamWaitEvent(c->stream, c->ev_imu, 0);
     prof_begin(c, 1);
-    k_solve<<<count, S_THREADS, smS, c->stream>>>(c->d_wins, first, opt, chol_smem ? 1 : 0);
+    if (P.solve_threads == 512) k_solve<512><<<count, 512, P.smS, c->stream>>>(c->d_wins, first, opt, P.chol_smem);
+    else k_solve<S_THREADS><<<count, S_THREADS, P.smS, c->stream>>>(c->d_wins, first, opt, P.chol_smem);
     prof_end(c);
-    c->launches += 2;
+    c->launches += 1;
   }
   OKB_CUDA(c, cudaGetLastError());
   return OKB_OK;
 }
 
 // post-solve landmark quality (Estimator.cpp:880-894)
-static int launch_quality(okb_ctx* c, int first, int count) {
-  size_t smQ = 0;
-  int maxL = 1;
-  for (int i = first; i < first + count; ++i) {
-    smQ = std::max(smQ, (size_t)c->host[i].NS * sizeof(SlotCtx));
-    maxL = std::max(maxL, c->host[i].L);
-  }
-  const int gx = std::max(1, std::min((maxL + 127) / 128, (4 * c->sm_count + count - 1) / count));
+static int launch_quality(okb_ctx* c, int first, int count, const RoundPlan& P) {
   prof_begin(c, 2);
-  k_quality<<<dim3(gx, count), 128, smQ, c->stream>>>(c->d_wins, first);
+  k_quality<<<dim3(P.gxQ, count), 128, P.smQ, c->stream>>>(c->d_wins, first);
   prof_end(c);
   c->launches += 1;
   OKB_CUDA(c, cudaGetLastError());
+  return OKB_OK;
+}
+
+// The fixed launch sequence of one optimize (rounds + quality pass) as a CUDA graph: captured once per launch
+// geometry / option set and replayed -- one host call instead of ~70 launches and ~40 event operations, which is
+// what bounds the latency of a single window (SURVEY 8d "B = 1").  OKB_NO_GRAPH=1 disables it (diagnostics).
+static int run_rounds(okb_ctx* c, int first, int count, const okb_solve_options& opt, int rounds, bool with_quality) {
+  RoundPlan P;
+  int rc = plan_rounds(c, first, count, P);
+  if (rc) return rc;
+  static const bool no_graph = getenv("OKB_NO_GRAPH") != nullptr;
+  // landmark-sharded windows spin on their peers inside k_solve: their kernels must reach the device in stream order,
+  // not behind whatever hardware queue a graph's internal branches were mapped to
+  if (c->profile || no_graph || c->shard_world > 1) {
+    rc = launch_rounds(c, first, count, opt, rounds, P);
+    if (!rc && with_quality) rc = launch_quality(c, first, count, P);
+    return rc;
+  }
+  okb_ctx::GraphEntry key;
+  std::memset(&key, 0, sizeof key);
+  key.first = first; key.count = count; key.rounds = rounds; key.with_quality = with_quality ? 1 : 0;
+  key.opt_iter = opt.max_iterations; key.opt_min = opt.min_iterations; key.opt_cauchy = opt.use_cauchy_loss; key.opt_time = opt.time_limit_s;
+  static_assert(sizeof(RoundPlan) <= sizeof(key.plan), "plan blob");
+  std::memcpy(key.plan, &P, sizeof P);
+  for (auto& e : c->graphs)
+    if (e.exec && !std::memcmp(&e, &key, offsetof(okb_ctx::GraphEntry, exec))) {
+      e.stamp = ++c->graph_clock;
+      OKB_CUDA(c, cudaGraphLaunch(e.exec, c->stream));
+      c->launches += e.launches;
+      return OKB_OK;
+    }
+  const int64_t l0 = c->launches;
+  cudaGraph_t graph = nullptr;
+  OKB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  rc = launch_rounds(c, first, count, opt, rounds, P);
+  if (!rc && with_quality) rc = launch_quality(c, first, count, P);
+  const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  OKB_CUDA(c, ce);
+  key.launches = c->launches - l0;
+  c->launches = l0;
+  OKB_CUDA(c, cudaGraphInstantiate(&key.exec, graph, 0));
+  cudaGraphDestroy(graph);
+  okb_ctx::GraphEntry* slot = nullptr;
+  for (auto& e : c->graphs) if (!e.exec) { slot = &e; break; }
+  if (!slot && c->graphs.size() < 16) { c->graphs.emplace_back(); slot = &c->graphs.back(); }
+  if (!slot) {     // evict the least recently used
+    slot = &c->graphs[0];
+    for (auto& e : c->graphs) if (e.stamp < slot->stamp) slot = &e;
+    cudaGraphExecDestroy(slot->exec);
+  }
+  key.stamp = ++c->graph_clock;
+  *slot = key;
+  OKB_CUDA(c, cudaGraphLaunch(slot->exec, c->stream));
+  c->launches += slot->launches;
   return OKB_OK;
 }
 
@@ -1168,9 +1240,8 @@ extern "C" int okb_optimize_async(okb_ctx* c, int first, int count, const okb_so
   c->launches += 1;
   for (int i = first; i < first + count; ++i) c->wins[i].opt = *opt;     // okb_optimize_finish relaunches with the range's own options
   // round 0 linearises at the initial state; each later round judges one step and proposes the next
-  rc = launch_rounds(c, first, count, *opt, opt->max_iterations + 1);
+  rc = run_rounds(c, first, count, *opt, opt->max_iterations + 1, true);
   if (rc) return rc;
-  rc = launch_quality(c, first, count);
   OKB_CUDA(c, cudaMemcpyAsync(c->h_states + first, c->d_states + first, sizeof(SolverState) * count, cudaMemcpyDeviceToHost, c->stream));
   mark_work(c, first, count);
   return rc;
@@ -1188,9 +1259,7 @@ extern "C" int okb_optimize_finish(okb_ctx* c, int first, int count, okb_summary
     bool all_done = true;
     for (int i = first; i < first + count; ++i) all_done = all_done && c->h_states[i].done;
     if (all_done) break;
-    rc = launch_rounds(c, first, count, c->wins[first].opt, 2);
-    if (rc) return rc;
-    rc = launch_quality(c, first, count);
+    rc = run_rounds(c, first, count, c->wins[first].opt, 2, true);
     if (rc) return rc;
     OKB_CUDA(c, cudaMemcpyAsync(c->h_states + first, c->d_states + first, sizeof(SolverState) * count, cudaMemcpyDeviceToHost, c->stream));
     mark_work(c, first, count);

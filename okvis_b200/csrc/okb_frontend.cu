@@ -11,7 +11,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <cub/cub.cuh>
 #include <mutex>
 #include <vector>
 
@@ -90,10 +89,11 @@ struct SlotBuffers {
   uint8_t* d_img = nullptr;
   int32_t* d_score = nullptr;
   uint32_t* d_integral = nullptr;
-  unsigned long long *d_keys = nullptr, *d_keys_sorted = nullptr;
+  unsigned long long* d_keys = nullptr;
   int* d_count = nullptr;          // [0] candidates, [1] accepted
-  void* d_cub = nullptr;
-  size_t cub_bytes = 0;
+  uint32_t *d_cell_start = nullptr, *d_cell_cur = nullptr, *d_order = nullptr, *d_acc = nullptr;   // uniformity scratch
+  uint8_t* d_state = nullptr;
+  int max_cells = 0;
   okb_keypoint* d_kp = nullptr;
   uint8_t* d_desc = nullptr;
   int kp_cap = 0, desc_cap = 0;
@@ -129,8 +129,9 @@ void okb_frontend_release(okb_ctx* c) {
   okb_frontend_state* F = c->frontend;
   for (auto& s : F->slots) {
     if (s.stream) cudaStreamDestroy(s.stream);
-    cudaFree(s.d_img); cudaFree(s.d_score); cudaFree(s.d_integral); cudaFree(s.d_keys); cudaFree(s.d_keys_sorted);
-    cudaFree(s.d_count); cudaFree(s.d_cub); cudaFree(s.d_kp); cudaFree(s.d_desc);
+    cudaFree(s.d_img); cudaFree(s.d_score); cudaFree(s.d_integral); cudaFree(s.d_keys);
+    cudaFree(s.d_cell_start); cudaFree(s.d_cell_cur); cudaFree(s.d_order); cudaFree(s.d_acc); cudaFree(s.d_state);
+    cudaFree(s.d_count); cudaFree(s.d_kp); cudaFree(s.d_desc);
     if (s.h_img) cudaFreeHost(s.h_img);
     if (s.h_kp) cudaFreeHost(s.h_kp);
     if (s.h_desc) cudaFreeHost(s.h_desc);
@@ -228,54 +229,144 @@ __global__ void k_nms(const int32_t* __restrict__ score, int W, int H, int32_t t
   if (slot < cap) keys[slot] = ((unsigned long long)(uint32_t)s << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(y * W + x));
 }
 
-// Greedy uniformity in sorted order with an occupancy bitmap in shared memory (one CTA per image).
-__global__ void __launch_bounds__(256) k_uniformity(const unsigned long long* __restrict__ keys, const int* __restrict__ count, int cap,
-                                                    int W, int H, double radius, int max_kp, okb_keypoint* kps, int* n_out) {
-  extern __shared__ uint32_t occ[];   // W*H bits
-  __shared__ int s_next, s_idx, s_acc;
-  const int nwords = (W * H + 31) / 32;
-  for (int i = threadIdx.x; i < nwords; i += blockDim.x) occ[i] = 0u;
-  if (threadIdx.x == 0) { s_next = 0; s_acc = 0; }
+// Uniformity.  Specification (DESIGN.md "Frontend spec"): walk the NMS candidates in descending (score, raster) order and
+// accept a candidate iff no accepted one lies closer than `radius`; stop after max_kp.  That greedy pass is the
+// lexicographically-first maximal independent set of the "closer than radius" graph, and it is computed here WITHOUT
+// a sort and without a serial walk: in every round a candidate that has no live neighbour of higher priority is
+// accepted, accepted candidates kill their live neighbours (Blelloch et al.'s deterministic parallel MIS -- the result
+// is identical to the sequential greedy order, not merely equivalent).  Neighbours are found through a bucket grid
+// (cell size >= radius: 3x3 cells).  The accepted set is then ranked by counting (score order) and cut at max_kp.
+// One CTA of 1024 threads per image; all scratch lives in global memory.
+constexpr int UT = 1024;
+struct UniScratch {
+  uint32_t* cell_start;   // [n_cells + 1]
+  uint32_t* cell_cur;     // [n_cells]
+  uint32_t* order;        // [cap] candidate indices grouped by cell
+  uint8_t* state;         // [cap] 0 alive, 1 pending, 2 accepted, 3 dead
+  uint32_t* acc;          // [cap] accepted candidates
+  int max_cells;
+};
+__device__ __forceinline__ int uni_block_scan(int v, int* s_warp, int* total) {     // exclusive scan over the CTA
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
   __syncthreads();
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  const int base = warp ? s_warp[warp - 1] : 0;
+  *total = s_warp[31];
+  return base + x - v;
+}
+__global__ void __launch_bounds__(UT) k_uniformity(const unsigned long long* __restrict__ keys, const int* __restrict__ count, int cap,
+                                                   int W, int H, double radius, int max_kp, UniScratch sc, okb_keypoint* kps, int* n_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_n;
+  const int tid = threadIdx.x;
   const int n = min(*count, cap);
-  const double r2 = radius * radius;
-  const int R = (int)ceil(radius);
-  while (true) {
-    if (threadIdx.x == 0) {
-      int i = s_next, found = -1;
-      while (i < n && s_acc < max_kp) {
-        const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull);
-        if (!((occ[idx >> 5] >> (idx & 31)) & 1u)) { found = (int)idx; break; }
-        ++i;
-      }
-      s_idx = found;
-      if (found >= 0) {
-        const unsigned long long k = keys[i];
-        okb_keypoint kp;
-        kp.x = (float)(found % W); kp.y = (float)(found / W); kp.size = 12.0f; kp.angle = 0.0f;
-        kp.response = (float)(int32_t)(uint32_t)(k >> 32); kp.octave = 0;
-        kps[s_acc] = kp;
-        s_acc += 1;
-        s_next = i + 1;
-      }
-    }
-    __syncthreads();
-    const int idx = s_idx;
-    if (idx < 0) break;
-    const int cx = idx % W, cy = idx / W;
-    const int side = 2 * R + 1;
-    for (int e = threadIdx.x; e < side * side; e += blockDim.x) {
-      const int dy = e / side - R, dx = e % side - R;
-      const int x = cx + dx, y = cy + dy;
-      if (x < 0 || x >= W || y < 0 || y >= H) continue;
-      if ((double)(dx * dx + dy * dy) < r2) {
-        const uint32_t p = (uint32_t)(y * W + x);
-        atomicOr(&occ[p >> 5], 1u << (p & 31));
-      }
-    }
+  const int cs = max(4, (int)ceil(radius));
+  const int gw = (W + cs - 1) / cs, gh = (H + cs - 1) / cs, n_cells = gw * gh;
+  const long long r2i = (long long)ceil(radius * radius - 1e-9);     // integer test: dx^2 + dy^2 < radius^2
+  auto px = [&](int i, int& x, int& y) { const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull); x = (int)(idx % (uint32_t)W); y = (int)(idx / (uint32_t)W); };
+  // ---- bucket grid (counting sort by cell)
+  for (int c = tid; c < n_cells; c += UT) sc.cell_cur[c] = 0u;
+  __syncthreads();
+  for (int i = tid; i < n; i += UT) { int x, y; px(i, x, y); atomicAdd(&sc.cell_cur[(y / cs) * gw + x / cs], 1u); sc.state[i] = 0; }
+  __syncthreads();
+  int run = 0;
+  for (int base = 0; base < n_cells; base += UT) {
+    const int c = base + tid;
+    const int v = (c < n_cells) ? (int)sc.cell_cur[c] : 0;
+    int total;
+    const int ex = uni_block_scan(v, s_warp, &total);
+    if (c < n_cells) sc.cell_start[c] = (uint32_t)(run + ex);
+    run += total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *n_out = s_acc;
+  if (tid == 0) sc.cell_start[n_cells] = (uint32_t)run;
+  for (int c = tid; c < n_cells; c += UT) sc.cell_cur[c] = sc.cell_start[c];
+  __syncthreads();
+  for (int i = tid; i < n; i += UT) { int x, y; px(i, x, y); const uint32_t pos = atomicAdd(&sc.cell_cur[(y / cs) * gw + x / cs], 1u); sc.order[pos] = (uint32_t)i; }
+  __syncthreads();
+  // ---- rounds
+  int alive = n;
+  while (alive > 0) {
+    // accept: no live (alive or pending) neighbour with a larger key
+    for (int i = tid; i < n; i += UT) {
+      if (sc.state[i] != 0) continue;
+      int x, y; px(i, x, y);
+      const unsigned long long ki = keys[i];
+      bool blocked = false;
+      const int cx = x / cs, cy = y / cs;
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1) && !blocked; ++yy)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, gw - 1) && !blocked; ++xx) {
+          const uint32_t e = sc.cell_start[yy * gw + xx + 1];
+          for (uint32_t q = sc.cell_start[yy * gw + xx]; q < e; ++q) {
+            const int j = (int)sc.order[q];
+            if (keys[j] <= ki || sc.state[j] > 1) continue;
+            int xj, yj; px(j, xj, yj);
+            const long long dx = xj - x, dy = yj - y;
+            if (dx * dx + dy * dy < r2i) { blocked = true; break; }
+          }
+        }
+      if (!blocked) sc.state[i] = 1;
+    }
+    __syncthreads();
+    // kill: alive candidates next to a pending one
+    int still = 0;
+    for (int i = tid; i < n; i += UT) {
+      if (sc.state[i] != 0) continue;
+      int x, y; px(i, x, y);
+      bool dead = false;
+      const int cx = x / cs, cy = y / cs;
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1) && !dead; ++yy)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, gw - 1) && !dead; ++xx) {
+          const uint32_t e = sc.cell_start[yy * gw + xx + 1];
+          for (uint32_t q = sc.cell_start[yy * gw + xx]; q < e; ++q) {
+            const int j = (int)sc.order[q];
+            if (sc.state[j] != 1) continue;
+            int xj, yj; px(j, xj, yj);
+            const long long dx = xj - x, dy = yj - y;
+            if (dx * dx + dy * dy < r2i) { dead = true; break; }
+          }
+        }
+      if (dead) sc.state[i] = 3; else ++still;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += UT) if (sc.state[i] == 1) sc.state[i] = 2;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    if (still) atomicAdd(&s_n, still);           // integer sum: order independent
+    __syncthreads();
+    alive = s_n;
+    __syncthreads();
+  }
+  // ---- accepted set -> score order, first max_kp
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += UT) if (sc.state[i] == 2) sc.acc[atomicAdd(&s_n, 1)] = (uint32_t)i;
+  __syncthreads();
+  const int m = s_n;
+  for (int a = tid; a < m; a += UT) {
+    const unsigned long long ka = keys[sc.acc[a]];
+    int rank = 0;
+    for (int b = 0; b < m; ++b) rank += keys[sc.acc[b]] > ka;
+    if (rank < max_kp) {
+      int x, y; px((int)sc.acc[a], x, y);
+      okb_keypoint kp;
+      kp.x = (float)x; kp.y = (float)y; kp.size = 12.0f; kp.angle = 0.0f;
+      kp.response = (float)(int32_t)(uint32_t)(ka >> 32); kp.octave = 0;
+      kps[rank] = kp;
+    }
+  }
+  if (tid == 0) *n_out = min(m, max_kp);
 }
 
 // integral image (H+1) x (W+1), uint32
@@ -406,7 +497,6 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   if (!c || !img || !cam || !R_CW || !prm || !out_kp || !out_desc || !n_out) return OKB_ERR_INVALID_ARG;
   if (cam_slot < 0 || cam_slot >= kMaxSlots || width < 64 || height < 64 || stride < width) return OKB_ERR_INVALID_ARG;
   if (prm->desc_bytes < 4 || prm->desc_bytes > 128 || (prm->desc_bytes % 4) != 0) return OKB_ERR_INVALID_ARG;
-  if ((size_t)width * height > (size_t)1 << 21) { c->set_error("image too large for the uniformity bitmap"); return OKB_ERR_CAPACITY; }
   cudaSetDevice(c->device);
   okb_frontend_state* F = fe(c);
   int rc = ensure_pattern(c, F, prm->desc_bytes);
@@ -418,19 +508,21 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   if (maxk < 1) return OKB_ERR_INVALID_ARG;
   if (!S.stream) FE_CUDA(c, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
   if (S.W != W || S.H != H) {
-    cudaFree(S.d_img); cudaFree(S.d_score); cudaFree(S.d_integral); cudaFree(S.d_keys); cudaFree(S.d_keys_sorted); cudaFree(S.d_count);
-    cudaFree(S.d_cub);
+    cudaFree(S.d_img); cudaFree(S.d_score); cudaFree(S.d_integral); cudaFree(S.d_keys); cudaFree(S.d_count);
+    cudaFree(S.d_cell_start); cudaFree(S.d_cell_cur); cudaFree(S.d_order); cudaFree(S.d_acc); cudaFree(S.d_state);
     if (S.h_img) cudaFreeHost(S.h_img);
     if (S.h_count) cudaFreeHost(S.h_count);
     FE_CUDA(c, cudaMalloc(&S.d_img, (size_t)W * H));
     FE_CUDA(c, cudaMalloc(&S.d_score, sizeof(int32_t) * W * H));
     FE_CUDA(c, cudaMalloc(&S.d_integral, sizeof(uint32_t) * (W + 1) * (H + 1)));
     FE_CUDA(c, cudaMalloc(&S.d_keys, sizeof(unsigned long long) * kMaxCand));
-    FE_CUDA(c, cudaMalloc(&S.d_keys_sorted, sizeof(unsigned long long) * kMaxCand));
     FE_CUDA(c, cudaMalloc(&S.d_count, sizeof(int) * 2 + sizeof(double) * 4));
-    S.cub_bytes = 0;
-    cub::DeviceRadixSort::SortKeysDescending(nullptr, S.cub_bytes, S.d_keys, S.d_keys_sorted, kMaxCand);
-    FE_CUDA(c, cudaMalloc(&S.d_cub, S.cub_bytes));
+    S.max_cells = ((W + 3) / 4) * ((H + 3) / 4);          // smallest cell is 4 px
+    FE_CUDA(c, cudaMalloc(&S.d_cell_start, sizeof(uint32_t) * (S.max_cells + 1)));
+    FE_CUDA(c, cudaMalloc(&S.d_cell_cur, sizeof(uint32_t) * S.max_cells));
+    FE_CUDA(c, cudaMalloc(&S.d_order, sizeof(uint32_t) * kMaxCand));
+    FE_CUDA(c, cudaMalloc(&S.d_acc, sizeof(uint32_t) * kMaxCand));
+    FE_CUDA(c, cudaMalloc(&S.d_state, kMaxCand));
     FE_CUDA(c, cudaMallocHost(&S.h_img, (size_t)W * H));
     FE_CUDA(c, cudaMallocHost(&S.h_count, sizeof(int) * 2));
     S.W = W; S.H = H;
@@ -449,7 +541,6 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   cudaStream_t st = S.stream;
   FE_CUDA(c, cudaMemcpyAsync(S.d_img, S.h_img, (size_t)W * H, cudaMemcpyHostToDevice, st));
   FE_CUDA(c, cudaMemsetAsync(S.d_count, 0, sizeof(int) * 2, st));
-  FE_CUDA(c, cudaMemsetAsync(S.d_keys, 0, sizeof(unsigned long long) * kMaxCand, st));   // unused keys sort last
   // gravity direction in the camera frame: R_CW * (0,0,-1)
   double gC[3] = {-R_CW[2], -R_CW[5], -R_CW[8]};
   double* d_gC = reinterpret_cast<double*>(S.d_count + 2);
@@ -458,17 +549,13 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   k_harris<<<hg, hb, 0, st>>>(S.d_img, W, H, S.d_score);
   const dim3 nb(32, 8), ng((W + 31) / 32, (H + 7) / 8);
   k_nms<<<ng, nb, 0, st>>>(S.d_score, W, H, (int32_t)std::ceil(prm->absolute_threshold), S.d_keys, S.d_count, kMaxCand);
-  cub::DeviceRadixSort::SortKeysDescending(S.d_cub, S.cub_bytes, S.d_keys, S.d_keys_sorted, kMaxCand, 0, 64, st);
-  const size_t occ_bytes = sizeof(uint32_t) * (((size_t)W * H + 31) / 32);
-  if (occ_bytes + 1024 > (size_t)c->smem_optin) { c->set_error("image too large for the uniformity bitmap"); return OKB_ERR_CAPACITY; }
-  if (occ_bytes > 48 * 1024 - 64)
-    FE_CUDA(c, cudaFuncSetAttribute(k_uniformity, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occ_bytes));
-  k_uniformity<<<1, 256, occ_bytes, st>>>(S.d_keys_sorted, S.d_count, kMaxCand, W, H, prm->uniformity_radius, maxk, S.d_kp, S.d_count + 1);
+  UniScratch us{S.d_cell_start, S.d_cell_cur, S.d_order, S.d_state, S.d_acc, S.max_cells};
+  k_uniformity<<<1, UT, 0, st>>>(S.d_keys, S.d_count, kMaxCand, W, H, prm->uniformity_radius, maxk, us, S.d_kp, S.d_count + 1);
   k_integral_rows<<<(H + 1 + 3) / 4, 128, 0, st>>>(S.d_img, W, H, S.d_integral);
   k_integral_cols<<<(W + 1 + 63) / 64, 64, 0, st>>>(W, H, S.d_integral);
   k_describe<<<(maxk + 3) / 4, 128, 0, st>>>(S.d_integral, W, H, *cam, d_gC, prm->rotation_invariance, F->d_half, F->d_pi, F->d_pj,
                                              F->d_lut, prm->desc_bytes, S.d_kp, S.d_count + 1, S.d_desc);
-  c->launches += 6 + 3;   // + the radix-sort passes issued by CUB
+  c->launches += 6;
   FE_CUDA(c, cudaGetLastError());
   FE_CUDA(c, cudaMemcpyAsync(S.h_count, S.d_count, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
   FE_CUDA(c, cudaMemcpyAsync(S.h_kp, S.d_kp, sizeof(okb_keypoint) * maxk, cudaMemcpyDeviceToHost, st));
@@ -486,18 +573,25 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
 // matcher kernels
 // =================================================================================================
 namespace {
-constexpr int MT = 128;          // threads per CTA = A rows per CTA
+constexpr int MW = 8;            // warps per CTA = A rows per CTA (one warp per A descriptor)
+constexpr int MT = 32 * MW;
 constexpr int MB_TILE = 128;     // B descriptors staged per shared-memory tile
 constexpr int MAX_BEST = 8;
 
-// thread per A: sequential scan over B with the reference's insertion rule (listBIteration)
+// Warp per A descriptor.  Every lane computes the Hamming distance (XOR + __popc over NW words) of A to one of 32
+// consecutive B descriptors, staged tile by tile in shared memory for the CTA's 8 warps; the top-`num_best` list of
+// DenseMatcher::listBIteration (implementation/DenseMatcher.hpp:137-225) is kept replicated in the warp and updated
+// with exactly the reference's sequential rule -- candidates are taken in ascending B order (lowest set bit of the
+// ballot first), a candidate enters only if it beats the CURRENT worst entry (re-voted after every insertion, the
+// worst only shrinks), std::lower_bound position, i.e. before entries of equal distance.
 template <int NW>
 __global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict__ A, int nA, const uint32_t* __restrict__ B, int nB,
                                                      const uint8_t* __restrict__ skipA, const uint8_t* __restrict__ skipB, float list_thr,
                                                      int num_best, okb_pair* __restrict__ topk) {
   __shared__ uint32_t sB[MB_TILE][NW + 1];
   __shared__ uint8_t sSkip[MB_TILE];
-  const int a = blockIdx.x * MT + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = blockIdx.x * MW + warp;
   const bool active = a < nA && !(skipA && skipA[a]);
   uint32_t wa[NW];
 #pragma unroll
@@ -506,6 +600,7 @@ __global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict_
   float bd[MAX_BEST];
 #pragma unroll
   for (int k = 0; k < MAX_BEST; ++k) { bi[k] = -1; bd[k] = list_thr; }
+  float worst = list_thr;
   for (int b0 = 0; b0 < nB; b0 += MB_TILE) {
     const int nb = min(MB_TILE, nB - b0);
     __syncthreads();
@@ -513,30 +608,38 @@ __global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict_
     for (int i = threadIdx.x; i < nb; i += MT) sSkip[i] = skipB ? skipB[b0 + i] : 0;
     __syncthreads();
     if (!active) continue;
-    for (int j = 0; j < nb; ++j) {
-      if (sSkip[j]) continue;
-      int dist = 0;
+    for (int j0 = 0; j0 < nb; j0 += 32) {
+      const int j = j0 + lane;
+      float t = 3.0e38f;
+      if (j < nb && !sSkip[j]) {
+        int dist = 0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) dist += __popc(wa[w] ^ sB[j][w]);
-      const float t = (float)dist;
-      float worst = bd[0];
-#pragma unroll
-      for (int k = 1; k < MAX_BEST; ++k) if (k == num_best - 1) worst = bd[k];
-      if (t < worst) {
-        // lower_bound on distance, shift the tail, insert before equal distances
+        for (int w = 0; w < NW; ++w) dist += __popc(wa[w] ^ sB[j][w]);
+        t = (float)dist;
+      }
+      uint32_t mask = __ballot_sync(0xffffffffu, t < worst);
+      while (mask) {
+        const int src = __ffs((int)mask) - 1;
+        const float tt = __shfl_sync(0xffffffffu, t, src);
+        // lower_bound on distance, shift the tail, insert before equal distances (replicated in every lane)
 #pragma unroll
         for (int k = MAX_BEST - 1; k > 0; --k) {
-          if (k < num_best && bd[k - 1] >= t) { bd[k] = bd[k - 1]; bi[k] = bi[k - 1]; }
+          if (k < num_best && bd[k - 1] >= tt) { bd[k] = bd[k - 1]; bi[k] = bi[k - 1]; }
         }
         int pos = 0;
 #pragma unroll
-        for (int k = 0; k < MAX_BEST; ++k) if (k < num_best && bd[k] < t) pos = k + 1;
+        for (int k = 0; k < MAX_BEST; ++k) if (k < num_best && bd[k] < tt) pos = k + 1;
 #pragma unroll
-        for (int k = 0; k < MAX_BEST; ++k) if (k == pos) { bd[k] = t; bi[k] = b0 + j; }
+        for (int k = 0; k < MAX_BEST; ++k) if (k == pos) { bd[k] = tt; bi[k] = b0 + j0 + src; }
+        worst = bd[0];
+#pragma unroll
+        for (int k = 1; k < MAX_BEST; ++k) if (k == num_best - 1) worst = bd[k];
+        // later lanes vote again against the new worst; earlier ones already failed against a larger one
+        mask = __ballot_sync(0xffffffffu, t < worst) & ~((2u << src) - 1u);
       }
     }
   }
-  if (a < nA) {
+  if (a < nA && lane == 0) {
     for (int k = 0; k < num_best; ++k) {
       okb_pair p;
       p.index_a = active ? bi[k] : -1;
@@ -546,39 +649,77 @@ __global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict_
   }
 }
 
-// sequential greedy assignment, A ascending (assignbest, DenseMatcher.cpp:69-110; tail recursion unrolled)
-__global__ void k_assign(const okb_pair* __restrict__ topk, int nA, int nB, int num_best, const uint8_t* __restrict__ skipA,
-                         okb_pair* pairs) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  for (int b = 0; b < nB; ++b) { pairs[b].index_a = -1; pairs[b].distance = 3.402823466e+38f; }
-  for (int a0 = 0; a0 < nA; ++a0) {
-    if (skipA && skipA[a0]) continue;
-    int a = a0, start = 0;
-    while (a >= 0) {
-      int next = -1;
-      for (int idx = start; idx < num_best; ++idx) {
-        const okb_pair cand = topk[(size_t)a * num_best + idx];
-        if (cand.index_a == -1) break;
-        const int b = cand.index_a;
-        if (pairs[b].index_a == -1) { pairs[b].index_a = a; pairs[b].distance = cand.distance; break; }
-        if (cand.distance < pairs[b].distance) {
-          next = pairs[b].index_a;
-          pairs[b].index_a = a; pairs[b].distance = cand.distance;
-          break;
+// Sequential greedy assignment, A ascending (assignbest, DenseMatcher.cpp:69-110; tail recursion unrolled).  The order
+// dependence is the reference's semantics, so the walk itself stays serial; what makes it fast is that nothing on its
+// dependent chain touches global memory: the per-B winners live in shared memory and the lists of 32 consecutive A's
+// are prefetched into registers (one A per lane) and handed to the walk by shuffles.  Displacement chains (rare) read
+// the displaced A's list from global memory.  One warp; all lanes run the same walk, lane 0 stores.
+__global__ void __launch_bounds__(32) k_assign(const okb_pair* __restrict__ topk, int nA, int nB, int num_best, const uint8_t* __restrict__ skipA,
+                                               okb_pair* pairs, int pairs_in_smem) {
+  extern __shared__ okb_pair s_pairs[];
+  okb_pair* P = pairs_in_smem ? s_pairs : pairs;
+  const int lane = threadIdx.x;
+  for (int b = lane; b < nB; b += 32) { P[b].index_a = -1; P[b].distance = 3.402823466e+38f; }
+  __syncwarp();
+  for (int base = 0; base < nA; base += 32) {
+    const int mine = base + lane;
+    int ei[MAX_BEST];
+    float ed[MAX_BEST];
+    bool skip = true;
+#pragma unroll
+    for (int k = 0; k < MAX_BEST; ++k) { ei[k] = -1; ed[k] = 0.f; }
+    if (mine < nA) {
+      skip = skipA && skipA[mine];
+#pragma unroll
+      for (int k = 0; k < MAX_BEST; ++k)
+        if (k < num_best) { const okb_pair e = topk[(size_t)mine * num_best + k]; ei[k] = e.index_a; ed[k] = e.distance; }
+    }
+    const int cnt = min(32, nA - base);
+    for (int i = 0; i < cnt; ++i) {
+      if (__shfl_sync(0xffffffffu, (int)skip, i)) continue;
+      int a = base + i, start = 0;
+      bool from_regs = true;
+      while (a >= 0) {
+        int next = -1;
+        for (int idx = start; idx < num_best; ++idx) {
+          int cb; float cd;
+          if (from_regs) {
+            cb = 0; cd = 0.f;
+#pragma unroll
+            for (int k = 0; k < MAX_BEST; ++k) if (k == idx) { cb = __shfl_sync(0xffffffffu, ei[k], i); cd = __shfl_sync(0xffffffffu, ed[k], i); }
+          } else {
+            const okb_pair e = topk[(size_t)a * num_best + idx];
+            cb = e.index_a; cd = e.distance;
+          }
+          if (cb == -1) break;
+          const okb_pair cur = P[cb];
+          if (cur.index_a == -1) { if (lane == 0) { P[cb].index_a = a; P[cb].distance = cd; } break; }
+          if (cd < cur.distance) {
+            next = cur.index_a;
+            if (lane == 0) { P[cb].index_a = a; P[cb].distance = cd; }
+            break;
+          }
         }
+        __syncwarp();
+        a = next;
+        start = 1;
+        from_regs = false;
       }
-      a = next;
-      start = 1;
     }
   }
+  __syncwarp();
+  if (pairs_in_smem) for (int b = lane; b < nB; b += 32) pairs[b] = P[b];
 }
 
+// Candidate lists (every B with distance < thr, ascending B): warp per A, lanes over 32 consecutive B's; the ballot's
+// prefix population count gives each hit its position, so the CSR rows come out in ascending B order.
 template <int NW>
 __global__ void __launch_bounds__(MT) k_cand_count(const uint32_t* __restrict__ A, int nA, const uint32_t* __restrict__ B, int nB,
                                                    float thr, uint32_t* counts, const uint32_t* row_ptr, uint32_t* col, uint16_t* dist,
                                                    int cap, int fill) {
   __shared__ uint32_t sB[MB_TILE][NW + 1];
-  const int a = blockIdx.x * MT + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = blockIdx.x * MW + warp;
   uint32_t wa[NW];
 #pragma unroll
   for (int w = 0; w < NW; ++w) wa[w] = (a < nA) ? A[(size_t)a * NW + w] : 0u;
@@ -590,24 +731,40 @@ __global__ void __launch_bounds__(MT) k_cand_count(const uint32_t* __restrict__ 
     for (int i = threadIdx.x; i < nb * NW; i += MT) sB[i / NW][i % NW] = B[(size_t)b0 * NW + i];
     __syncthreads();
     if (a >= nA) continue;
-    for (int j = 0; j < nb; ++j) {
-      int d = 0;
+    for (int j0 = 0; j0 < nb; j0 += 32) {
+      const int j = j0 + lane;
+      int d = 1 << 30;
+      if (j < nb) {
+        d = 0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) d += __popc(wa[w] ^ sB[j][w]);
-      if ((float)d < thr) {
-        if (fill && base + n < (uint32_t)cap) { col[base + n] = (uint32_t)(b0 + j); dist[base + n] = (uint16_t)d; }
-        ++n;
+        for (int w = 0; w < NW; ++w) d += __popc(wa[w] ^ sB[j][w]);
       }
+      const bool hit = j < nb && (float)d < thr;
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (fill && hit) {
+        const uint32_t pos = base + n + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (pos < (uint32_t)cap) { col[pos] = (uint32_t)(b0 + j); dist[pos] = (uint16_t)d; }
+      }
+      n += (uint32_t)__popc(m);
     }
   }
-  if (!fill && a < nA) counts[a] = n;
+  if (!fill && a < nA && lane == 0) counts[a] = n;
 }
 
-__global__ void k_exclusive_scan(const uint32_t* counts, int n, uint32_t* row_ptr) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint32_t s = 0;
-  for (int i = 0; i < n; ++i) { row_ptr[i] = s; s += counts[i]; }
-  row_ptr[n] = s;
+// exclusive scan of the per-A counts (one CTA, 1024 threads, chunks of 1024 with a running carry)
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* counts, int n, uint32_t* row_ptr) {
+  __shared__ int s_warp[32];
+  int run = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = (i < n) ? (int)counts[i] : 0;
+    int total;
+    const int ex = uni_block_scan(v, s_warp, &total);
+    if (i < n) row_ptr[i] = (uint32_t)(run + ex);
+    run += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) row_ptr[n] = (uint32_t)run;
 }
 }  // namespace
 
@@ -660,10 +817,15 @@ extern "C" int okb_hamming_match(okb_ctx* c, const uint8_t* A, int nA, const uin
   const float list_thr = use_ratio ? 3.402823466e+38f : threshold;
   const int nw = desc_bytes / 4;
   if (desc_bytes % 4) { c->set_error("descriptor length must be a multiple of 4"); return OKB_ERR_UNSUPPORTED; }
-  DISPATCH_NW(nw, (k_hamming_topk<NW><<<(nA + MT - 1) / MT, MT, 0, c->stream>>>(
+  DISPATCH_NW(nw, (k_hamming_topk<NW><<<(nA + MW - 1) / MW, MT, 0, c->stream>>>(
                       reinterpret_cast<const uint32_t*>(F->d_A), nA, reinterpret_cast<const uint32_t*>(F->d_B), nB, dSA, dSB, list_thr,
                       num_best, F->d_topk)));
-  k_assign<<<1, 32, 0, c->stream>>>(F->d_topk, nA, nB, num_best, dSA, F->d_pairs);
+  {
+    const size_t sm_pairs = sizeof(okb_pair) * (size_t)nB;
+    const int in_smem = sm_pairs <= 96 * 1024 ? 1 : 0;
+    if (in_smem && sm_pairs > 48 * 1024 - 64) FE_CUDA(c, cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pairs));
+    k_assign<<<1, 32, in_smem ? sm_pairs : 0, c->stream>>>(F->d_topk, nA, nB, num_best, dSA, F->d_pairs, in_smem);
+  }
   c->launches += 2;
   FE_CUDA(c, cudaGetLastError());
   if (out_topk) FE_CUDA(c, cudaMemcpyAsync(out_topk, F->d_topk, sizeof(okb_pair) * nA * num_best, cudaMemcpyDeviceToHost, c->stream));
@@ -691,12 +853,12 @@ extern "C" int okb_hamming_candidates(okb_ctx* c, const uint8_t* A, int nA, cons
   uint32_t* d_counts = F->d_rowptr + nA + 1;
   const int nw = desc_bytes / 4;
   if (desc_bytes % 4) { c->set_error("descriptor length must be a multiple of 4"); return OKB_ERR_UNSUPPORTED; }
-  DISPATCH_NW(nw, (k_cand_count<NW><<<(nA + MT - 1) / MT, MT, 0, c->stream>>>(
+  DISPATCH_NW(nw, (k_cand_count<NW><<<(nA + MW - 1) / MW, MT, 0, c->stream>>>(
                       reinterpret_cast<const uint32_t*>(F->d_A), nA, reinterpret_cast<const uint32_t*>(F->d_B), nB, threshold, d_counts,
                       nullptr, nullptr, nullptr, 0, 0)));
-  k_exclusive_scan<<<1, 32, 0, c->stream>>>(d_counts, nA, F->d_rowptr);
+  k_exclusive_scan<<<1, 1024, 0, c->stream>>>(d_counts, nA, F->d_rowptr);
   if (cap > 0) {
-    DISPATCH_NW(nw, (k_cand_count<NW><<<(nA + MT - 1) / MT, MT, 0, c->stream>>>(
+    DISPATCH_NW(nw, (k_cand_count<NW><<<(nA + MW - 1) / MW, MT, 0, c->stream>>>(
                         reinterpret_cast<const uint32_t*>(F->d_A), nA, reinterpret_cast<const uint32_t*>(F->d_B), nB, threshold, d_counts,
                         F->d_rowptr, F->d_col, F->d_dist, cap, 1)));
   }

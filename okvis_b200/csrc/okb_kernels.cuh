@@ -220,7 +220,10 @@ __host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_im
   return b;
 }
 
-__global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict__ wins, int win_first, okb_solve_options opt,
+// NT = 256: two CTAs per SM (batched throughput); NT = 512: one CTA per SM with twice the threads for small batches
+// (latency: the parallel phases -- assembly, trailing updates, landmark back-substitution -- run twice as wide).
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* __restrict__ wins, int win_first, okb_solve_options opt,
                                                         int chol_in_smem) {
   const WinDev& W = wins[win_first + blockIdx.x];
   SolverState* st = W.st;
@@ -261,8 +264,8 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
   // lower triangle; an appended row carries the right-hand side through the factorisation); windows whose system
   // does not fit keep it in global memory.
   double* Hd = chol_in_smem ? s_big : W.Hd;
-  for (int i = tid; i < (int)tri_row(d); i += S_THREADS) Hd[i] = 0.0;
-  for (int i = tid; i < d; i += S_THREADS) gd[i] = 0.0;
+  for (int i = tid; i < (int)tri_row(d); i += NT) Hd[i] = 0.0;
+  for (int i = tid; i < d; i += NT) gd[i] = 0.0;
   __syncthreads();
   double cost_dense_local = 0.0;   // accumulated by thread 0
   // IMU terms were evaluated by k_imu (one warp per term); add their 30x30 blocks term by term
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
     const okb_imu_term& T = W.imu_terms[t];
     const double* out = W.imu_out + (size_t)t * kImuOut;
     const int offs[4] = {6 * (int)T.pose0, dc + 9 * (int)T.sb0, 6 * (int)T.pose1, dc + 9 * (int)T.sb1};
-    for (int e = tid; e < 930; e += S_THREADS) {
+    for (int e = tid; e < 930; e += NT) {
       if (e < 900) {
         const int a = e / 30, b = e % 30;
         const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
   if (W.marg_n > 0) {
     const int n = W.marg_n;
     // Delta chi
-    for (int b = tid; b < W.marg_nb; b += S_THREADS) {
+    for (int b = tid; b < W.marg_nb; b += NT) {
       const int kind = W.marg_kind[b], col = W.marg_col[b], xo = W.marg_off[b];
       if (col < 0) continue;
       if (kind == OKB_BLOCK_SPEED_BIAS) {
@@ -311,13 +314,13 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       }
     }
     __syncthreads();
-    for (int r0 = tid; r0 < n; r0 += S_THREADS) {
+    for (int r0 = tid; r0 < n; r0 += NT) {
       double s = W.marg_e0[r0];
       for (int c = 0; c < n; ++c) s += W.marg_J[(size_t)r0 * n + c] * s_dchi[c];
       s_me[r0] = s;
     }
     __syncthreads();
-    for (int c = tid; c < n; c += S_THREADS) {   // J^T e
+    for (int c = tid; c < n; c += NT) {   // J^T e
       double s = 0;
       for (int r0 = 0; r0 < n; ++r0) s += W.marg_J[(size_t)r0 * n + c] * s_me[r0];
       s_mJte[c] = s;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       double Bi[9], Bj[9];
       if (ki == OKB_BLOCK_POSE) marg_pose_rot_block(W.marg_x0 + W.marg_off[bi], W.pose_c + 7 * W.marg_idx[bi], Bi);
       if (kj == OKB_BLOCK_POSE) marg_pose_rot_block(W.marg_x0 + W.marg_off[bj], W.pose_c + 7 * W.marg_idx[bj], Bj);
-      for (int e = tid; e < mi * mj; e += S_THREADS) {
+      for (int e = tid; e < mi * mj; e += NT) {
         const int a = e / mj, b = e % mj;
         // (B_i^T H0_ij B_j)[a][b]
         double s = 0;
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
         hd_add(Hd, (oi + a), oj + b, s);
       }
       if (bi == bj) {
-        for (int a = tid; a < mi; a += S_THREADS) {
+        for (int a = tid; a < mi; a += NT) {
           double s = 0;
           if (ki == OKB_BLOCK_POSE && a >= 3) { for (int k = 0; k < 3; ++k) s += Bi[k * 3 + (a - 3)] * s_mJte[ci + 3 + k]; }
           else s = s_mJte[ci + a];
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       return;
     }
     const int nA = dcp * dcp, nH = K * kPartH;
-    for (int i = tid; i < nA + nH + 1; i += S_THREADS) {
+    for (int i = tid; i < nA + nH + 1; i += NT) {
       double s = 0.0;
       for (int r = 0; r < world; ++r) s += __ldcg(shard_box(W, me, par, r) + i);
       if (i < nA) W.partA[i] = s;
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
     stepn2_lm += W.partH[(size_t)i * kPartH + 28];
   }
   // H_pp / g_p block contributions
-  for (int i = tid; i < 27 * K; i += S_THREADS) {
+  for (int i = tid; i < 27 * K; i += NT) {
     const int e = i / K, f = i % K, o = 6 * f;
     double s = 0;
     for (int c = 0; c < n_cx; ++c) s += W.partH[((size_t)c * K + f) * kPartH + e];
@@ -497,16 +500,16 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
   // ================= phase 4: adopt the speculative linearisation =================
   if (adopt) {
     // commit dense parameters
-    for (int i = tid; i < 7 * K; i += S_THREADS) W.pose[i] = W.pose_c[i];
-    for (int i = tid; i < 9 * W.NSB; i += S_THREADS) W.sb[i] = W.sb_c[i];
+    for (int i = tid; i < 7 * K; i += NT) W.pose[i] = W.pose_c[i];
+    for (int i = tid; i < 9 * W.NSB; i += NT) W.sb[i] = W.sb_c[i];
     cur = spec;
     __syncthreads();
     if (tid == 0) st->cur = cur;
-    for (int f = tid; f < K; f += S_THREADS) {
+    for (int f = tid; f < K; f += NT) {
       s_tws[4 * f] = W.pose[7 * f]; s_tws[4 * f + 1] = W.pose[7 * f + 1]; s_tws[4 * f + 2] = W.pose[7 * f + 2];
     }
     // metric E_d (and, once, the Jacobi scale)
-    for (int i = tid; i < d; i += S_THREADS) {
+    for (int i = tid; i < d; i += NT) {
       const double hjj = Hd[tri_row(i) + i];
       double sc;
       if (mode == MODE_INIT) { sc = 1.0 / (1.0 + sqrt(hjj)); W.scale_d[i] = sc; }
@@ -528,7 +531,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
     if (!skip_solve) {
       // VHV (dense-dense part): v^T H v
       double vhv_loc = 0.0;
-      for (int i = tid; i < d; i += S_THREADS) {     // v^T H v from the lower triangle
+      for (int i = tid; i < d; i += NT) {     // v^T H v from the lower triangle
         const double* hrow = Hd + tri_row(i);
         double s = 0;
         for (int j = 0; j < i; ++j) s += hrow[j] * s_v[j];
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       // reduced system M = Hd + mu E - [Sacc], rhs = g - [sum Y z]
       double* Mx = chol_in_smem ? s_big : W.chol;
       const double mu = st->mu;
-      for (int i = tid; i < d * d; i += S_THREADS) {
+      for (int i = tid; i < d * d; i += NT) {
         const int r0 = i / d, c0 = i % d;
         if (c0 > r0) continue;                      // the factorisation only references the lower triangle
         double v = Hd[tri_row(r0) + c0];            // in place when the system lives in shared memory
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
         }
         Mx[tri_row(r0) + c0] = v;
       }
-      for (int i = tid; i < d; i += S_THREADS) {
+      for (int i = tid; i < d; i += NT) {
         double v = s_g[i];
         if (i < dc) {
           v -= W.partA[(size_t)dc * dcp + i];
@@ -562,10 +565,10 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       if (!chol_fail) chol_fail = block_cholesky(Mx, d, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8);
       PHASE_MARK(3);
       if (!chol_fail) {
-        for (int i = tid; i < d; i += S_THREADS) s_tmp[i] = Mx[tri_row(d) + i];
+        for (int i = tid; i < d; i += NT) s_tmp[i] = Mx[tri_row(d) + i];
         __syncthreads();
         block_cholesky_backward(Mx, d, s_col, s_tmp);
-        for (int i = tid; i < d; i += S_THREADS) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
+        for (int i = tid; i < d; i += NT) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
         __syncthreads();
       }
     }
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
     int bad = 0;
     const double* gl_ = W.lm_g[cur];
     const double* El_ = W.lm_E[cur];
-    for (int l = tid; l < L; l += S_THREADS) {
+    for (int l = tid; l < L; l += NT) {
       const double4 X = *reinterpret_cast<const double4*>(W.lm_c + 4 * (size_t)l);
       *reinterpret_cast<double4*>(W.lm + 4 * (size_t)l) = X;
       xn2 += X.x * X.x + X.y * X.y + X.z * X.z + X.w * X.w;
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       VHV += hv;
       gmax = fmax(gmax, fmax(fabs(g0), fmax(fabs(g1), fabs(g2))));
     }
-    for (int i = tid; i < d; i += S_THREADS) {
+    for (int i = tid; i < d; i += NT) {
       if (chol_fail || !dense_owner) break;
       const double g = s_g[i], E = s_E[i];
       if (skip_solve) { gmax = fmax(gmax, fabs(g)); continue; }
@@ -631,8 +634,8 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
       gmax = fmax(gmax, fabs(g));
     }
     if (dense_owner) {
-      for (int i = tid; i < 7 * K; i += S_THREADS) xn2 += W.pose[i] * W.pose[i];
-      for (int i = tid; i < 9 * W.NSB; i += S_THREADS) xn2 += W.sb[i] * W.sb[i];
+      for (int i = tid; i < 7 * K; i += NT) xn2 += W.pose[i] * W.pose[i];
+      for (int i = tid; i < 9 * W.NSB; i += NT) xn2 += W.sb[i] * W.sb[i];
     }
     xs[0] = block_sum(N2, sh->red);
     xs[1] = block_sum(GU, sh->red);
@@ -756,10 +759,10 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
     const double a = st->a, b = st->b;
     const double* gcur = W.gd[cur];
     const double* Ecur = W.Ed[cur];
-    for (int i = tid; i < d; i += S_THREADS) s_delta[i] = (what == 1) ? (a * gcur[i] / Ecur[i] - b * W.ud[i]) : 0.0;
+    for (int i = tid; i < d; i += NT) s_delta[i] = (what == 1) ? (a * gcur[i] / Ecur[i] - b * W.ud[i]) : 0.0;
     __syncthreads();
     double sn2 = 0.0;
-    for (int f = tid; f < K; f += S_THREADS) {
+    for (int f = tid; f < K; f += NT) {
       double o[7];
       if (what == 1) pose_plus(W.pose + 7 * f, s_delta + 6 * f, o);
       else for (int k = 0; k < 7; ++k) o[k] = W.pose[7 * f + k];
@@ -769,14 +772,14 @@ __global__ void __launch_bounds__(S_THREADS, 2) k_solve(const WinDev* __restrict
         W.pose_c[7 * f + k] = o[k];
       }
     }
-    for (int i = tid; i < 9 * W.NSB; i += S_THREADS) {
+    for (int i = tid; i < 9 * W.NSB; i += NT) {
       const double dlt = s_delta[dc + i];
       W.sb_c[i] = W.sb[i] + dlt;
       sn2 += dlt * dlt;
     }
     sn2 = block_sum(sn2, sh->red);
     if (tid == 0) st->cand_step_norm2_dense = sn2;
-    build_slot_ctx(W, tid, S_THREADS);        // (frame, camera) contexts of the next linearisation
+    build_slot_ctx(W, tid, NT);        // (frame, camera) contexts of the next linearisation
   }
   PHASE_MARK(6);
 #undef PHASE_MARK
