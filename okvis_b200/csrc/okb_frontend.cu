@@ -10,6 +10,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -92,6 +94,7 @@ struct SlotBuffers {
   unsigned long long* d_keys = nullptr;
   int* d_count = nullptr;          // [0] candidates, [1] accepted
   uint32_t *d_cell_start = nullptr, *d_cell_cur = nullptr, *d_order = nullptr, *d_acc = nullptr;   // uniformity scratch
+  uint32_t* d_rounds = nullptr;      // [4][kMaxCand]: blocker | alive list 0 | alive list 1 | pending
   uint8_t* d_state = nullptr;
   int max_cells = 0;
   okb_keypoint* d_kp = nullptr;
@@ -121,16 +124,22 @@ struct okb_frontend_state {
   uint32_t *d_rowptr = nullptr, *d_col = nullptr;
   uint16_t* d_dist = nullptr;
   size_t cap_rows = 0, cap_cand = 0;
+  uint8_t* h_stage = nullptr;      // pinned staging: descriptors in, top-k lists + winners out
+  size_t h_stage_cap = 0;
+  uint8_t* d_io = nullptr;         // device mirror of the staging buffer
+  size_t d_io_cap = 0;
   std::mutex match_mtx;
 };
 
 void okb_frontend_release(okb_ctx* c) {
   if (!c->frontend) return;
   okb_frontend_state* F = c->frontend;
+  if (F->h_stage) cudaFreeHost(F->h_stage);
+  cudaFree(F->d_io);
   for (auto& s : F->slots) {
     if (s.stream) cudaStreamDestroy(s.stream);
     cudaFree(s.d_img); cudaFree(s.d_score); cudaFree(s.d_integral); cudaFree(s.d_keys);
-    cudaFree(s.d_cell_start); cudaFree(s.d_cell_cur); cudaFree(s.d_order); cudaFree(s.d_acc); cudaFree(s.d_state);
+    cudaFree(s.d_cell_start); cudaFree(s.d_cell_cur); cudaFree(s.d_order); cudaFree(s.d_acc); cudaFree(s.d_state); cudaFree(s.d_rounds);
     cudaFree(s.d_count); cudaFree(s.d_kp); cudaFree(s.d_desc);
     if (s.h_img) cudaFreeHost(s.h_img);
     if (s.h_kp) cudaFreeHost(s.h_kp);
@@ -244,6 +253,7 @@ struct UniScratch {
   uint32_t* order;        // [cap] candidate indices grouped by cell
   uint8_t* state;         // [cap] 0 alive, 1 pending, 2 accepted, 3 dead
   uint32_t* acc;          // [cap] accepted candidates
+  uint32_t *blocker, *list0, *list1, *pend;   // [cap] each: rounds scratch
   int max_cells;
 };
 __device__ __forceinline__ int uni_block_scan(int v, int* s_warp, int* total) {     // exclusive scan over the CTA
@@ -295,12 +305,26 @@ __global__ void __launch_bounds__(UT) k_uniformity(const unsigned long long* __r
   __syncthreads();
   for (int i = tid; i < n; i += UT) { int x, y; px(i, x, y); const uint32_t pos = atomicAdd(&sc.cell_cur[(y / cs) * gw + x / cs], 1u); sc.order[pos] = (uint32_t)i; }
   __syncthreads();
-  // ---- rounds
-  int alive = n;
+  // ---- rounds over a shrinking list of live candidates (lists A / B alternate; appended with a shared-memory
+  // counter: the ORDER inside a list is arbitrary, the SET is not, and only the set matters).  blocker[i] remembers the
+  // live higher-priority neighbour that blocked i: while it lives, i stays blocked without another neighbourhood scan.
+  uint32_t* blocker = sc.blocker;
+  uint32_t* listA = sc.list0;
+  uint32_t* listB = sc.list1;
+  uint32_t* pend = sc.pend;
+  __shared__ int s_alive, s_pend;
+  for (int i = tid; i < n; i += UT) listA[i] = (uint32_t)i;
+  int alive = n, rounds = 0;
+  bool first_round = true;
+  __syncthreads();
   while (alive > 0) {
+    ++rounds;
+    if (tid == 0) { s_alive = 0; s_pend = 0; }
+    __syncthreads();
     // accept: no live (alive or pending) neighbour with a larger key
-    for (int i = tid; i < n; i += UT) {
-      if (sc.state[i] != 0) continue;
+    for (int t = tid; t < alive; t += UT) {
+      const int i = (int)listA[t];
+      if (!first_round && sc.state[blocker[i]] <= 1) continue;
       int x, y; px(i, x, y);
       const unsigned long long ki = keys[i];
       bool blocked = false;
@@ -313,39 +337,42 @@ __global__ void __launch_bounds__(UT) k_uniformity(const unsigned long long* __r
             if (keys[j] <= ki || sc.state[j] > 1) continue;
             int xj, yj; px(j, xj, yj);
             const long long dx = xj - x, dy = yj - y;
-            if (dx * dx + dy * dy < r2i) { blocked = true; break; }
+            if (dx * dx + dy * dy < r2i) { blocked = true; blocker[i] = (uint32_t)j; break; }
           }
         }
-      if (!blocked) sc.state[i] = 1;
+      if (!blocked) { sc.state[i] = 1; pend[atomicAdd(&s_pend, 1)] = (uint32_t)i; }
     }
     __syncthreads();
-    // kill: alive candidates next to a pending one
-    int still = 0;
-    for (int i = tid; i < n; i += UT) {
-      if (sc.state[i] != 0) continue;
+    // kill: every pending candidate marks its live neighbours dead (two pending candidates are never neighbours);
+    // a warp per pending candidate, lanes over the candidates of the 3x3 cells
+    const int n_pend = s_pend;
+    for (int t = tid >> 5; t < n_pend; t += UT / 32) {
+      const int i = (int)pend[t];
       int x, y; px(i, x, y);
-      bool dead = false;
       const int cx = x / cs, cy = y / cs;
-      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1) && !dead; ++yy)
-        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, gw - 1) && !dead; ++xx) {
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1); ++yy)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, gw - 1); ++xx) {
           const uint32_t e = sc.cell_start[yy * gw + xx + 1];
-          for (uint32_t q = sc.cell_start[yy * gw + xx]; q < e; ++q) {
+          for (uint32_t q = sc.cell_start[yy * gw + xx] + (tid & 31); q < e; q += 32) {
             const int j = (int)sc.order[q];
-            if (sc.state[j] != 1) continue;
+            if (sc.state[j] != 0) continue;
             int xj, yj; px(j, xj, yj);
             const long long dx = xj - x, dy = yj - y;
-            if (dx * dx + dy * dy < r2i) { dead = true; break; }
+            if (dx * dx + dy * dy < r2i) sc.state[j] = 3;
           }
         }
-      if (dead) sc.state[i] = 3; else ++still;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += UT) if (sc.state[i] == 1) sc.state[i] = 2;
-    if (tid == 0) s_n = 0;
+    for (int t = tid; t < alive; t += UT) {
+      const int i = (int)listA[t];
+      const uint8_t st = sc.state[i];
+      if (st == 1) sc.state[i] = 2;
+      else if (st == 0) listB[atomicAdd(&s_alive, 1)] = (uint32_t)i;
+    }
     __syncthreads();
-    if (still) atomicAdd(&s_n, still);           // integer sum: order independent
-    __syncthreads();
-    alive = s_n;
+    alive = s_alive;
+    uint32_t* tl = listA; listA = listB; listB = tl;
+    first_round = false;
     __syncthreads();
   }
   // ---- accepted set -> score order, first max_kp
@@ -366,7 +393,7 @@ __global__ void __launch_bounds__(UT) k_uniformity(const unsigned long long* __r
       kps[rank] = kp;
     }
   }
-  if (tid == 0) *n_out = min(m, max_kp);
+  if (tid == 0) { *n_out = min(m, max_kp); n_out[1] = rounds; }
 }
 
 // integral image (H+1) x (W+1), uint32
@@ -393,21 +420,28 @@ __global__ void __launch_bounds__(128) k_integral_rows(const uint8_t* __restrict
     carry += __shfl_sync(0xffffffffu, v, 31);
   }
 }
-// column pass: one thread per column; 16 independent loads are in flight per step instead of one dependent load
-__global__ void __launch_bounds__(64) k_integral_cols(int W, int H, uint32_t* II) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x > W) return;
-  uint32_t s = 0;
-  for (int y0 = 0; y0 <= H; y0 += 16) {
-    uint32_t v[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = (y0 + k <= H) ? II[(size_t)(y0 + k) * (W + 1) + x] : 0u;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      s += v[k];
-      if (y0 + k <= H) II[(size_t)(y0 + k) * (W + 1) + x] = s;
+// column pass: a CTA owns 32 columns; its 16 warps split the rows into 16 segments (lanes = columns: every access is a
+// 128-byte row).  Pass 1 sums each segment, the segment offsets are combined through shared memory, pass 2 writes the
+// running sums.  Integer arithmetic: any summation order gives the same bits.
+constexpr int IC_SEG = 16;
+__global__ void __launch_bounds__(32 * IC_SEG) k_integral_cols(int W, int H, uint32_t* II) {
+  __shared__ uint32_t seg[IC_SEG][33];
+  const int lane = threadIdx.x & 31, s_ = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + lane;
+  const int rows = H + 1, per = (rows + IC_SEG - 1) / IC_SEG;
+  const int y0 = s_ * per, y1 = min(rows, y0 + per);
+  uint32_t sum = 0;
+  if (x <= W)
+    for (int y = y0; y < y1; ++y) sum += II[(size_t)y * (W + 1) + x];
+  seg[s_][lane] = sum;
+  __syncthreads();
+  uint32_t run = 0;
+  for (int k = 0; k < s_; ++k) run += seg[k][lane];
+  if (x <= W)
+    for (int y = y0; y < y1; ++y) {
+      run += II[(size_t)y * (W + 1) + x];
+      II[(size_t)y * (W + 1) + x] = run;
     }
-  }
 }
 
 __device__ void undistort_gn(const CamIntr& cam, double d0, double d1, double* pu) {
@@ -509,22 +543,23 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   if (!S.stream) FE_CUDA(c, cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
   if (S.W != W || S.H != H) {
     cudaFree(S.d_img); cudaFree(S.d_score); cudaFree(S.d_integral); cudaFree(S.d_keys); cudaFree(S.d_count);
-    cudaFree(S.d_cell_start); cudaFree(S.d_cell_cur); cudaFree(S.d_order); cudaFree(S.d_acc); cudaFree(S.d_state);
+    cudaFree(S.d_cell_start); cudaFree(S.d_cell_cur); cudaFree(S.d_order); cudaFree(S.d_acc); cudaFree(S.d_state); cudaFree(S.d_rounds);
     if (S.h_img) cudaFreeHost(S.h_img);
     if (S.h_count) cudaFreeHost(S.h_count);
     FE_CUDA(c, cudaMalloc(&S.d_img, (size_t)W * H));
     FE_CUDA(c, cudaMalloc(&S.d_score, sizeof(int32_t) * W * H));
     FE_CUDA(c, cudaMalloc(&S.d_integral, sizeof(uint32_t) * (W + 1) * (H + 1)));
     FE_CUDA(c, cudaMalloc(&S.d_keys, sizeof(unsigned long long) * kMaxCand));
-    FE_CUDA(c, cudaMalloc(&S.d_count, sizeof(int) * 2 + sizeof(double) * 4));
+    FE_CUDA(c, cudaMalloc(&S.d_count, sizeof(int) * 4 + sizeof(double) * 4));      // candidates, accepted, rounds, - | gravity direction
     S.max_cells = ((W + 3) / 4) * ((H + 3) / 4);          // smallest cell is 4 px
     FE_CUDA(c, cudaMalloc(&S.d_cell_start, sizeof(uint32_t) * (S.max_cells + 1)));
     FE_CUDA(c, cudaMalloc(&S.d_cell_cur, sizeof(uint32_t) * S.max_cells));
     FE_CUDA(c, cudaMalloc(&S.d_order, sizeof(uint32_t) * kMaxCand));
     FE_CUDA(c, cudaMalloc(&S.d_acc, sizeof(uint32_t) * kMaxCand));
     FE_CUDA(c, cudaMalloc(&S.d_state, kMaxCand));
+    FE_CUDA(c, cudaMalloc(&S.d_rounds, sizeof(uint32_t) * 4 * kMaxCand));
     FE_CUDA(c, cudaMallocHost(&S.h_img, (size_t)W * H));
-    FE_CUDA(c, cudaMallocHost(&S.h_count, sizeof(int) * 2));
+    FE_CUDA(c, cudaMallocHost(&S.h_count, sizeof(int) * 4));
     S.W = W; S.H = H;
   }
   if (S.kp_cap < maxk || S.desc_cap < maxk * prm->desc_bytes) {
@@ -540,27 +575,29 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   for (int y = 0; y < H; ++y) std::memcpy(S.h_img + (size_t)y * W, img + (size_t)y * stride, W);
   cudaStream_t st = S.stream;
   FE_CUDA(c, cudaMemcpyAsync(S.d_img, S.h_img, (size_t)W * H, cudaMemcpyHostToDevice, st));
-  FE_CUDA(c, cudaMemsetAsync(S.d_count, 0, sizeof(int) * 2, st));
+  FE_CUDA(c, cudaMemsetAsync(S.d_count, 0, sizeof(int) * 4, st));
   // gravity direction in the camera frame: R_CW * (0,0,-1)
   double gC[3] = {-R_CW[2], -R_CW[5], -R_CW[8]};
-  double* d_gC = reinterpret_cast<double*>(S.d_count + 2);
+  double* d_gC = reinterpret_cast<double*>(S.d_count + 4);
   FE_CUDA(c, cudaMemcpyAsync(d_gC, gC, sizeof gC, cudaMemcpyHostToDevice, st));
   const dim3 hb(HT_X, HT_Y), hg((W + HT_X - 1) / HT_X, (H + HT_Y - 1) / HT_Y);
   k_harris<<<hg, hb, 0, st>>>(S.d_img, W, H, S.d_score);
   const dim3 nb(32, 8), ng((W + 31) / 32, (H + 7) / 8);
   k_nms<<<ng, nb, 0, st>>>(S.d_score, W, H, (int32_t)std::ceil(prm->absolute_threshold), S.d_keys, S.d_count, kMaxCand);
-  UniScratch us{S.d_cell_start, S.d_cell_cur, S.d_order, S.d_state, S.d_acc, S.max_cells};
+  UniScratch us{S.d_cell_start, S.d_cell_cur, S.d_order, S.d_state, S.d_acc, S.d_rounds, S.d_rounds + kMaxCand, S.d_rounds + 2 * kMaxCand,
+                S.d_rounds + 3 * kMaxCand, S.max_cells};
   k_uniformity<<<1, UT, 0, st>>>(S.d_keys, S.d_count, kMaxCand, W, H, prm->uniformity_radius, maxk, us, S.d_kp, S.d_count + 1);
   k_integral_rows<<<(H + 1 + 3) / 4, 128, 0, st>>>(S.d_img, W, H, S.d_integral);
-  k_integral_cols<<<(W + 1 + 63) / 64, 64, 0, st>>>(W, H, S.d_integral);
+  k_integral_cols<<<(W + 1 + 31) / 32, 32 * IC_SEG, 0, st>>>(W, H, S.d_integral);
   k_describe<<<(maxk + 3) / 4, 128, 0, st>>>(S.d_integral, W, H, *cam, d_gC, prm->rotation_invariance, F->d_half, F->d_pi, F->d_pj,
                                              F->d_lut, prm->desc_bytes, S.d_kp, S.d_count + 1, S.d_desc);
   c->launches += 6;
   FE_CUDA(c, cudaGetLastError());
-  FE_CUDA(c, cudaMemcpyAsync(S.h_count, S.d_count, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+  FE_CUDA(c, cudaMemcpyAsync(S.h_count, S.d_count, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
   FE_CUDA(c, cudaMemcpyAsync(S.h_kp, S.d_kp, sizeof(okb_keypoint) * maxk, cudaMemcpyDeviceToHost, st));
   FE_CUDA(c, cudaMemcpyAsync(S.h_desc, S.d_desc, (size_t)maxk * prm->desc_bytes, cudaMemcpyDeviceToHost, st));
   FE_CUDA(c, cudaStreamSynchronize(st));
+  { static const bool dbg = getenv("OKB_FE_DEBUG") != nullptr; if (dbg) fprintf(stderr, "[okb frontend] candidates %d accepted %d uniformity rounds %d\n", S.h_count[0], S.h_count[1], S.h_count[2]); }
   if (S.h_count[0] > kMaxCand) { c->set_error("too many corner candidates"); return OKB_ERR_CAPACITY; }
   const int n = S.h_count[1];
   std::memcpy(out_kp, S.h_kp, sizeof(okb_keypoint) * n);
@@ -650,65 +687,72 @@ __global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict_
 }
 
 // Sequential greedy assignment, A ascending (assignbest, DenseMatcher.cpp:69-110; tail recursion unrolled).  The order
-// dependence is the reference's semantics, so the walk itself stays serial; what makes it fast is that nothing on its
-// dependent chain touches global memory: the per-B winners live in shared memory and the lists of 32 consecutive A's
-// are prefetched into registers (one A per lane) and handed to the walk by shuffles.  Displacement chains (rare) read
-// the displaced A's list from global memory.  One warp; all lanes run the same walk, lane 0 stores.
-__global__ void __launch_bounds__(32) k_assign(const okb_pair* __restrict__ topk, int nA, int nB, int num_best, const uint8_t* __restrict__ skipA,
-                                               okb_pair* pairs, int pairs_in_smem) {
-  extern __shared__ okb_pair s_pairs[];
-  okb_pair* P = pairs_in_smem ? s_pairs : pairs;
-  const int lane = threadIdx.x;
-  for (int b = lane; b < nB; b += 32) { P[b].index_a = -1; P[b].distance = 3.402823466e+38f; }
-  __syncwarp();
-  for (int base = 0; base < nA; base += 32) {
-    const int mine = base + lane;
-    int ei[MAX_BEST];
-    float ed[MAX_BEST];
-    bool skip = true;
-#pragma unroll
-    for (int k = 0; k < MAX_BEST; ++k) { ei[k] = -1; ed[k] = 0.f; }
-    if (mine < nA) {
-      skip = skipA && skipA[mine];
-#pragma unroll
-      for (int k = 0; k < MAX_BEST; ++k)
-        if (k < num_best) { const okb_pair e = topk[(size_t)mine * num_best + k]; ei[k] = e.index_a; ed[k] = e.distance; }
+// dependence is the reference's semantics, so the walk itself stays serial (thread 0); what makes it fast is that
+// nothing on its dependent chain touches global memory: the per-B winners live in shared memory and the top-k lists
+// are staged 256 A's at a time by the whole CTA.  Displacement chains read the displaced A's list from shared memory
+// when it is in the staged chunk, else from global memory (rare).
+// Uncontested A's leave the walk before it starts: if A's first choice b is listed by no other A (count[b] == 1 over all
+// list entries of all non-skipped A's), then b is free when A's turn comes, A takes it, nobody can displace A and A
+// touches no other b -- its outcome is independent of the order.  Those are assigned in parallel; only A's whose first
+// choice is contested walk serially (typically a small fraction).
+constexpr int AS_T = 256, AS_CHUNK = 256;
+__global__ void __launch_bounds__(AS_T) k_assign(const okb_pair* __restrict__ topk, int nA, int nB, int num_best, const uint8_t* __restrict__ skipA,
+                                                 okb_pair* pairs, uint8_t* done /* [nA] scratch */, int in_smem) {
+  extern __shared__ okb_pair s_dyn[];
+  okb_pair* s_top = s_dyn;                                   // [AS_CHUNK][num_best]
+  okb_pair* P = in_smem ? s_dyn + (size_t)AS_CHUNK * MAX_BEST : pairs;
+  int* cnt = in_smem ? reinterpret_cast<int*>(P + nB) : nullptr;   // [nB] how many A's list this b
+  __shared__ uint8_t s_skip[AS_CHUNK];
+  const int tid = threadIdx.x;
+  for (int b = tid; b < nB; b += AS_T) { P[b].index_a = -1; P[b].distance = 3.402823466e+38f; if (cnt) cnt[b] = 0; }
+  for (int a = tid; a < nA; a += AS_T) done[a] = 0;
+  __syncthreads();
+  if (cnt) {
+    for (int e = tid; e < nA * num_best; e += AS_T) {
+      const int a = e / num_best;
+      if (skipA && skipA[a]) continue;
+      const int b = topk[e].index_a;
+      if (b >= 0) atomicAdd(&cnt[b], 1);
     }
-    const int cnt = min(32, nA - base);
-    for (int i = 0; i < cnt; ++i) {
-      if (__shfl_sync(0xffffffffu, (int)skip, i)) continue;
+    __syncthreads();
+    for (int a = tid; a < nA; a += AS_T) {
+      if (skipA && skipA[a]) continue;
+      const okb_pair first = topk[(size_t)a * num_best];
+      if (first.index_a >= 0 && cnt[first.index_a] == 1) { P[first.index_a].index_a = a; P[first.index_a].distance = first.distance; done[a] = 1; }
+    }
+  }
+  for (int base = 0; base < nA; base += AS_CHUNK) {
+    const int n_in = min(AS_CHUNK, nA - base);
+    __syncthreads();
+    for (int e = tid; e < n_in * num_best; e += AS_T) s_top[e] = topk[(size_t)base * num_best + e];
+    for (int i = tid; i < n_in; i += AS_T) s_skip[i] = (skipA ? skipA[base + i] : 0) | done[base + i];
+    __syncthreads();
+    if (tid != 0) continue;
+    for (int i = 0; i < n_in; ++i) {
+      if (s_skip[i]) continue;
       int a = base + i, start = 0;
-      bool from_regs = true;
       while (a >= 0) {
         int next = -1;
+        const okb_pair* lst = (a >= base && a < base + n_in) ? s_top + (size_t)(a - base) * num_best : topk + (size_t)a * num_best;
         for (int idx = start; idx < num_best; ++idx) {
-          int cb; float cd;
-          if (from_regs) {
-            cb = 0; cd = 0.f;
-#pragma unroll
-            for (int k = 0; k < MAX_BEST; ++k) if (k == idx) { cb = __shfl_sync(0xffffffffu, ei[k], i); cd = __shfl_sync(0xffffffffu, ed[k], i); }
-          } else {
-            const okb_pair e = topk[(size_t)a * num_best + idx];
-            cb = e.index_a; cd = e.distance;
-          }
-          if (cb == -1) break;
-          const okb_pair cur = P[cb];
-          if (cur.index_a == -1) { if (lane == 0) { P[cb].index_a = a; P[cb].distance = cd; } break; }
-          if (cd < cur.distance) {
+          const okb_pair cand = lst[idx];
+          if (cand.index_a == -1) break;
+          const int b = cand.index_a;
+          const okb_pair cur = P[b];
+          if (cur.index_a == -1) { P[b].index_a = a; P[b].distance = cand.distance; break; }
+          if (cand.distance < cur.distance) {
             next = cur.index_a;
-            if (lane == 0) { P[cb].index_a = a; P[cb].distance = cd; }
+            P[b].index_a = a; P[b].distance = cand.distance;
             break;
           }
         }
-        __syncwarp();
         a = next;
         start = 1;
-        from_regs = false;
       }
     }
   }
-  __syncwarp();
-  if (pairs_in_smem) for (int b = lane; b < nB; b += 32) pairs[b] = P[b];
+  __syncthreads();
+  if (in_smem) for (int b = tid; b < nB; b += AS_T) pairs[b] = P[b];
 }
 
 // Candidate lists (every B with distance < thr, ascending B): warp per A, lanes over 32 consecutive B's; the ballot's
@@ -799,38 +843,67 @@ static int upload_descriptors(okb_ctx* c, okb_frontend_state* F, const uint8_t* 
   return OKB_OK;
 }
 
+static int ensure_io(okb_ctx* c, okb_frontend_state* F, size_t bytes) {
+  if (F->h_stage_cap < bytes) {
+    if (F->h_stage) cudaFreeHost(F->h_stage);
+    F->h_stage = nullptr; F->h_stage_cap = 0;
+    FE_CUDA(c, cudaMallocHost(&F->h_stage, bytes));
+    F->h_stage_cap = bytes;
+  }
+  if (F->d_io_cap < bytes) {
+    cudaFree(F->d_io);
+    F->d_io = nullptr; F->d_io_cap = 0;
+    FE_CUDA(c, cudaMalloc(&F->d_io, bytes));
+    F->d_io_cap = bytes;
+  }
+  return OKB_OK;
+}
+
 extern "C" int okb_hamming_match(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, const uint8_t* skipA,
                                  const uint8_t* skipB, float threshold, int num_best, int use_ratio, float ratio_threshold,
                                  okb_pair* out_topk, okb_pair* out_pairs) {
   (void)ratio_threshold;   // the ratio test itself belongs to the serial epilogue on the caller's side
   if (!c || !A || !B || nA < 1 || nB < 1 || num_best < 1 || num_best > MAX_BEST || !out_pairs) return OKB_ERR_INVALID_ARG;
+  if (desc_bytes % 4) { c->set_error("descriptor length must be a multiple of 4"); return OKB_ERR_UNSUPPORTED; }
   cudaSetDevice(c->device);
   okb_frontend_state* F = fe(c);
   std::lock_guard<std::mutex> lk(F->match_mtx);
-  int rc = upload_descriptors(c, F, A, nA, B, nB, desc_bytes, skipA, skipB);
+  // one pinned staging buffer, one copy in, one copy out:  [A | B | skipA | skipB | pad]  ...  [top-k lists | winners]
+  auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  const size_t oA = 0, oB = up16((size_t)nA * desc_bytes), oSA = oB + up16((size_t)nB * desc_bytes), oSB = oSA + up16((size_t)nA);
+  const size_t in_bytes = oSB + up16((size_t)nB);
+  const size_t oT = in_bytes, oP = oT + sizeof(okb_pair) * (size_t)nA * num_best, oD = oP + sizeof(okb_pair) * (size_t)nB, total = oD + up16((size_t)nA);
+  int rc = ensure_io(c, F, total);
   if (rc) return rc;
-  if ((rc = grow(c, &F->d_topk, &F->cap_topk, (size_t)nA * num_best))) return rc;
-  if ((rc = grow(c, &F->d_pairs, &F->cap_pairs, (size_t)nB))) return rc;
-  const uint8_t* dSA = skipA ? F->d_A + (size_t)nA * desc_bytes : nullptr;
-  const uint8_t* dSB = skipB ? F->d_B + (size_t)nB * desc_bytes : nullptr;
+  std::memcpy(F->h_stage + oA, A, (size_t)nA * desc_bytes);
+  std::memcpy(F->h_stage + oB, B, (size_t)nB * desc_bytes);
+  if (skipA) std::memcpy(F->h_stage + oSA, skipA, nA);
+  if (skipB) std::memcpy(F->h_stage + oSB, skipB, nB);
+  FE_CUDA(c, cudaMemcpyAsync(F->d_io, F->h_stage, in_bytes, cudaMemcpyHostToDevice, c->stream));
+  const uint8_t* dSA = skipA ? F->d_io + oSA : nullptr;
+  const uint8_t* dSB = skipB ? F->d_io + oSB : nullptr;
+  okb_pair* d_topk = reinterpret_cast<okb_pair*>(F->d_io + oT);
+  okb_pair* d_pairs = reinterpret_cast<okb_pair*>(F->d_io + oP);
   // DenseMatcher.hpp(impl):188-193: with the ratio test the lists are built without a threshold
   const float list_thr = use_ratio ? 3.402823466e+38f : threshold;
   const int nw = desc_bytes / 4;
-  if (desc_bytes % 4) { c->set_error("descriptor length must be a multiple of 4"); return OKB_ERR_UNSUPPORTED; }
   DISPATCH_NW(nw, (k_hamming_topk<NW><<<(nA + MW - 1) / MW, MT, 0, c->stream>>>(
-                      reinterpret_cast<const uint32_t*>(F->d_A), nA, reinterpret_cast<const uint32_t*>(F->d_B), nB, dSA, dSB, list_thr,
-                      num_best, F->d_topk)));
+                      reinterpret_cast<const uint32_t*>(F->d_io + oA), nA, reinterpret_cast<const uint32_t*>(F->d_io + oB), nB, dSA, dSB, list_thr,
+                      num_best, d_topk)));
   {
-    const size_t sm_pairs = sizeof(okb_pair) * (size_t)nB;
-    const int in_smem = sm_pairs <= 96 * 1024 ? 1 : 0;
-    if (in_smem && sm_pairs > 48 * 1024 - 64) FE_CUDA(c, cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pairs));
-    k_assign<<<1, 32, in_smem ? sm_pairs : 0, c->stream>>>(F->d_topk, nA, nB, num_best, dSA, F->d_pairs, in_smem);
+    const size_t sm_top = sizeof(okb_pair) * (size_t)AS_CHUNK * MAX_BEST;
+    const size_t sm_b = (sizeof(okb_pair) + sizeof(int)) * (size_t)nB;        // per-B winners + list counts
+    const int in_smem = sm_top + sm_b + 1024 <= (size_t)c->smem_optin ? 1 : 0;
+    const size_t sm = sm_top + (in_smem ? sm_b : 0);
+    if (sm > 48 * 1024 - 512) FE_CUDA(c, cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_assign<<<1, AS_T, sm, c->stream>>>(d_topk, nA, nB, num_best, dSA, d_pairs, F->d_io + oD, in_smem);
   }
   c->launches += 2;
   FE_CUDA(c, cudaGetLastError());
-  if (out_topk) FE_CUDA(c, cudaMemcpyAsync(out_topk, F->d_topk, sizeof(okb_pair) * nA * num_best, cudaMemcpyDeviceToHost, c->stream));
-  FE_CUDA(c, cudaMemcpyAsync(out_pairs, F->d_pairs, sizeof(okb_pair) * nB, cudaMemcpyDeviceToHost, c->stream));
+  FE_CUDA(c, cudaMemcpyAsync(F->h_stage + oT, F->d_io + oT, oD - oT, cudaMemcpyDeviceToHost, c->stream));
   FE_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (out_topk) std::memcpy(out_topk, F->h_stage + oT, sizeof(okb_pair) * (size_t)nA * num_best);
+  std::memcpy(out_pairs, F->h_stage + oP, sizeof(okb_pair) * (size_t)nB);
   return OKB_OK;
 }
 

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   };
 
   // ---- lane -> (block pair, column split) map of the current frame range: tid = kg * n_act + item
-  int cur_fa = -1, lane_fmax = 0;
+  int cur_fa = -1, cur_fb = -1, lane_fmax = 0;
   int KS = 1, kg = 0, n_act = 0, n_pairs = 0, n_pass = 1;
   int a_off = 0, b_off = 0, row0 = 0, col0 = 0;
   bool on = false, aug = false;
@@ -442,11 +442,10 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   // The KS column splits of a block pair are adjacent lanes of one warp: they are summed with shuffles (fixed
   // order) and the kg == 0 lane adds the result to the accumulator -- no barrier, one writer per element.
   auto flush = [&]() {
+    // KS is a power of two: pairwise tree over the column splits (fixed shape => deterministic)
+    for (int o = KS >> 1; o > 0; o >>= 1) {
 #pragma unroll
-    for (int i = 0; i < 36; ++i) {
-      double v = acc[i];
-      for (int o = 1; o < KS; ++o) v += __shfl_down_sync(0xffffffffu, acc[i], o);
-      acc[i] = v;
+      for (int i = 0; i < 36; ++i) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
     }
     if (on && kg == 0) { if (acc_smem) flush_smem(0); else flush_global(); }
 #pragma unroll
@@ -488,14 +487,14 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
     buf ^= 1;
     if (fa > fb) continue;                 // no observed landmark in this tile (CTA-uniform)
     const int u = fb - fa + 1;
-    // The lane -> block-pair map is rebuilt only when the tile's FIRST frame changes (landmarks are sorted by it:
-    // at most K times per chunk) and covers the frames [fa, K-1]; lanes whose pair reaches beyond the tile's last
-    // frame fb sit the tile out (their Y rows are not even written).  Pairs are enumerated row-major, so far-apart
-    // frame pairs share warps and whole warps skip narrow tiles.
-    if (fa != cur_fa) {
+    // The lane -> block-pair map covers exactly the tile's frame range [fa, fb] and is rebuilt (after a flush of the
+    // register accumulators: a shuffle tree over the column splits + one shared-memory add per element) whenever the
+    // range changes.  Landmarks are sorted by (first, last) frame, so neighbouring tiles mostly share or shrink the
+    // range; every lane that is mapped does useful multiply-adds (narrow tiles get up to 8 column splits per pair).
+    if (fa != cur_fa || fb != cur_fb) {
       flush();
-      cur_fa = fa;
-      const int um = K - fa;
+      cur_fa = fa; cur_fb = fb;
+      const int um = fb - fa + 1;
       n_pairs = um * (um + 1) / 2;
       n_act = n_pairs + um;
       // block pairs are dealt to the warps (ipw per warp); inside a warp lane = pair * KS + split
@@ -503,7 +502,8 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
       const int ipw = (n_act + NW - 1) / NW;
       if (ipw <= 32) {
         n_pass = 1;
-        KS = max(1, min(8, 32 / ipw));
+        KS = 1;
+        while (2 * KS <= 8 && 2 * KS * ipw <= 32) KS *= 2;          // largest power of two that fits the warp
         kg = lane % KS;
         const int il = lane / KS;
         decode(warp * ipw + il, fa);
