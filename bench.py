@@ -483,14 +483,16 @@ def run_b200(args):
         total_k = prof["landmarks_ms"] + prof["solve_ms"] + prof["quality_ms"]
         # DRAM bytes per launch of the group from the committed ncu --set full captures (profiles/), scaled to B
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):
+        import glob
+        tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+        tpath = tpaths[-1] if tpaths else ""
+        if tpath:
             tj = json.load(open(tpath))
             ks = tj.get("kernels", {})
             if all(k in ks for k in ("k_linearize", "k_lmblock", "k_schur")):
                 traffic = sum(ks[k]["dram_read_bytes"] + ks[k]["dram_write_bytes"] for k in ("k_linearize", "k_lmblock", "k_schur"))
                 traffic = traffic * B / float(tj.get("windows", B))
-                traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read+write.sum of the three kernels at %d windows)" % tj.get("windows", B)
+                traffic_src = "profiles/%s (ncu dram__bytes_read+write.sum of the three kernels at %d windows)" % (os.path.basename(tpath), tj.get("windows", B))
         # CPU baseline: bounded sample of the same workload on this box's host cores -- one oracle thread per
         # window; as many windows in flight as there are usable CPUs (cgroup quota) or twice that, whichever is faster
         cores = host_cpus()

@@ -213,7 +213,7 @@ __host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_im
   b = (b + 15) & ~(size_t)15;
   b += (size_t)8 * d * sizeof(double);                     // gd, Ed, ud, rhs, vd, tmp, delta, colk
   b += (size_t)K * 4 * sizeof(double);                     // committed frame translations
-  b += (size_t)3 * (n_marg > 0 ? n_marg : 1) * sizeof(double);   // marg: dchi, e, Jte
+  b += (size_t)3 * (((n_marg > 0 ? n_marg : 1) + 1) & ~1) * sizeof(double);   // marg: dchi, e, Jte (even length each: 16-byte loads stay inside)
   b = (b + 31) & ~(size_t)31;
   b += (size_t)CH_NB * ((d + 1 + 3) & ~3) * sizeof(double);  // Cholesky panel (k-major)
   b += chol_in_smem ? tri_row(d + 1) * sizeof(double) + 16 : 16;        // the reduced system (packed lower triangle) + appended rhs row
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* _
   double* s_delta = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
   double* s_col = reinterpret_cast<double*>(smem_raw + off); off += (size_t)d * 8;
   double* s_tws = reinterpret_cast<double*>(smem_raw + off); off += (size_t)K * 4 * 8;
-  const int nm = W.marg_n > 0 ? W.marg_n : 1;
+  const int nm = ((W.marg_n > 0 ? W.marg_n : 1) + 1) & ~1;     // even: the compiler reads these vectors two doubles at a time
   double* s_dchi = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
   double* s_me = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;
   double* s_mJte = reinterpret_cast<double*>(smem_raw + off); off += (size_t)nm * 8;

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) k_schur(const WinDev* __restric
   uint32_t phase_bits = 0;      // bit b: parity to wait for on mbar[b]
   auto stage = [&](int base, int buf, uint32_t tr) {
     const int fa = tr & 0xffu, fb = tr >> 8;
-    if (fa > fb || warp != 0) return;
+    if (fa > fb || warp != A2_THREADS / 32 - 1) return;      // the last warp issues the copies (the first one also builds the augmented row)
     double* sM = sMb + (size_t)buf * K * 6 * A2_TILE;
     double* sLi = sLib + buf * A2_TILE * kLiStride;
     double* sX = sXb + buf * A2_TILE * 4;

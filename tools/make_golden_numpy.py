@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generator of tests/golden/cfg1_numpy_optimum.npz -- an INDEPENDENT pin of the optimum of a keyframe window.
+"""Generator of tests/golden/numpy_costs.npz -- an INDEPENDENT pin of the cost functions of a keyframe window.
 
 Everything here is plain NumPy / SciPy written from the reference's source (no liboracle.so, no CUDA library):
   * ReprojectionError residual            okvis_ceres/include/okvis/ceres/implementation/ReprojectionError.hpp:87-140
@@ -8,15 +8,16 @@ Everything here is plain NumPy / SciPy written from the reference's source (no l
   * ImuError residual with a fresh preintegration at the CURRENT bias
                                           okvis_ceres/src/ImuError.cpp:76-284 (redoPreintegration), :514-560 (error)
   * PoseError / SpeedAndBiasError          okvis_ceres/src/PoseError.cpp:86-136, SpeedAndBiasError.cpp:89-116
-and the minimiser is scipy.optimize.least_squares (trust-region reflective, finite-difference Jacobian with the
-block sparsity pattern) -- a different algorithm from Ceres' dogleg, the oracle's restatement of it and the device
-solver.  The optimum of the cost is algorithm independent, so all of them must land on it (tests/test_golden.py).
+The fixture holds a few states of two cfg-1 windows and the cost 0.5 * sum rho(||r||^2) of every residual family at
+those states.  tests/test_golden.py checks the C++ oracle against it, tests/test_gpu_golden.py the device kernels
+(okb_optimize with max_iterations = 0 reports the cost at the uploaded state).  Measured agreement: 1e-15 relative.
+Independently of the fixture, at the state where the oracle's dogleg stops (FUNCTION_TOLERANCE after 36 iterations on
+cfg-1 window 0) this objective evaluates to 446.196556366 against the oracle's 446.196556916 (1.2e-9: the reference
+keeps the preintegration of an earlier bias and corrects to first order, ImuError.cpp:545-556, this script always
+re-preintegrates) and its Jacobi-scaled gradient norm is 440 times smaller than at the initial guess.
 
-Caveat written into the fixture: the reference's ImuError keeps its preintegration from an earlier bias and corrects to
-first order while |db_g| dt <= 1e-4 (ImuError.cpp:545-556); this script always re-preintegrates, which moves the
-optimum by O(db^2).  The tolerances of tests/test_golden.py account for it.
-
-Usage:  python tools/make_golden_numpy.py   (takes a few minutes on one core)"""
+Usage:  python tools/make_golden_numpy.py            (seconds)
+        python tools/make_golden_numpy.py --optimize (scipy least_squares run, ~10 min, diagnostic only)"""
 import os
 import sys
 
@@ -252,16 +253,81 @@ class NumpyWindow:
         return S
 
 
+def state_to_x(nw, poses, sb, lm):
+    """Minimal coordinates of a state relative to the window's initial poses (inverse of NumpyWindow.unpack)."""
+    x = nw.x0().copy()
+    for k in range(nw.K):
+        dq = qmul(poses[k, 3:], qinv(nw.pose0[k, 3:]))
+        nv = np.linalg.norm(dq[:3])
+        ang = 2 * np.arctan2(nv, dq[3])
+        x[6 * k:6 * k + 3] = poses[k, :3] - nw.pose0[k, :3]
+        x[6 * k + 3:6 * k + 6] = dq[:3] / max(nv, 1e-300) * ang
+    x[6 * nw.K:15 * nw.K] = sb.reshape(-1)
+    x[15 * nw.K:] = lm[:, :3].reshape(-1)
+    return x
+
+
+def family_costs(nw, x):
+    parts = nw.residuals(x, parts=True)
+    n_imu, n_pp = len(nw.w.imu_terms), len(nw.w.pose_priors)
+    c = [0.5 * float(p @ p) for p in parts]
+    return dict(reprojection=c[0], imu=sum(c[1:1 + n_imu]), pose_prior=sum(c[1 + n_imu:1 + n_imu + n_pp]), speed_bias_prior=sum(c[1 + n_imu + n_pp:]),
+                total=sum(c))
+
+
 def main():
+    """Fixture: cost values of the NumPy objective at a handful of states of two windows.  The states are INPUTS
+    (initial guess, random perturbations of it, one state far from it); the costs are the answers the oracle
+    (tests/test_golden.py) and the device (tests/test_gpu_golden.py) must reproduce."""
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
-    w = synthetic.make_window(1, 0)
+    fix = {}
+    for tag, cfg_id, idx in (("cfg1_w0", 1, 0), ("cfg1_w3", 1, 3)):
+        w = synthetic.make_window(cfg_id, idx)
+        nw = NumpyWindow(w)
+        rng = np.random.Generator(np.random.PCG64(0x0B200 + 77 + idx))
+        states = [nw.x0()]
+        for scale in (0.2, 1.0, 5.0):
+            x = nw.x0().copy()
+            x[:6 * nw.K] += scale * np.tile([0.01, 0.01, 0.01, 0.002, 0.002, 0.002], nw.K) * rng.normal(size=6 * nw.K)
+            x[6 * nw.K:15 * nw.K] += scale * np.tile([0.02] * 3 + [0.001] * 3 + [0.01] * 3, nw.K) * rng.normal(size=9 * nw.K)
+            x[15 * nw.K:] += scale * 0.03 * rng.normal(size=3 * nw.L)
+            states.append(x)
+        for i, x in enumerate(states):
+            poses, sb, lm = nw.unpack(x)
+            c = family_costs(nw, x)
+            fix["%s_s%d_poses" % (tag, i)] = poses
+            fix["%s_s%d_speed_bias" % (tag, i)] = sb
+            fix["%s_s%d_landmarks" % (tag, i)] = lm
+            fix["%s_s%d_cost" % (tag, i)] = np.array([c["total"], c["reprojection"], c["imu"], c["pose_prior"], c["speed_bias_prior"]])
+            print(tag, i, c)
+    fix["layout"] = np.array("<window>_s<i>_{poses,speed_bias,landmarks}: state; _cost: [total, reprojection (Cauchy), imu, pose prior, speed/bias prior]; "
+                             "windows: synthetic.make_window(1, 0) and (1, 3); generator: tools/make_golden_numpy.py")
+    np.savez_compressed(os.path.join(out_dir, "numpy_costs.npz"), **fix)
+
+
+def golden_window():
+    import dataclasses
+    return synthetic.make_window(1, 0, cfg=dataclasses.replace(synthetic.CONFIGS[1], outlier_fraction=0.0))
+
+
+def optimize():
+    """Optional (`--optimize`, ~10 minutes): scipy.optimize.least_squares from the initial guess.  With finite-difference
+    Jacobians it creeps along the flat valley of far landmarks and does not reach a certified optimum within the budget
+    (it passes BELOW the cost at which Ceres' function tolerance stops the dogleg: 421.1 vs 446.2 on cfg-1 window 0), so
+    no optimum is committed as a fixture; the committed fixture pins cost VALUES instead (main())."""
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    # cfg-1 without gross outliers: with CauchyLoss the cost of a window that contains outliers is non-convex and different
+    # algorithms may settle in different local minima (observed: scipy 421.1 vs the dogleg's 446.2 on the standard
+    # cfg-1 window); without outliers the minimum near the initial guess is unique and algorithm independent.
+    w = golden_window()
     nw = NumpyWindow(w)
     x0 = nw.x0()
     r0 = nw.residuals(x0)
     print("initial cost %.9g, %d parameters, %d residuals" % (0.5 * r0 @ r0, len(x0), len(r0)))
     sol = least_squares(nw.residuals, x0, jac_sparsity=nw.sparsity(), method="trf", x_scale="jac", ftol=1e-15, xtol=1e-15, gtol=1e-12,
-                        max_nfev=400, verbose=1)
+                        max_nfev=300, verbose=1)
     # polish: restart from the solution (a fresh scaling / trust region) until the cost stops moving
     for _ in range(3):
         sol2 = least_squares(nw.residuals, sol.x, jac_sparsity=nw.sparsity(), method="trf", x_scale="jac", ftol=1e-15, xtol=1e-15, gtol=1e-13,
@@ -272,10 +338,11 @@ def main():
         sol = sol2
     poses, sb, lm = nw.unpack(sol.x)
     print("final cost %.12g (status %d, %d evaluations)" % (sol.cost, sol.status, sol.nfev))
-    np.savez_compressed(os.path.join(out_dir, "cfg1_numpy_optimum.npz"), poses=poses, speed_bias=sb, landmarks=lm, cost=np.array(sol.cost),
-                        initial_cost=np.array(0.5 * r0 @ r0), config=np.array([1, 0]),
-                        note=np.array("scipy.optimize.least_squares optimum of synthetic.make_window(1, 0); see tools/make_golden_numpy.py"))
+    print("optimality (inf-norm of the scaled gradient) %.3e" % sol.optimality)
+    np.savez_compressed(os.path.join("/tmp", "cfg1_numpy_optimum.npz"), poses=poses, speed_bias=sb, landmarks=lm, cost=np.array(sol.cost),
+                        initial_cost=np.array(0.5 * r0 @ r0), optimality=np.array(sol.optimality), status=np.array(sol.status),
+                        note=np.array("scipy.optimize.least_squares optimum of cfg-1 (window 0) without outliers; see tools/make_golden_numpy.py"))
 
 
 if __name__ == "__main__":
-    main()
+    optimize() if "--optimize" in sys.argv else main()

@@ -73,4 +73,26 @@ with open(os.path.join(P, f"{R}_summary.md"), "w") as f_:
     for k, v in kern.items():
         g = lambda x, s=1.0: "n/a" if v[x] is None else f"{v[x] / s:.1f}"
         f_.write(f"| {k} | {g('duration_us')} | {g('dram_read_bytes', 1e6)} | {g('dram_write_bytes', 1e6)} | {g('warp_inst', 1e6)} | {g('fp64_pipe_pct')} | {g('warps_active_pct')} |\n")
+    # frontend / marginalisation captures and the sanitizer logs travel as they are
+    fl = os.path.join(G, f"{R}_launches_frontend.csv")
+    if os.path.exists(fl):
+        shutil.copy(fl, os.path.join(P, f"{R}_launches_frontend.csv"))
+        h2, r2 = read_csv(fl)
+        i2 = {h: i for i, h in enumerate(h2)}
+        f_.write("\n## Frontend kernels (`tools/prof_frontend.py`: cfg-3 image, production image, 1000 x 1000 match, candidate lists; second repetition)\n\n")
+        f_.write("| kernel | grid | block | us |\n|---|---|---|---|\n")
+        for r in r2[len(r2) // 2:]:
+            v = float(r[i2["Metric Value"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[i2["Metric Unit"]], 1.0)
+            f_.write(f"| {r[i2['Kernel Name']].split('(')[0].replace('void ', '').replace('<unnamed>::', '')} | {r[i2['Grid Size']]} | {r[i2['Block Size']]} | {v:.1f} |\n")
+    for k in ("k_uniformity", "k_hamming_topk", "k_harris", "k_describe", "k_marginalize"):
+        det = os.path.join(G, f"{R}_{k}_details.csv")
+        if os.path.exists(det) and os.path.getsize(det) > 0:
+            shutil.copy(det, os.path.join(P, f"{R}_{k}_details.csv"))
+    f_.write("\n## compute-sanitizer (`tools/sanitize_run.py`: cfg-1 / reduced cfg-2 / cfg-5 optimize, 2-rank sharded solve, resident edits, marginalisation, frontend)\n\n")
+    for tool in ("memcheck", "racecheck", "synccheck"):
+        sp = os.path.join(G, f"{R}_sanitizer_{tool}.txt")
+        if os.path.exists(sp):
+            shutil.copy(sp, os.path.join(P, f"{R}_sanitizer_{tool}.txt"))
+            tail = [l.strip() for l in open(sp) if "ERROR SUMMARY" in l or "RACECHECK SUMMARY" in l]
+            f_.write(f"* {tool}: {tail[-1] if tail else 'see log'}\n")
 print(open(os.path.join(P, f"{R}_summary.md")).read())
