@@ -2,8 +2,8 @@
 // Blocked right-looking factorisation, panel width CH_NB:
 //   (1) the 16x16 diagonal block is factored by warp 0 with one matrix row per lane (registers +
 //       shuffles), (2) the panel below it is solved row-per-thread and transposed into a k-major
-//       shared buffer, (3) the trailing matrix gets a rank-16 update as a register-tiled SYRK
-//       (4x4 micro-tiles).  ~3 block barriers per 16 columns instead of 3 per column.
+//       shared buffer, (3) the trailing matrix gets the rank-8 update on the FP64 tensor cores
+//       (mma.sync.m8n8k4.f64, 8x8 tiles, one warp per tile).  ~3 block barriers per 16 columns instead of 3 per column.
 // The matrix lives in shared memory when it fits (d <= ~150) and in global memory otherwise.
 #pragma once
 #include <cuda_runtime.h>
@@ -22,7 +22,7 @@ __host__ __device__ inline size_t tri_row(int r) { return (size_t)r * (r + 1) / 
 // (ld_p >= nrows rounded up to 4), `flag` a shared int.  Returns 0 on success, 1 on a non-positive
 // pivot (uniform over the CTA).
 __device__ inline int block_cholesky(double* M, int d, int nrows, double* panel, int ld_p, double* rdiag, int* flag,
-                                     unsigned long long* prof = nullptr) {
+                                     unsigned long long* prof = nullptr, bool use_dmma = true) {
   const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *flag = 0;
   __syncthreads();
@@ -103,38 +103,71 @@ __device__ inline int block_cholesky(double* M, int d, int nrows, double* panel,
     for (int e = tid; e < CH_NB * (n4 - n); e += nthr) panel[(size_t)(e / (n4 - n)) * ld_p + n + e % (n4 - n)] = 0.0;
     __syncthreads();
     CHOL_MARK(1);
-    // ---- (3) trailing update: A[r0+i][r0+j] -= sum_c P[c][i] P[c][j], i >= j, 4x4 micro-tiles
-    const int nt = n4 >> 2;
-    const int ntt = nt * (nt + 1) / 2;
-    for (int t = tid; t < ntt; t += nthr) {
-      int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-      while (ti * (ti + 1) / 2 > t) --ti;
-      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-      const int tj = t - ti * (ti + 1) / 2;
-      double acc[16];
+    // ---- (3) trailing update: A[r0+i][r0+j] -= sum_c P[c][i] P[c][j], i >= j.  This is the one dense contraction of
+    // the reduced solve, so it runs on the FP64 tensor cores: 8x8 output tiles, one warp per tile, the rank-8 panel
+    // product as two mma.sync.m8n8k4.f64 (A = P^T tile rows, B = P tile columns, both read from the k-major panel in
+    // shared memory).  Fragment layout (PTX ISA, m8n8k4 f64): lane = 4 g + t holds A[g][t], B[t][g], C[g][2t..2t+1].
+    if (use_dmma) {
+      const int nt8 = (n + 7) >> 3;
+      const int ntt8 = nt8 * (nt8 + 1) / 2;
+      const int nwarps = nthr >> 5;
+      const int g = lane >> 2, t4 = lane & 3;
+      const int n4m1 = n4 - 1;
+      for (int t = warp; t < ntt8; t += nwarps) {
+        int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while (ti * (ti + 1) / 2 > t) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        const int ia = min(8 * ti + g, n4m1), jb = min(8 * tj + g, n4m1);     // rows beyond n are zero padding (masked below)
+        double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+        for (int k0 = 0; k0 < CH_NB; k0 += 4) {
+          const double a = panel[(size_t)(k0 + t4) * ld_p + ia];
+          const double b = panel[(size_t)(k0 + t4) * ld_p + jb];
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+        }
+        const int i = 8 * ti + g, j = 8 * tj + 2 * t4;
+        if (i < n) {
+          double* mrow = M + tri_row(r0 + i) + r0;
+          if (j <= i && j < ncol) mrow[j] -= d0;
+          if (j + 1 <= i && j + 1 < ncol) mrow[j + 1] -= d1;
+        }
+      }
+    } else {
+      // matrix in global memory (d > ~150): register-tiled 4x4 micro-tiles, one per thread -- sixteen independent
+      // read-modify-writes in flight per thread hide the L2 latency better than the warp-wide tensor-core tiles
+      const int nt = n4 >> 2;
+      const int ntt = nt * (nt + 1) / 2;
+      for (int t = tid; t < ntt; t += nthr) {
+        int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while (ti * (ti + 1) / 2 > t) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        double acc[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[q] = 0.0;
 #pragma unroll 4
-      for (int c = 0; c < CH_NB; ++c) {
-        const double* pr = panel + (size_t)c * ld_p;
-        const double2 a01 = *reinterpret_cast<const double2*>(pr + 4 * ti);
-        const double2 a23 = *reinterpret_cast<const double2*>(pr + 4 * ti + 2);
-        const double2 b01 = *reinterpret_cast<const double2*>(pr + 4 * tj);
-        const double2 b23 = *reinterpret_cast<const double2*>(pr + 4 * tj + 2);
-        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+        for (int c = 0; c < CH_NB; ++c) {
+          const double* pr = panel + (size_t)c * ld_p;
+          const double2 a01 = *reinterpret_cast<const double2*>(pr + 4 * ti);
+          const double2 a23 = *reinterpret_cast<const double2*>(pr + 4 * ti + 2);
+          const double2 b01 = *reinterpret_cast<const double2*>(pr + 4 * tj);
+          const double2 b23 = *reinterpret_cast<const double2*>(pr + 4 * tj + 2);
+          const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+          const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[ii * 4 + jj] += a[ii] * b[jj];
+        }
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) acc[ii * 4 + jj] += a[ii] * b[jj];
+          for (int jj = 0; jj < 4; ++jj) {
+            const int i = 4 * ti + ii, j = 4 * tj + jj;
+            if (i < n && j <= i && j < ncol) M[tri_row(r0 + i) + r0 + j] -= acc[ii * 4 + jj];
+          }
       }
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int i = 4 * ti + ii, j = 4 * tj + jj;
-          if (i < n && j <= i && j < ncol) M[tri_row(r0 + i) + r0 + j] -= acc[ii * 4 + jj];
-        }
     }
     __syncthreads();
     CHOL_MARK(2);

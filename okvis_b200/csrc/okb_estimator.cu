@@ -1113,8 +1113,7 @@ static int plan_rounds(okb_ctx* c, int first, int count, RoundPlan& P) {
   }
   if (P.smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
   P.acc_copies = acc_copies; P.chol_smem = chol_smem ? 1 : 0;
-  // few windows: one wide CTA per SM (sharded windows keep the 256-thread CTA: every rank must run the same reduction tree)
-  P.solve_threads = (2 * count <= c->sm_count && c->shard_world <= 1) ? 512 : S_THREADS;
+  P.solve_threads = (2 * count <= c->sm_count) ? 512 : S_THREADS;      // few windows: one wide CTA per SM (all ranks of a sharded window choose alike)
   P.gxQ = std::max(1, std::min((maxL + 127) / 128, (4 * c->sm_count + count - 1) / count));
   P.shard = c->shard_world > 1 ? 1 : 0;
   P.push_gx = std::max(1, std::min(16, c->sm_count / std::max(1, count)));

@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* _
       __syncthreads();
       PHASE_MARK(2);
       // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh); row d comes out as z = L^-1 rhs
-      if (!chol_fail) chol_fail = block_cholesky(Mx, d, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8);
+      if (!chol_fail) chol_fail = block_cholesky(Mx, d, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8, chol_in_smem != 0);
       PHASE_MARK(3);
       if (!chol_fail) {
         for (int i = tid; i < d; i += NT) s_tmp[i] = Mx[tri_row(d) + i];
