@@ -71,6 +71,21 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.sm_max)), "reasons": sorted(self.reasons)}
 
 
+def fp64_roofline(achieved_gflops):
+    """The Jacobian / J^T J / Schur group against the FP64 peak (the bound that really applies: ~50 FLOP per byte).  The
+    driver's MEASURED_PEAKS.json has no FP64 figure; the peak is this project's own measurement (tools/fp64_peak.cu,
+    DFMA and DMMA both 37 TFLOP/s on this B200), committed under profiles/."""
+    path = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
+    try:
+        pk = json.load(open(path))
+        peak = 1e3 * float(max(pk["fp64_fma_tflops"], pk["fp64_dmma_tflops"]))
+        src = "profiles/r01_fp64_peak.json (tools/fp64_peak.cu)"
+    except Exception:
+        peak, src = 37000.0, "fallback 37 TFLOP/s"
+    return {"bound": "fp64", "achieved": achieved_gflops, "peak": peak, "unit": "GFLOP/s", "frac": achieved_gflops / peak,
+            "flops": "SURVEY 8d model: 1500 N_obs + 324 sum f_l^2 + d^3/3 + 14000 (K-1) per window-iteration", "peak_source": src}
+
+
 def make_windows(n_distinct, base_idx):
     from okvis_b200 import synthetic
     return [synthetic.make_window(2, base_idx + i) for i in range(n_distinct)]
@@ -525,6 +540,7 @@ def run_b200(args):
                          "fp64_gflops": B * flops_iter / (lm_ms * 1e-3) / 1e9,
                          "share_of_kernel_time": prof["landmarks_ms"] / max(total_k, 1e-9),
                          "k_solve_avg_launch_ms": sv_ms, "k_solve_share": prof["solve_ms"] / max(total_k, 1e-9)},
+            "roofline_fp64": fp64_roofline(B * flops_iter / (lm_ms * 1e-3) / 1e9),
             "cpu_baseline": {"value": cpu_iters / cpu_dt, "unit": "iterations/s", "cores": cores, "kind": "port",
                              "sample": "%d windows x optimize(%d) + quality pass, one oracle thread per window, %d threads" % (n_cpu, ITERS, cores)},
             "latency": lat,
