@@ -22,6 +22,8 @@
  *                                okvis_ceres/src/MarginalizationError.cpp:127-435, 507-846 (driven by Estimator.cpp:434-773)
  *   okb_hamming_match         <- okvis::DenseMatcher::match            okvis_matcher/include/okvis/implementation/DenseMatcher.hpp:48-225
  *                                + assignbest                          okvis_matcher/src/DenseMatcher.cpp:69-110
+ *   okb_hamming_match_gated   <- VioKeyframeWindowMatchingAlgorithm::distance + verifyMatch (hpp:132-144, cpp:304-339),
+ *                                ProbabilisticStereoTriangulator::stereoTriangulate (cpp:168-227), triangulateFast
  *   okb_hamming_candidates    <- VioKeyframeWindowMatchingAlgorithm::specificDescriptorDistance
  *                                okvis_frontend/include/okvis/VioKeyframeWindowMatchingAlgorithm.hpp:246-254
  *   okb_detect_describe       <- okvis::Frontend::detectAndDescribe    okvis_frontend/src/Frontend.cpp:92-114
@@ -418,6 +420,39 @@ typedef struct okb_pair {          /* DenseMatcher::Pairing */
 int okb_hamming_match(okb_ctx* ctx, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes,
                       const uint8_t* skipA, const uint8_t* skipB, float threshold, int num_best,
                       int use_ratio, float ratio_threshold, okb_pair* out_topk, okb_pair* out_pairs);
+
+/* ---- geometry-gated matching --------------------------------------------------------------
+ * VioKeyframeWindowMatchingAlgorithm::distance (okvis_frontend/include/okvis/VioKeyframeWindowMatchingAlgorithm.hpp:132-144)
+ * returns the Hamming distance only if it is below the threshold AND verifyMatch passes
+ * (okvis_frontend/src/VioKeyframeWindowMatchingAlgorithm.cpp:304-339), else FLT_MAX; the top-k lists and assignbest of
+ * DenseMatcher then run over these gated distances.  okb_hamming_match_gated evaluates the gate on the device inside
+ * the list kernel, so no candidate list has to travel back to the host.
+ *   OKB_GATE_3D2D : chi-square test of landmark A's projection into frame B against keypoint B (:317-338);
+ *                   proj_into_b / proj_uncertainty are what doSetup computes (:159-208)
+ *   OKB_GATE_2D2D : ProbabilisticStereoTriangulator::stereoTriangulate (src/ProbabilisticStereoTriangulator.cpp:168-227):
+ *                   triangulateFast (src/stereo_triangulation.cpp:51-125) of the two back-projected rays with
+ *                   sigma = max(raySigmasA[a], raySigmasB[b]) and the two reprojection checks (:359-384).  The
+ *                   bearing vectors are the cameras' backProject() of the keypoints (the caller has the camera
+ *                   objects; the reference recomputes them inside every call). */
+enum { OKB_GATE_NONE = 0, OKB_GATE_3D2D = 1, OKB_GATE_2D2D = 2 };
+typedef struct okb_match_gate {
+  int32_t mode, _pad;
+  const double* kp_b;              /* [nB][2] keypoint coordinates in B (both modes) */
+  const double* kp_size_b;         /* [nB]    keypoint size (both modes) */
+  const double* proj_into_b;       /* 3D-2D: [nA][2] projectionsIntoB_ */
+  const double* proj_uncertainty;  /* 3D-2D: [nA][4] projectionsIntoBUncertainties_, 2x2 row-major */
+  const double* kp_a;              /* 2D-2D: [nA][2] */
+  const double* kp_size_a;         /* 2D-2D: [nA] */
+  const double* bearing_a;         /* 2D-2D: [nA][3] backProject(kp_a), camera A frame, any length */
+  const double* bearing_b;         /* 2D-2D: [nB][3] backProject(kp_b), camera B frame */
+  const double* ray_sigma_a;       /* 2D-2D: [nA] raySigmasA_ */
+  const double* ray_sigma_b;       /* 2D-2D: [nB] raySigmasB_ */
+  okb_camera cam_a, cam_b;         /* 2D-2D: geometries for the reprojection checks */
+  double T_AB[7];                  /* 2D-2D: pose of camera B in camera A [t, q_xyzw] */
+} okb_match_gate;
+int okb_hamming_match_gated(okb_ctx* ctx, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes,
+                            const uint8_t* skipA, const uint8_t* skipB, float threshold, int num_best, int use_ratio,
+                            float ratio_threshold, const okb_match_gate* gate, okb_pair* out_topk, okb_pair* out_pairs);
 
 /* Candidate-list mode for the production (geometry-gated) matching algorithm: for every A, every B
  * with Hamming distance < threshold in ascending B order, CSR layout.  row_ptr [nA+1];

@@ -67,6 +67,39 @@ def make_marg_job(block_kind, block_idx, block_prev, block_marginalize, imu_term
     return j
 
 
+class MatchGate(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("_pad", C.c_int32), ("kp_b", c_double_p), ("kp_size_b", c_double_p), ("proj_into_b", c_double_p),
+                ("proj_uncertainty", c_double_p), ("kp_a", c_double_p), ("kp_size_a", c_double_p), ("bearing_a", c_double_p),
+                ("bearing_b", c_double_p), ("ray_sigma_a", c_double_p), ("ray_sigma_b", c_double_p), ("cam_a", Camera), ("cam_b", Camera),
+                ("T_AB", C.c_double * 7)]
+
+
+GATE_NONE, GATE_3D2D, GATE_2D2D = 0, 1, 2
+
+
+def make_match_gate(mode, kp_b, kp_size_b, proj_into_b=None, proj_uncertainty=None, kp_a=None, kp_size_a=None, bearing_a=None,
+                    bearing_b=None, ray_sigma_a=None, ray_sigma_b=None, cam_a=None, cam_b=None, T_AB=None):
+    """okb_match_gate over numpy arrays (kept alive on the returned object)."""
+    g = MatchGate()
+    g.mode = mode
+    keep = []
+    for name, arr in (("kp_b", kp_b), ("kp_size_b", kp_size_b), ("proj_into_b", proj_into_b), ("proj_uncertainty", proj_uncertainty),
+                      ("kp_a", kp_a), ("kp_size_a", kp_size_a), ("bearing_a", bearing_a), ("bearing_b", bearing_b),
+                      ("ray_sigma_a", ray_sigma_a), ("ray_sigma_b", ray_sigma_b)):
+        if arr is not None:
+            a = np.ascontiguousarray(arr, np.float64)
+            keep.append(a)
+            setattr(g, name, a.ctypes.data_as(c_double_p))
+    for name, cam in (("cam_a", cam_a), ("cam_b", cam_b)):
+        if cam is not None:
+            C.memmove(C.addressof(getattr(g, name)), np.array([cam], camera_dtype).ctypes.data, C.sizeof(Camera))
+    if T_AB is not None:
+        for k in range(7):
+            g.T_AB[k] = float(T_AB[k])
+    g._keep = keep
+    return g
+
+
 class WindowDesc(C.Structure):
     _fields_ = [("n_poses", C.c_int32), ("n_speed_bias", C.c_int32), ("n_extrinsics", C.c_int32),
                 ("n_landmarks", C.c_int32), ("n_cameras", C.c_int32), ("n_obs", C.c_int32),

@@ -363,6 +363,19 @@ class Context:
                                             num_best, int(use_ratio), C.c_float(ratio_threshold), _p(topk), _p(pairs)))
         return dict(topk=topk, pairs=pairs)
 
+    def hamming_match_gated(self, A, B, gate, skipA=None, skipB=None, threshold=60.0, num_best=4, use_ratio=False, ratio_threshold=3.0):
+        """okb_hamming_match_gated; gate from abi.make_match_gate."""
+        A = np.ascontiguousarray(A, dtype=np.uint8)
+        B = np.ascontiguousarray(B, dtype=np.uint8)
+        nA, nB, nbytes = A.shape[0], B.shape[0], A.shape[1]
+        topk = np.zeros((nA, num_best), abi.pair_dtype)
+        pairs = np.zeros(nB, abi.pair_dtype)
+        sa = np.ascontiguousarray(skipA, dtype=np.uint8) if skipA is not None else None
+        sb = np.ascontiguousarray(skipB, dtype=np.uint8) if skipB is not None else None
+        self._check(lib().okb_hamming_match_gated(self._h, _p(A), nA, _p(B), nB, nbytes, _p(sa), _p(sb), C.c_float(threshold), num_best,
+                                                  int(use_ratio), C.c_float(ratio_threshold), C.byref(gate), _p(topk), _p(pairs)))
+        return dict(topk=topk, pairs=pairs)
+
     def hamming_candidates(self, A, B, threshold=60.0, cap=None):
         A = np.ascontiguousarray(A, dtype=np.uint8)
         B = np.ascontiguousarray(B, dtype=np.uint8)

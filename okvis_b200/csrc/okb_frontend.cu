@@ -609,6 +609,109 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
 // =================================================================================================
 // matcher kernels
 // =================================================================================================
+// =================================================================================================
+// geometric match gate (VioKeyframeWindowMatchingAlgorithm::verifyMatch) -- evaluated per
+// (A, B) pair inside the list kernel for pairs whose Hamming distance is below the threshold
+// =================================================================================================
+namespace {
+struct GateDev {
+  int mode;
+  const double *kp_b, *kp_size_b, *proj_into_b, *proj_unc, *kp_a, *kp_size_a, *bearing_a, *bearing_b, *ray_sigma_a, *ray_sigma_b;
+  CamIntr cam_a, cam_b;
+  int wa, ha, wb, hb;
+  double R_AB[9], t_AB[3];
+};
+
+// PinholeCamera::projectHomogeneous(...) == Successful (PinholeCamera.hpp(impl):147-226, 345-378; CameraBase::isInImage)
+__device__ __forceinline__ bool gate_project(const CamIntr& cam, int W, int H, const double* hp, double* y) {
+  double head[3] = {hp[0], hp[1], hp[2]};
+  if (hp[3] < 0) { head[0] = -head[0]; head[1] = -head[1]; head[2] = -head[2]; }
+  double J[6];
+  if (!project<false>(cam, head, y, J)) return false;
+  if (y[0] < 0.0 || y[1] < 0.0 || y[0] >= (double)W || y[1] >= (double)H) return false;
+  return head[2] > 0.0;
+}
+// ProbabilisticStereoTriangulator::computeReprojectionError4 (ProbabilisticStereoTriangulator.cpp:359-384)
+__device__ __forceinline__ bool gate_reproj_err(const CamIntr& cam, int W, int H, const double* kp, double size, const double* hp, double& err) {
+  double y[2];
+  if (!gate_project(cam, W, H, hp, y)) return false;
+  const double sd = 0.8 * size / 12.0;
+  const double w = 1.0 / (sd * sd);
+  const double d0 = y[0] - kp[0], d1 = y[1] - kp[1];
+  err = d0 * (w * d0) + d1 * (w * d1);
+  return true;
+}
+__device__ bool gate_verify(const GateDev& g, int a, int b) {
+  if (g.mode == OKB_GATE_2D2D) {
+    // stereoTriangulate (ProbabilisticStereoTriangulator.cpp:168-227) -> triangulateFast (stereo_triangulation.cpp:51-125)
+    const double* ba = g.bearing_a + 3 * a;
+    const double* bb = g.bearing_b + 3 * b;
+    double e1[3], e2[3], eb[3];
+    const double na = sqrt(ba[0] * ba[0] + ba[1] * ba[1] + ba[2] * ba[2]);
+    e1[0] = ba[0] / na; e1[1] = ba[1] / na; e1[2] = ba[2] / na;
+    mat3vec(g.R_AB, bb, eb);
+    const double nb = sqrt(eb[0] * eb[0] + eb[1] * eb[1] + eb[2] * eb[2]);
+    e2[0] = eb[0] / nb; e2[1] = eb[1] / nb; e2[2] = eb[2] / nb;
+    const double sigma = fmax(g.ray_sigma_a[a], g.ray_sigma_b[b]);
+    const double* t12 = g.t_AB;                    // p1 = 0, p2 = t_AB
+    const double b0 = t12[0] * e1[0] + t12[1] * e1[1] + t12[2] * e1[2];
+    const double b1 = t12[0] * e2[0] + t12[1] * e2[1] + t12[2] * e2[2];
+    const double A00 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
+    double A10 = e1[0] * e2[0] + e1[1] * e2[1] + e1[2] * e2[2], A01 = -A10;
+    const double A11 = -(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+    if (A10 < 0.0) { A10 = -A10; A01 = -A01; }
+    const double det = A00 * A11 - A01 * A10;
+    double hpA[4];
+    if (!(fabs(det) > 1.0e-6)) {
+      double c[3];
+      cross3(e1, e2, c);
+      if (!(sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) < 6 * sigma)) return false;
+      const double v[4] = {(e1[0] + e2[0]) / 2.0, (e1[1] + e2[1]) / 2.0, (e1[2] + e2[2]) / 2.0, 1e-3};
+      const double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+      hpA[0] = v[0] / n; hpA[1] = v[1] / n; hpA[2] = v[2] / n; hpA[3] = v[3] / n;
+    } else {
+      const double i00 = A11 / det, i01 = -A01 / det, i10 = -A10 / det, i11 = A00 / det;
+      const double l0 = i00 * b0 + i01 * b1, l1 = i10 * b0 + i11 * b1;
+      double mid[3], err[3], diff[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double xm = l0 * e1[k], xn = l1 * e2[k] + t12[k];
+        mid[k] = (xm + xn) / 2.0;
+        err[k] = mid[k] - xm;
+        diff[k] = mid[k] - (0.5 * t12[k]);
+      }
+      const double diff_sq = diff[0] * diff[0] + diff[1] * diff[1] + diff[2] * diff[2];
+      const double chi2 = (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]) * (1.0 / (diff_sq * sigma * sigma));
+      if (chi2 > 9) return false;
+      if (diff[0] * e1[0] + diff[1] * e1[1] + diff[2] * e1[2] < 0)
+        for (int k = 0; k < 3; ++k) mid[k] = (0.5 * t12[k]) - diff[k];
+      const double n = sqrt(mid[0] * mid[0] + mid[1] * mid[1] + mid[2] * mid[2] + 1.0);
+      hpA[0] = mid[0] / n; hpA[1] = mid[1] / n; hpA[2] = mid[2] / n; hpA[3] = 1.0 / n;
+    }
+    double errA, errB;
+    if (!gate_reproj_err(g.cam_a, g.wa, g.ha, g.kp_a + 2 * a, g.kp_size_a[a], hpA, errA)) return false;
+    double hpB[4];        // T_BA * hpA = [C_AB^T (x - t_AB w), w]
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double tk = -(g.R_AB[k] * g.t_AB[0] + g.R_AB[3 + k] * g.t_AB[1] + g.R_AB[6 + k] * g.t_AB[2]);
+      hpB[k] = g.R_AB[k] * hpA[0] + g.R_AB[3 + k] * hpA[1] + g.R_AB[6 + k] * hpA[2] + tk * hpA[3];
+    }
+    hpB[3] = hpA[3];
+    if (!gate_reproj_err(g.cam_b, g.wb, g.hb, g.kp_b + 2 * b, g.kp_size_b[b], hpB, errB)) return false;
+    return !(errA > 4.0 || errB > 4.0);
+  }
+  // 3D-2D (VioKeyframeWindowMatchingAlgorithm.cpp:317-338)
+  const double sd = 0.8 * g.kp_size_b[b] / 12.0;
+  const double* P = g.proj_unc + 4 * a;
+  const double U00 = sd * sd + P[0], U01 = P[1], U10 = P[2], U11 = sd * sd + P[3];
+  const double det = U00 * U11 - U01 * U10;
+  const double e0 = g.proj_into_b[2 * a] - g.kp_b[2 * b], e1 = g.proj_into_b[2 * a + 1] - g.kp_b[2 * b + 1];
+  const double v0 = (U11 * e0 - U01 * e1) / det, v1 = (-U10 * e0 + U00 * e1) / det;
+  const int chi2 = (int)(e0 * v0 + e1 * v1);      // the reference truncates to int before comparing with 4.0
+  return chi2 < 4.0;
+}
+}  // namespace
+
 namespace {
 constexpr int MW = 8;            // warps per CTA = A rows per CTA (one warp per A descriptor)
 constexpr int MT = 32 * MW;
@@ -621,10 +724,10 @@ constexpr int MAX_BEST = 8;
 // with exactly the reference's sequential rule -- candidates are taken in ascending B order (lowest set bit of the
 // ballot first), a candidate enters only if it beats the CURRENT worst entry (re-voted after every insertion, the
 // worst only shrinks), std::lower_bound position, i.e. before entries of equal distance.
-template <int NW>
+template <int NW, bool GATED>
 __global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict__ A, int nA, const uint32_t* __restrict__ B, int nB,
                                                      const uint8_t* __restrict__ skipA, const uint8_t* __restrict__ skipB, float list_thr,
-                                                     int num_best, okb_pair* __restrict__ topk) {
+                                                     int num_best, okb_pair* __restrict__ topk, float gate_thr, const GateDev* __restrict__ gate) {
   __shared__ uint32_t sB[MB_TILE][NW + 1];
   __shared__ uint8_t sSkip[MB_TILE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -653,6 +756,9 @@ __global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict_
 #pragma unroll
         for (int w = 0; w < NW; ++w) dist += __popc(wa[w] ^ sB[j][w]);
         t = (float)dist;
+        // VioKeyframeWindowMatchingAlgorithm::distance: the Hamming distance counts only below the threshold and
+        // if the geometric gate passes, else FLT_MAX (which never enters a list)
+        if (GATED) t = (t < gate_thr && gate_verify(*gate, a, b0 + j)) ? t : 3.402823466e+38f;
       }
       uint32_t mask = __ballot_sync(0xffffffffu, t < worst);
       while (mask) {
@@ -859,19 +965,30 @@ static int ensure_io(okb_ctx* c, okb_frontend_state* F, size_t bytes) {
   return OKB_OK;
 }
 
-extern "C" int okb_hamming_match(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, const uint8_t* skipA,
-                                 const uint8_t* skipB, float threshold, int num_best, int use_ratio, float ratio_threshold,
-                                 okb_pair* out_topk, okb_pair* out_pairs) {
-  (void)ratio_threshold;   // the ratio test itself belongs to the serial epilogue on the caller's side
+static int hamming_match_impl(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, const uint8_t* skipA,
+                              const uint8_t* skipB, float threshold, int num_best, int use_ratio, const okb_match_gate* gate,
+                              okb_pair* out_topk, okb_pair* out_pairs) {
   if (!c || !A || !B || nA < 1 || nB < 1 || num_best < 1 || num_best > MAX_BEST || !out_pairs) return OKB_ERR_INVALID_ARG;
   if (desc_bytes % 4) { c->set_error("descriptor length must be a multiple of 4"); return OKB_ERR_UNSUPPORTED; }
+  const int mode = gate ? gate->mode : OKB_GATE_NONE;
+  if (mode != OKB_GATE_NONE && mode != OKB_GATE_3D2D && mode != OKB_GATE_2D2D) return OKB_ERR_INVALID_ARG;
+  if (mode != OKB_GATE_NONE && (!gate->kp_b || !gate->kp_size_b)) return OKB_ERR_INVALID_ARG;
+  if (mode == OKB_GATE_3D2D && (!gate->proj_into_b || !gate->proj_uncertainty)) return OKB_ERR_INVALID_ARG;
+  if (mode == OKB_GATE_2D2D && (!gate->kp_a || !gate->kp_size_a || !gate->bearing_a || !gate->bearing_b || !gate->ray_sigma_a || !gate->ray_sigma_b))
+    return OKB_ERR_INVALID_ARG;
   cudaSetDevice(c->device);
   okb_frontend_state* F = fe(c);
   std::lock_guard<std::mutex> lk(F->match_mtx);
-  // one pinned staging buffer, one copy in, one copy out:  [A | B | skipA | skipB | pad]  ...  [top-k lists | winners]
+  // one pinned staging buffer, one copy in, one copy out:
+  //   [A | B | skipA | skipB | gate arrays | GateDev]  ...  [top-k lists | winners | scratch]
   auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   const size_t oA = 0, oB = up16((size_t)nA * desc_bytes), oSA = oB + up16((size_t)nB * desc_bytes), oSB = oSA + up16((size_t)nA);
-  const size_t in_bytes = oSB + up16((size_t)nB);
+  size_t oG = oSB + up16((size_t)nB);
+  // gate arrays (doubles): kp_b 2nB | size_b nB | proj 2nA | unc 4nA | kp_a 2nA | size_a nA | bear_a 3nA | bear_b 3nB | rs_a nA | rs_b nB
+  const size_t g_kpb = oG, g_szb = g_kpb + 16 * (size_t)nB, g_proj = g_szb + up16(8 * (size_t)nB), g_unc = g_proj + 16 * (size_t)nA,
+               g_kpa = g_unc + 32 * (size_t)nA, g_sza = g_kpa + 16 * (size_t)nA, g_ba = g_sza + up16(8 * (size_t)nA), g_bb = g_ba + up16(24 * (size_t)nA),
+               g_rsa = g_bb + up16(24 * (size_t)nB), g_rsb = g_rsa + up16(8 * (size_t)nA), g_dev = g_rsb + up16(8 * (size_t)nB);
+  const size_t in_bytes = mode == OKB_GATE_NONE ? oG : g_dev + up16(sizeof(GateDev));
   const size_t oT = in_bytes, oP = oT + sizeof(okb_pair) * (size_t)nA * num_best, oD = oP + sizeof(okb_pair) * (size_t)nB, total = oD + up16((size_t)nA);
   int rc = ensure_io(c, F, total);
   if (rc) return rc;
@@ -879,17 +996,47 @@ extern "C" int okb_hamming_match(okb_ctx* c, const uint8_t* A, int nA, const uin
   std::memcpy(F->h_stage + oB, B, (size_t)nB * desc_bytes);
   if (skipA) std::memcpy(F->h_stage + oSA, skipA, nA);
   if (skipB) std::memcpy(F->h_stage + oSB, skipB, nB);
+  if (mode != OKB_GATE_NONE) {
+    GateDev gd;
+    std::memset(&gd, 0, sizeof gd);
+    gd.mode = mode;
+    auto put = [&](size_t off, const double* src, size_t n) -> const double* {
+      if (src) std::memcpy(F->h_stage + off, src, 8 * n);
+      return reinterpret_cast<const double*>(F->d_io + off);
+    };
+    gd.kp_b = put(g_kpb, gate->kp_b, 2 * (size_t)nB); gd.kp_size_b = put(g_szb, gate->kp_size_b, nB);
+    if (mode == OKB_GATE_3D2D) { gd.proj_into_b = put(g_proj, gate->proj_into_b, 2 * (size_t)nA); gd.proj_unc = put(g_unc, gate->proj_uncertainty, 4 * (size_t)nA); }
+    else {
+      gd.kp_a = put(g_kpa, gate->kp_a, 2 * (size_t)nA); gd.kp_size_a = put(g_sza, gate->kp_size_a, nA);
+      gd.bearing_a = put(g_ba, gate->bearing_a, 3 * (size_t)nA); gd.bearing_b = put(g_bb, gate->bearing_b, 3 * (size_t)nB);
+      gd.ray_sigma_a = put(g_rsa, gate->ray_sigma_a, nA); gd.ray_sigma_b = put(g_rsb, gate->ray_sigma_b, nB);
+      cam_load(gate->cam_a, gd.cam_a); cam_load(gate->cam_b, gd.cam_b);
+      gd.wa = gate->cam_a.width; gd.ha = gate->cam_a.height; gd.wb = gate->cam_b.width; gd.hb = gate->cam_b.height;
+      double q[4] = {gate->T_AB[3], gate->T_AB[4], gate->T_AB[5], gate->T_AB[6]};
+      qnormalize(q);
+      q2R(q, gd.R_AB);
+      gd.t_AB[0] = gate->T_AB[0]; gd.t_AB[1] = gate->T_AB[1]; gd.t_AB[2] = gate->T_AB[2];
+    }
+    std::memcpy(F->h_stage + g_dev, &gd, sizeof gd);
+  }
   FE_CUDA(c, cudaMemcpyAsync(F->d_io, F->h_stage, in_bytes, cudaMemcpyHostToDevice, c->stream));
   const uint8_t* dSA = skipA ? F->d_io + oSA : nullptr;
   const uint8_t* dSB = skipB ? F->d_io + oSB : nullptr;
   okb_pair* d_topk = reinterpret_cast<okb_pair*>(F->d_io + oT);
   okb_pair* d_pairs = reinterpret_cast<okb_pair*>(F->d_io + oP);
+  const GateDev* d_gate = reinterpret_cast<const GateDev*>(F->d_io + g_dev);
   // DenseMatcher.hpp(impl):188-193: with the ratio test the lists are built without a threshold
   const float list_thr = use_ratio ? 3.402823466e+38f : threshold;
   const int nw = desc_bytes / 4;
-  DISPATCH_NW(nw, (k_hamming_topk<NW><<<(nA + MW - 1) / MW, MT, 0, c->stream>>>(
-                      reinterpret_cast<const uint32_t*>(F->d_io + oA), nA, reinterpret_cast<const uint32_t*>(F->d_io + oB), nB, dSA, dSB, list_thr,
-                      num_best, d_topk)));
+  if (mode == OKB_GATE_NONE) {
+    DISPATCH_NW(nw, (k_hamming_topk<NW, false><<<(nA + MW - 1) / MW, MT, 0, c->stream>>>(
+                        reinterpret_cast<const uint32_t*>(F->d_io + oA), nA, reinterpret_cast<const uint32_t*>(F->d_io + oB), nB, dSA, dSB, list_thr,
+                        num_best, d_topk, 0.f, nullptr)));
+  } else {
+    DISPATCH_NW(nw, (k_hamming_topk<NW, true><<<(nA + MW - 1) / MW, MT, 0, c->stream>>>(
+                        reinterpret_cast<const uint32_t*>(F->d_io + oA), nA, reinterpret_cast<const uint32_t*>(F->d_io + oB), nB, dSA, dSB, list_thr,
+                        num_best, d_topk, threshold, d_gate)));
+  }
   {
     const size_t sm_top = sizeof(okb_pair) * (size_t)AS_CHUNK * MAX_BEST;
     const size_t sm_b = (sizeof(okb_pair) + sizeof(int)) * (size_t)nB;        // per-B winners + list counts
@@ -905,6 +1052,21 @@ extern "C" int okb_hamming_match(okb_ctx* c, const uint8_t* A, int nA, const uin
   if (out_topk) std::memcpy(out_topk, F->h_stage + oT, sizeof(okb_pair) * (size_t)nA * num_best);
   std::memcpy(out_pairs, F->h_stage + oP, sizeof(okb_pair) * (size_t)nB);
   return OKB_OK;
+}
+
+extern "C" int okb_hamming_match(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, const uint8_t* skipA,
+                                 const uint8_t* skipB, float threshold, int num_best, int use_ratio, float ratio_threshold,
+                                 okb_pair* out_topk, okb_pair* out_pairs) {
+  (void)ratio_threshold;   // the ratio test itself belongs to the serial epilogue on the caller's side
+  return hamming_match_impl(c, A, nA, B, nB, desc_bytes, skipA, skipB, threshold, num_best, use_ratio, nullptr, out_topk, out_pairs);
+}
+
+extern "C" int okb_hamming_match_gated(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, const uint8_t* skipA,
+                                       const uint8_t* skipB, float threshold, int num_best, int use_ratio, float ratio_threshold,
+                                       const okb_match_gate* gate, okb_pair* out_topk, okb_pair* out_pairs) {
+  (void)ratio_threshold;
+  if (!gate) return OKB_ERR_INVALID_ARG;
+  return hamming_match_impl(c, A, nA, B, nB, desc_bytes, skipA, skipB, threshold, num_best, use_ratio, gate, out_topk, out_pairs);
 }
 
 extern "C" int okb_hamming_candidates(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, float threshold,

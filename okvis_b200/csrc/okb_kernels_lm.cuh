@@ -124,15 +124,18 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
       }
       if (f == 0) *reinterpret_cast<double4*>(W.lm_c + 4 * (size_t)l) = make_double4(X[0], X[1], X[2], X[3]);
       if (vis) {
-        double M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0, m0 = 0, m1 = 0, m2 = 0, cost = 0;
+        double M0 = 0, M1 = 0, M2 = 0, M3 = 0, M4 = 0, M5 = 0, m0 = 0, m1 = 0, m2 = 0, cost = 0, lprod = 1.0;
         auto add_obs = [&](const SlotCtx& sc, double wobs, double2 z) {
           if (wobs > 0.0 && sc.valid) {
             double r[2], A[6];
             reproj_slot<true>(sc.xf, sc.cam, X, z.x, z.y, wobs, r, A);
             const double sq = r[0] * r[0] + r[1] * r[1];
             double rho1 = 1.0;
-            if (cauchy) { rho1 = 1.0 / (1.0 + sq); cost += 0.5 * log(1.0 + sq); }
-            else cost += 0.5 * sq;
+            if (cauchy) {          // 0.5 log(1 + s) per block: the logs of a frame's cameras are taken as one log of the product
+              rho1 = 1.0 / (1.0 + sq);
+              lprod *= 1.0 + sq;
+              if (lprod > 1e250) { cost += 0.5 * log(lprod); lprod = 1.0; }
+            } else cost += 0.5 * sq;
             M0 += rho1 * (A[0] * A[0] + A[3] * A[3]);
             M1 += rho1 * (A[0] * A[1] + A[3] * A[4]);
             M2 += rho1 * (A[0] * A[2] + A[3] * A[5]);
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(L1_THREADS) k_linearize(const WinDev* __restri
           const size_t gi = gi0 + (size_t)c * L;
           add_obs(slots[c], W.obs_w[gi], W.obs_z[gi]);
         }
+        if (cauchy) cost += 0.5 * log(lprod);
         double* Mo = W.lm_M + lm_M_index(l, f, W.K);          // tile-major: a warp stores 256-byte rows
         Mo[0] = M0; Mo[32] = M1; Mo[64] = M2; Mo[96] = M3; Mo[128] = M4; Mo[160] = M5;
         double* mo = W.lm_mf + lm_mf_index(l, f, W.K);

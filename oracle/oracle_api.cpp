@@ -5,6 +5,7 @@
 
 #include "oracle_brisk.hpp"
 #include "oracle_errors.hpp"
+#include "oracle_gate.hpp"
 #include "oracle_marg.hpp"
 #include "oracle_marg_apply.hpp"
 #include "oracle_matcher.hpp"
@@ -159,6 +160,21 @@ int oko_match_hamming(const uint8_t* A, int nA, const uint8_t* B, int nB, int de
     if (matches) { matches[2 * i] = m[i].a; matches[2 * i + 1] = m[i].b; }
     if (match_dist) match_dist[i] = m[i].d;
   }
+  return (int)m.size();
+}
+
+// DenseMatcher over VioKeyframeWindowMatchingAlgorithm::distance: Hamming below the threshold AND verifyMatch, else FLT_MAX
+int oko_match_hamming_gated(const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, const uint8_t* skipA, const uint8_t* skipB,
+                            float threshold, int num_best, int use_ratio, float ratio_threshold, const okb_match_gate* gate, okb_pair* topk,
+                            okb_pair* pairs) {
+  std::vector<Match> m;
+  dense_match(nA, nB,
+              [&](int a, int b) {
+                const float d = (float)hamming(A + (size_t)a * desc_bytes, B + (size_t)b * desc_bytes, desc_bytes);
+                if (d < threshold && verify_match(*gate, a, b)) return d;
+                return std::numeric_limits<float>::max();
+              },
+              skipA, skipB, threshold, num_best, use_ratio != 0, ratio_threshold, topk, pairs, &m);
   return (int)m.size();
 }
 

@@ -300,6 +300,24 @@ def match_hamming(A, B, skipA=None, skipB=None, threshold=60.0, num_best=4, use_
     return dict(topk=topk, pairs=pairs, matches=matches[:n].copy(), distances=md[:n].copy())
 
 
+def match_hamming_gated(A, B, gate, skipA=None, skipB=None, threshold=60.0, num_best=4, use_ratio=False, ratio_threshold=3.0):
+    """DenseMatcher over VioKeyframeWindowMatchingAlgorithm::distance (Hamming + verifyMatch), oracle_gate.hpp."""
+    A = np.ascontiguousarray(A, dtype=np.uint8)
+    B = np.ascontiguousarray(B, dtype=np.uint8)
+    nA, nB, nbytes = A.shape[0], B.shape[0], A.shape[1]
+    topk = np.zeros((nA, num_best), abi.pair_dtype)
+    pairs = np.zeros(nB, abi.pair_dtype)
+    sa = np.ascontiguousarray(skipA, dtype=np.uint8) if skipA is not None else None
+    sb = np.ascontiguousarray(skipB, dtype=np.uint8) if skipB is not None else None
+    f = lib().oko_match_hamming_gated
+    f.restype = C.c_int
+    f(C.c_void_p(A.ctypes.data), C.c_int(nA), C.c_void_p(B.ctypes.data), C.c_int(nB), C.c_int(nbytes),
+      C.c_void_p(sa.ctypes.data) if sa is not None else None, C.c_void_p(sb.ctypes.data) if sb is not None else None,
+      C.c_float(threshold), C.c_int(num_best), C.c_int(int(use_ratio)), C.c_float(ratio_threshold), C.byref(gate),
+      C.c_void_p(topk.ctypes.data), C.c_void_p(pairs.ctypes.data))
+    return dict(topk=topk, pairs=pairs)
+
+
 def hamming_candidates(A, B, threshold=60.0, cap=None):
     A = np.ascontiguousarray(A, dtype=np.uint8)
     B = np.ascontiguousarray(B, dtype=np.uint8)
