@@ -247,6 +247,8 @@ __global__ void k_nms(const int32_t* __restrict__ score, int W, int H, int32_t t
 // (cell size >= radius: 3x3 cells).  The accepted set is then ranked by counting (score order) and cut at max_kp.
 // One CTA of 1024 threads per image; all scratch lives in global memory.
 constexpr int UT = 1024;
+constexpr int UNI_SN = 6144, UNI_SC = UNI_SN / 2;      // candidates / cells the shared-memory kernel holds
+__host__ __device__ inline bool uni_fits_smem(int n, int n_cells) { return n <= UNI_SN && n_cells <= UNI_SC; }
 struct UniScratch {
   uint32_t* cell_start;   // [n_cells + 1]
   uint32_t* cell_cur;     // [n_cells]
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(UT) k_uniformity(const unsigned long long* __r
   const int n = min(*count, cap);
   const int cs = max(4, (int)ceil(radius));
   const int gw = (W + cs - 1) / cs, gh = (H + cs - 1) / cs, n_cells = gw * gh;
+  if (uni_fits_smem(n, n_cells)) return;       // k_uniformity_smem (launched next) does this image
   const long long r2i = (long long)ceil(radius * radius - 1e-9);     // integer test: dx^2 + dy^2 < radius^2
   auto px = [&](int i, int& x, int& y) { const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull); x = (int)(idx % (uint32_t)W); y = (int)(idx / (uint32_t)W); };
   // ---- bucket grid (counting sort by cell)
@@ -389,6 +392,140 @@ __global__ void __launch_bounds__(UT) k_uniformity(const unsigned long long* __r
       int x, y; px((int)sc.acc[a], x, y);
       okb_keypoint kp;
       kp.x = (float)x; kp.y = (float)y; kp.size = 12.0f; kp.angle = 0.0f;
+      kp.response = (float)(int32_t)(uint32_t)(ka >> 32); kp.octave = 0;
+      kps[rank] = kp;
+    }
+  }
+  if (tid == 0) { *n_out = min(m, max_kp); n_out[1] = rounds; }
+}
+
+// The same algorithm with every hot array in shared memory (the common case: a few thousand NMS candidates, a few
+// thousand cells): one CTA walks dependent chains of loads, so the latency of each load is what the kernel costs.
+// Images with more candidates / cells than fit take the global-memory kernel above (both are launched, one returns).
+struct UniSmem {
+  unsigned long long keys[UNI_SN];
+  ushort2 xy[UNI_SN];
+  unsigned short order[UNI_SN], blocker[UNI_SN], listA[UNI_SN], listB[UNI_SN], pend[UNI_SN];
+  unsigned short cell_start[UNI_SC + 1], cell_cur[UNI_SC];
+  unsigned char state[UNI_SN];
+};
+__global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long* __restrict__ keys, const int* __restrict__ count, int cap,
+                                                        int W, int H, double radius, int max_kp, okb_keypoint* kps, int* n_out) {
+  extern __shared__ __align__(16) unsigned char uni_raw[];
+  UniSmem& S = *reinterpret_cast<UniSmem*>(uni_raw);
+  __shared__ int s_warp[32];
+  __shared__ int s_n, s_alive, s_pend;
+  const int tid = threadIdx.x;
+  const int n = min(*count, cap);
+  const int cs = max(4, (int)ceil(radius));
+  const int gw = (W + cs - 1) / cs, gh = (H + cs - 1) / cs, n_cells = gw * gh;
+  if (!uni_fits_smem(n, n_cells)) return;
+  const int r2i = (int)ceil(radius * radius - 1e-9);
+  for (int c = tid; c < n_cells; c += UT) S.cell_cur[c] = 0;
+  for (int i = tid; i < n; i += UT) {
+    const unsigned long long k = keys[i];
+    const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull);
+    S.keys[i] = k;
+    S.xy[i] = make_ushort2((unsigned short)(idx % (uint32_t)W), (unsigned short)(idx / (uint32_t)W));
+    S.state[i] = 0;
+    S.listA[i] = (unsigned short)i;
+  }
+  __syncthreads();
+  // bucket grid: 32-bit counters alias the (still unused) second live list -- UNI_SC cells fit its 2 * UNI_SN bytes
+  unsigned int* cnt32 = reinterpret_cast<unsigned int*>(S.listB);
+  {
+
+    for (int c = tid; c < n_cells; c += UT) cnt32[c] = 0u;
+    __syncthreads();
+    for (int i = tid; i < n; i += UT) atomicAdd(&cnt32[(S.xy[i].y / cs) * gw + S.xy[i].x / cs], 1u);
+    __syncthreads();
+    int run = 0;
+    for (int base = 0; base < n_cells; base += UT) {
+      const int c = base + tid;
+      const int v = (c < n_cells) ? (int)cnt32[c] : 0;
+      int total;
+      const int ex = uni_block_scan(v, s_warp, &total);
+      if (c < n_cells) S.cell_start[c] = (unsigned short)(run + ex);
+      run += total;
+      __syncthreads();
+    }
+    if (tid == 0) S.cell_start[n_cells] = (unsigned short)run;
+    __syncthreads();
+    for (int c = tid; c < n_cells; c += UT) cnt32[c] = S.cell_start[c];
+    __syncthreads();
+    for (int i = tid; i < n; i += UT) { const unsigned int pos = atomicAdd(&cnt32[(S.xy[i].y / cs) * gw + S.xy[i].x / cs], 1u); S.order[pos] = (unsigned short)i; }
+    __syncthreads();
+  }
+  int alive = n, rounds = 0;
+  bool first_round = true;
+  unsigned short* listA = S.listA;
+  unsigned short* listB = S.listB;
+  while (alive > 0) {
+    ++rounds;
+    if (tid == 0) { s_alive = 0; s_pend = 0; }
+    __syncthreads();
+    for (int t = tid; t < alive; t += UT) {
+      const int i = listA[t];
+      if (!first_round && S.state[S.blocker[i]] <= 1) continue;
+      const int x = S.xy[i].x, y = S.xy[i].y;
+      const unsigned long long ki = S.keys[i];
+      bool blocked = false;
+      const int cx = x / cs, cy = y / cs;
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1) && !blocked; ++yy)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, gw - 1) && !blocked; ++xx) {
+          const int e = S.cell_start[yy * gw + xx + 1];
+          for (int q = S.cell_start[yy * gw + xx]; q < e; ++q) {
+            const int j = S.order[q];
+            if (S.keys[j] <= ki || S.state[j] > 1) continue;
+            const int dx = (int)S.xy[j].x - x, dy = (int)S.xy[j].y - y;
+            if (dx * dx + dy * dy < r2i) { blocked = true; S.blocker[i] = (unsigned short)j; break; }
+          }
+        }
+      if (!blocked) { S.state[i] = 1; S.pend[atomicAdd(&s_pend, 1)] = (unsigned short)i; }
+    }
+    __syncthreads();
+    const int n_pend = s_pend;
+    for (int t = tid >> 5; t < n_pend; t += UT / 32) {
+      const int i = S.pend[t];
+      const int x = S.xy[i].x, y = S.xy[i].y;
+      const int cx = x / cs, cy = y / cs;
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1); ++yy)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, gw - 1); ++xx) {
+          const int e = S.cell_start[yy * gw + xx + 1];
+          for (int q = S.cell_start[yy * gw + xx] + (tid & 31); q < e; q += 32) {
+            const int j = S.order[q];
+            if (S.state[j] != 0) continue;
+            const int dx = (int)S.xy[j].x - x, dy = (int)S.xy[j].y - y;
+            if (dx * dx + dy * dy < r2i) S.state[j] = 3;
+          }
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < alive; t += UT) {
+      const int i = listA[t];
+      const unsigned char st = S.state[i];
+      if (st == 1) S.state[i] = 2;
+      else if (st == 0) listB[atomicAdd(&s_alive, 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    alive = s_alive;
+    unsigned short* tl = listA; listA = listB; listB = tl;
+    first_round = false;
+    __syncthreads();
+  }
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  unsigned short* acc = S.pend;
+  for (int i = tid; i < n; i += UT) if (S.state[i] == 2) acc[atomicAdd(&s_n, 1)] = (unsigned short)i;
+  __syncthreads();
+  const int m = s_n;
+  for (int a = tid; a < m; a += UT) {
+    const unsigned long long ka = S.keys[acc[a]];
+    int rank = 0;
+    for (int b = 0; b < m; ++b) rank += S.keys[acc[b]] > ka;
+    if (rank < max_kp) {
+      okb_keypoint kp;
+      kp.x = (float)S.xy[acc[a]].x; kp.y = (float)S.xy[acc[a]].y; kp.size = 12.0f; kp.angle = 0.0f;
       kp.response = (float)(int32_t)(uint32_t)(ka >> 32); kp.octave = 0;
       kps[rank] = kp;
     }
@@ -587,11 +724,15 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   UniScratch us{S.d_cell_start, S.d_cell_cur, S.d_order, S.d_state, S.d_acc, S.d_rounds, S.d_rounds + kMaxCand, S.d_rounds + 2 * kMaxCand,
                 S.d_rounds + 3 * kMaxCand, S.max_cells};
   k_uniformity<<<1, UT, 0, st>>>(S.d_keys, S.d_count, kMaxCand, W, H, prm->uniformity_radius, maxk, us, S.d_kp, S.d_count + 1);
+  {
+    FE_CUDA(c, cudaFuncSetAttribute(k_uniformity_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UniSmem)));
+    k_uniformity_smem<<<1, UT, sizeof(UniSmem), st>>>(S.d_keys, S.d_count, kMaxCand, W, H, prm->uniformity_radius, maxk, S.d_kp, S.d_count + 1);
+  }
   k_integral_rows<<<(H + 1 + 3) / 4, 128, 0, st>>>(S.d_img, W, H, S.d_integral);
   k_integral_cols<<<(W + 1 + 31) / 32, 32 * IC_SEG, 0, st>>>(W, H, S.d_integral);
   k_describe<<<(maxk + 3) / 4, 128, 0, st>>>(S.d_integral, W, H, *cam, d_gC, prm->rotation_invariance, F->d_half, F->d_pi, F->d_pj,
                                              F->d_lut, prm->desc_bytes, S.d_kp, S.d_count + 1, S.d_desc);
-  c->launches += 6;
+  c->launches += 7;
   FE_CUDA(c, cudaGetLastError());
   FE_CUDA(c, cudaMemcpyAsync(S.h_count, S.d_count, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
   FE_CUDA(c, cudaMemcpyAsync(S.h_kp, S.d_kp, sizeof(okb_keypoint) * maxk, cudaMemcpyDeviceToHost, st));
@@ -750,7 +891,7 @@ __global__ void __launch_bounds__(MT) k_hamming_topk(const uint32_t* __restrict_
     if (!active) continue;
     for (int j0 = 0; j0 < nb; j0 += 32) {
       const int j = j0 + lane;
-      float t = 3.0e38f;
+      float t = 3.402823466e+38f;          // FLT_MAX: lanes without a B (tail, skipped) never beat any list entry
       if (j < nb && !sSkip[j]) {
         int dist = 0;
 #pragma unroll
@@ -809,7 +950,9 @@ __global__ void __launch_bounds__(AS_T) k_assign(const okb_pair* __restrict__ to
   okb_pair* P = in_smem ? s_dyn + (size_t)AS_CHUNK * MAX_BEST : pairs;
   int* cnt = in_smem ? reinterpret_cast<int*>(P + nB) : nullptr;   // [nB] how many A's list this b
   __shared__ uint8_t s_skip[AS_CHUNK];
+  __shared__ int s_contested;          // rows that have to take the serial walk
   const int tid = threadIdx.x;
+  if (tid == 0) s_contested = 0;
   for (int b = tid; b < nB; b += AS_T) { P[b].index_a = -1; P[b].distance = 3.402823466e+38f; if (cnt) cnt[b] = 0; }
   for (int a = tid; a < nA; a += AS_T) done[a] = 0;
   __syncthreads();
@@ -825,9 +968,11 @@ __global__ void __launch_bounds__(AS_T) k_assign(const okb_pair* __restrict__ to
       if (skipA && skipA[a]) continue;
       const okb_pair first = topk[(size_t)a * num_best];
       if (first.index_a >= 0 && cnt[first.index_a] == 1) { P[first.index_a].index_a = a; P[first.index_a].distance = first.distance; done[a] = 1; }
+      else if (first.index_a >= 0) atomicAdd(&s_contested, 1);
     }
-  }
-  for (int base = 0; base < nA; base += AS_CHUNK) {
+  } else if (tid == 0) s_contested = nA;
+  __syncthreads();
+  for (int base = 0; base < nA && s_contested > 0; base += AS_CHUNK) {
     const int n_in = min(AS_CHUNK, nA - base);
     __syncthreads();
     for (int e = tid; e < n_in * num_best; e += AS_T) s_top[e] = topk[(size_t)base * num_best + e];
