@@ -213,4 +213,175 @@ __device__ inline void block_cholesky_backward(const double* M, int d, const dou
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Speed/bias chain elimination.  The reduced system orders the unknowns [poses (dc) | speed/bias blocks (9 each)].
+// The speed/bias part A of the matrix is block-tridiagonal (an IMU term couples consecutive frames, priors touch one
+// block), so it is eliminated first:  A = L_A L_A^T block by block (one warp, an 18-row window in registers),
+// Y = L_A^-1 B column by column (one thread per pose column -- column j of block row b only needs column j of block
+// row b-1, so the recursion runs without a barrier), C' = C - Y^T Y on the FP64 tensor cores, and only the dc x dc
+// pose system C' goes through the dense blocked factorisation.
+// ChainView addresses A through one offset per speed/bias row i (block b = i / 9):  ab[ao[i] + k] is the entry in
+// column 9 (b - 1) + k, k = 0..8 the previous block's columns and k = 9 + c this block's column c.  That covers both
+// homes of A: in place in the packed system (ao[i] = tri_row(dc + i) + dc + 9 b - 9) and the banded shared-memory
+// copy used when the system itself lives in global memory (ao[i] = 18 i).  yo[i] = tri_row(dc + i) is row i of Y.
+// ------------------------------------------------------------------------------------------------
+struct ChainView {
+  double* ab;
+  const int* ao;
+  double* M;
+  const int* yo;
+  int dc;
+};
+
+// warp 0 only.  rd[i] receives 1 / L_ii.  Sets *flag on a non-positive pivot.  pipelined: arrives at the named barrier 1 + b after block b
+// (producer side of the hand-off to chain_forward; needs nsb <= 15).
+// Lanes 0..8 hold the rows of the diagonal block A_bb, lanes 9..17 the rows of [A_{b+1,b} | A_{b+1,b+1}]: nine
+// right-looking column steps leave L_bb, L_{b+1,b} and the updated A_{b+1,b+1} in the registers.
+__device__ inline void chain_factor(const ChainView& A, int nsb, double* rd, int* flag, bool pipelined) {
+  const int lane = threadIdx.x & 31;
+  bool bad = false;
+  for (int b = 0; b < nsb; ++b) {
+    const int i0 = 9 * b;
+    const bool mine = lane < 9 || (lane < 18 && b + 1 < nsb);
+    double* q = A.ab + (mine ? A.ao[i0 + lane] + (lane < 9 ? 9 : 0) : 0);
+    double row[18];
+#pragma unroll
+    for (int c = 0; c < 18; ++c) row[c] = (mine && c <= lane) ? q[c] : 0.0;
+    double piv = __shfl_sync(0xffffffffu, row[0], 0);
+    if (!(piv > 0.0)) bad = true;
+    double rs = rsqrt(piv);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const double lij = (lane == j) ? piv * rs : row[j] * rs;
+      row[j] = lij;
+      if (lane == j) rd[i0 + j] = rs;
+      if (j + 1 < 9) {     // the next pivot first: its reciprocal square root overlaps the remaining updates
+        const double l1 = __shfl_sync(0xffffffffu, lij, j + 1);
+        if (lane >= j + 1) row[j + 1] -= lij * l1;
+        piv = __shfl_sync(0xffffffffu, row[j + 1], j + 1);
+        if (!(piv > 0.0)) bad = true;
+        rs = rsqrt(piv);
+      }
+#pragma unroll
+      for (int c = (j + 1 < 9) ? j + 2 : j + 1; c < 18; ++c) {
+        const double lcj = __shfl_sync(0xffffffffu, lij, c);
+        if (lane >= c) row[c] -= lij * lcj;
+      }
+    }
+    if (mine) {
+#pragma unroll
+      for (int c = 0; c < 18; ++c) if (c <= lane) q[c] = row[c];
+    }
+    __syncwarp();
+    if (pipelined) asm volatile("bar.arrive %0, %1;" :: "r"(1 + b), "r"((int)blockDim.x) : "memory");     // releases chain_forward's block row b
+  }
+  if (bad && lane == 0) *flag = 1;
+}
+
+// Y = L_A^-1 [B | g_s] in place: one thread per pose column j of the speed/bias rows of M (j < dc) or the right-hand
+// side (j == dc, the vector rhs_s of length 9 nsb).  No block barrier inside.
+// pipelined: called by the warps >= 1 WHILE warp 0 runs chain_factor; block row b starts when the named barrier
+// 1 + b completes (L_bb and L_{b,b-1} are final), so the recursion trails the factorisation by one block instead of
+// following it.  Needs dc + 1 <= blockDim.x - 32 (one column per thread).  Otherwise all threads call it after a
+// __syncthreads.
+__device__ inline void chain_forward(const ChainView& A, int nsb, const double* rd, double* rhs_s, bool pipelined) {
+  const int dc = A.dc, nthr = (int)blockDim.x, skip = pipelined ? 32 : 0;
+  for (int j0 = 0; j0 <= dc; j0 += nthr - skip) {
+    const int j = j0 + (int)threadIdx.x - skip;
+    const bool act = j <= dc;
+    double yp[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) yp[k] = 0.0;
+    for (int b = 0; b < nsb; ++b) {
+      const int i0 = 9 * b;
+      if (pipelined) {
+        __syncwarp();      // lanes without a column take part in the barrier, converged
+        asm volatile("bar.sync %0, %1;" :: "r"(1 + b), "r"(nthr) : "memory");
+      }
+      if (!act) continue;
+      double t[9];
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        const double* lr = A.ab + A.ao[i0 + r];
+        double s = (j < dc) ? A.M[A.yo[i0 + r] + j] : rhs_s[i0 + r];
+        if (b > 0) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) s -= lr[k] * yp[k];
+        }
+#pragma unroll
+        for (int c = 0; c < 9; ++c) if (c < r) s -= lr[9 + c] * t[c];
+        t[r] = s * rd[i0 + r];
+      }
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        if (j < dc) A.M[A.yo[i0 + r] + j] = t[r]; else rhs_s[i0 + r] = t[r];
+        yp[r] = t[r];
+      }
+    }
+  }
+}
+
+// C' = C - Y^T Y (lower triangle, written to Cp -- which may be M itself) and g' = g_p - Y^T z (in place in rhs_p).
+// Y = the first dc entries of the ns speed/bias rows of M; z = rhs_s.  8x8 tiles, one warp per tile, the contraction over
+// the ns rows of Y as mma.sync.m8n8k4.f64 (fragment layout as in block_cholesky).
+__device__ inline void chain_schur(const ChainView& A, double* Cp, int ns, double* rhs_p, const double* rhs_s) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  const int dc = A.dc;
+  const double* M = A.M;
+  const int nt8 = (dc + 7) >> 3;
+  const int ntt8 = nt8 * (nt8 + 1) / 2;
+  const int g = lane >> 2, t4 = lane & 3;
+  for (int t = warp; t < ntt8; t += nwarps) {
+    int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (ti * (ti + 1) / 2 > t) --ti;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int ia = min(8 * ti + g, dc - 1), jb = min(8 * tj + g, dc - 1);     // rows beyond dc are masked at the store
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll 4
+    for (int k0 = 0; k0 < ns; k0 += 4) {
+      const int k = k0 + t4;
+      const int yo = A.yo[min(k, ns - 1)];
+      double a = M[yo + ia], bq = M[yo + jb];
+      if (k >= ns) { a = 0.0; bq = 0.0; }
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(bq));
+    }
+    const int i = 8 * ti + g, j = 8 * tj + 2 * t4;
+    if (i < dc) {
+      if (j <= i) Cp[tri_row(i) + j] = M[tri_row(i) + j] - d0;
+      if (j + 1 <= i) Cp[tri_row(i) + j + 1] = M[tri_row(i) + j + 1] - d1;
+    }
+  }
+  for (int i = nthr - 1 - tid; i < dc; i += nthr) {     // right-hand side, on the warps that got the fewest tiles
+    double s = rhs_p[i];
+    for (int r = 0; r < ns; ++r) s -= M[A.yo[r] + i] * rhs_s[r];
+    rhs_p[i] = s;
+  }
+}
+
+// u_s = L_A^-T (z - Y u_p): x holds u_p in [0, dc); on entry x[dc + r] = z_r - (Y u_p)_r.  warp 0 only.
+__device__ inline void chain_backward(const ChainView& A, int nsb, const double* rd, double* x) {
+  const int lane = threadIdx.x & 31, dc = A.dc;
+  const int l9 = min(lane, 8);
+  for (int b = nsb - 1; b >= 0; --b) {
+    const int i0 = 9 * b;
+    double t = (lane < 9) ? x[dc + i0 + lane] : 0.0;
+    if (b + 1 < nsb) {      // L_{b+1,b}^T u_{b+1}
+#pragma unroll
+      for (int k = 0; k < 9; ++k) t -= A.ab[A.ao[i0 + 9 + k] + l9] * x[dc + i0 + 9 + k];
+    }
+    double m[9], r9[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { m[j] = (lane < j) ? A.ab[A.ao[i0 + j] + 9 + lane] : 0.0; r9[j] = rd[i0 + j]; }
+#pragma unroll
+    for (int j = 8; j >= 0; --j) {
+      const double uj = __shfl_sync(0xffffffffu, t, j) * r9[j];
+      if (lane == j) t = uj;
+      else if (lane < j) t -= m[j] * uj;
+    }
+    if (lane < 9) x[dc + i0 + lane] = t;
+    __syncwarp();
+  }
+}
+
 }  // namespace okb

@@ -1086,7 +1086,7 @@ struct RoundPlan {
 };
 static int plan_rounds(okb_ctx* c, int first, int count, RoundPlan& P) {
   P = RoundPlan();
-  bool chol_smem = true;
+  int chol_smem = 1;       // solve_mode of k_solve: 1 system in shared memory, 2 pose system + chain band, 0 chain band only
   // Schur accumulator in shared memory if two CTAs per SM still fit (else one CTA; else accumulate in global memory)
   int acc_copies = 1;
   const size_t sm_two = ((size_t)c->smem_per_sm - 2048) / 2;
@@ -1103,16 +1103,21 @@ static int plan_rounds(okb_ctx* c, int first, int count, RoundPlan& P) {
     P.smA = std::max(P.smA, smemA2_bytes(W.K, W.dcp, acc_copies));
     P.max_cx = std::max(P.max_cx, (W.L + L1_THREADS - 1) / L1_THREADS);
     P.max_K = std::max(P.max_K, W.K);
-    if (smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, true) > (size_t)c->smem_optin) chol_smem = false;
+    {      // the roomiest mode this window fits; the range runs in the most modest one (1 > 2 > 0)
+      const int wm = smemS_bytes(W.d, W.dc, W.K, W.marg_n, W.n_imu, 1) <= (size_t)c->smem_optin ? 1
+                   : smemS_bytes(W.d, W.dc, W.K, W.marg_n, W.n_imu, 2) <= (size_t)c->smem_optin ? 2 : 0;
+      if (wm == 0 || chol_smem == 0) chol_smem = 0;
+      else if (wm == 2) chol_smem = 2;
+    }
     P.smQ = std::max(P.smQ, (size_t)W.NS * sizeof(SlotCtx));
     maxL = std::max(maxL, W.L);
   }
   for (int i = first; i < first + count; ++i) {
     const WinDev& W = c->host[i];
-    P.smS = std::max(P.smS, smemS_bytes(W.d, W.K, W.marg_n, W.n_imu, chol_smem));
+    P.smS = std::max(P.smS, smemS_bytes(W.d, W.dc, W.K, W.marg_n, W.n_imu, chol_smem));
   }
   if (P.smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
-  P.acc_copies = acc_copies; P.chol_smem = chol_smem ? 1 : 0;
+  P.acc_copies = acc_copies; P.chol_smem = chol_smem;
   P.solve_threads = (2 * count <= c->sm_count) ? 512 : S_THREADS;      // few windows: one wide CTA per SM (all ranks of a sharded window choose alike)
   P.gxQ = std::max(1, std::min((maxL + 127) / 128, (4 * c->sm_count + count - 1) / count));
   P.shard = c->shard_world > 1 ? 1 : 0;

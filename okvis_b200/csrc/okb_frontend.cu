@@ -407,7 +407,8 @@ struct UniSmem {
   ushort2 xy[UNI_SN];
   unsigned short order[UNI_SN], blocker[UNI_SN], listA[UNI_SN], listB[UNI_SN], pend[UNI_SN];
   unsigned short cell_start[UNI_SC + 1], cell_cur[UNI_SC];
-  unsigned char state[UNI_SN];
+  unsigned int killed[UNI_SN / 32];     // suppressed this round (atomicOr: several accepted neighbours may hit the same candidate)
+  unsigned char state[UNI_SN];          // 0 candidate, 2 accepted, 3 suppressed; only written between the phases
 };
 __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long* __restrict__ keys, const int* __restrict__ count, int cap,
                                                         int W, int H, double radius, int max_kp, okb_keypoint* kps, int* n_out) {
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long
     S.state[i] = 0;
     S.listA[i] = (unsigned short)i;
   }
+  for (int i = tid; i < UNI_SN / 32; i += UT) S.killed[i] = 0u;
   __syncthreads();
   // bucket grid: 32-bit counters alias the (still unused) second live list -- UNI_SC cells fit its 2 * UNI_SN bytes
   unsigned int* cnt32 = reinterpret_cast<unsigned int*>(S.listB);
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long
             if (dx * dx + dy * dy < r2i) { blocked = true; S.blocker[i] = (unsigned short)j; break; }
           }
         }
-      if (!blocked) { S.state[i] = 1; S.pend[atomicAdd(&s_pend, 1)] = (unsigned short)i; }
+      if (!blocked) S.pend[atomicAdd(&s_pend, 1)] = (unsigned short)i;       // two candidates accepted in one round are never neighbours
     }
     __syncthreads();
     const int n_pend = s_pend;
@@ -494,18 +496,20 @@ __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long
           const int e = S.cell_start[yy * gw + xx + 1];
           for (int q = S.cell_start[yy * gw + xx] + (tid & 31); q < e; q += 32) {
             const int j = S.order[q];
-            if (S.state[j] != 0) continue;
+            if (S.state[j] != 0 || j == i) continue;
             const int dx = (int)S.xy[j].x - x, dy = (int)S.xy[j].y - y;
-            if (dx * dx + dy * dy < r2i) S.state[j] = 3;
+            if (dx * dx + dy * dy < r2i) atomicOr(&S.killed[j >> 5], 1u << (j & 31));
           }
         }
     }
     __syncthreads();
+    for (int t = tid; t < n_pend; t += UT) S.state[S.pend[t]] = 2;
+    __syncthreads();
     for (int t = tid; t < alive; t += UT) {
       const int i = listA[t];
-      const unsigned char st = S.state[i];
-      if (st == 1) S.state[i] = 2;
-      else if (st == 0) listB[atomicAdd(&s_alive, 1)] = (unsigned short)i;
+      if (S.state[i] != 0) continue;
+      if ((S.killed[i >> 5] >> (i & 31)) & 1u) S.state[i] = 3;
+      else listB[atomicAdd(&s_alive, 1)] = (unsigned short)i;
     }
     __syncthreads();
     alive = s_alive;

@@ -105,7 +105,7 @@ struct SShared {
   // broadcast scalars
   double cand_cost, cost_lm, stepn2_lm, cost_dense;
   int adopt, terminate, commit_only, fail, spec, chol_flag;
-  int shard_fault;
+  int shard_fault, chain_ok;
   double x2[8];         // landmark-sharded windows: step scalars combined over the ranks
 };
 
@@ -208,7 +208,10 @@ __device__ void dense_priors(const WinDev& W, double* Hd, double* gd, double* co
   *cost_out = cost;
 }
 
-__host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_imu, bool chol_in_smem) {
+// solve_mode: 1 = the packed reduced system lives in shared memory (d <= ~150); 2 = system in global memory, the
+// speed/bias chain band and the dc x dc pose system (after the chain elimination) in shared memory; 0 = system and
+// pose system in global memory, only the chain band in shared memory.
+__host__ __device__ inline size_t smemS_bytes(int d, int dc, int K, int n_marg, int n_imu, int solve_mode) {
   size_t b = sizeof(SShared);
   b = (b + 15) & ~(size_t)15;
   b += (size_t)8 * d * sizeof(double);                     // gd, Ed, ud, rhs, vd, tmp, delta, colk
@@ -216,7 +219,11 @@ __host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_im
   b += (size_t)3 * (((n_marg > 0 ? n_marg : 1) + 1) & ~1) * sizeof(double);   // marg: dchi, e, Jte (even length each: 16-byte loads stay inside)
   b = (b + 31) & ~(size_t)31;
   b += (size_t)CH_NB * ((d + 1 + 3) & ~3) * sizeof(double);  // Cholesky panel (k-major)
-  b += chol_in_smem ? tri_row(d + 1) * sizeof(double) + 16 : 16;        // the reduced system (packed lower triangle) + appended rhs row
+  if (solve_mode == 1) b += tri_row(d + 1) * sizeof(double) + 16;        // the reduced system (packed lower triangle) + appended rhs row
+  else {
+    b += (size_t)(d - dc) * 18 * sizeof(double) + 16;                    // chain band
+    if (solve_mode == 2) b += tri_row(dc + 1) * sizeof(double);          // pose system + appended rhs row
+  }
   return b;
 }
 
@@ -224,7 +231,8 @@ __host__ __device__ inline size_t smemS_bytes(int d, int K, int n_marg, int n_im
 // (latency: the parallel phases -- assembly, trailing updates, landmark back-substitution -- run twice as wide).
 template <int NT>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* __restrict__ wins, int win_first, okb_solve_options opt,
-                                                        int chol_in_smem) {
+                                                        int solve_mode) {
+  const int chol_in_smem = (solve_mode == 1);
   const WinDev& W = wins[win_first + blockIdx.x];
   SolverState* st = W.st;
   if (st->done) return;
@@ -561,15 +569,109 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* _
       }
       __syncthreads();
       PHASE_MARK(2);
-      // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh); row d comes out as z = L^-1 rhs
-      if (!chol_fail) chol_fail = block_cholesky(Mx, d, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8, chol_in_smem != 0);
-      PHASE_MARK(3);
-      if (!chol_fail) {
-        for (int i = tid; i < d; i += NT) s_tmp[i] = Mx[tri_row(d) + i];
+      if (tid == 0) {
+        // the chain elimination needs a block-tridiagonal speed/bias part: IMU terms between consecutive blocks,
+        // at most two neighbouring blocks in the marginalisation prior (anything else takes the plain dense path)
+        int ok = (W.NSB > 0) ? 1 : 0;
+        for (int t = 0; t < W.n_imu; ++t) {
+          const int dsb = (int)W.imu_terms[t].sb1 - (int)W.imu_terms[t].sb0;
+          if (dsb > 1 || dsb < -1) ok = 0;
+        }
+        int lo = 1 << 30, hi = -1;
+        for (int b = 0; b < W.marg_nb; ++b)
+          if (W.marg_kind[b] == OKB_BLOCK_SPEED_BIAS && W.marg_col[b] >= 0) { lo = min(lo, (int)W.marg_idx[b]); hi = max(hi, (int)W.marg_idx[b]); }
+        if (hi - lo > 1) ok = 0;
+        sh->chain_ok = ok;
+      }
+      __syncthreads();
+      if (sh->chain_ok) {
+        // ---- speed/bias chain first (okb_chol.cuh), then the dense blocked Cholesky of the dc x dc pose system
+        const int nsb = W.NSB, ns = 9 * nsb;
+        double* s_band = chol_in_smem ? nullptr : s_big;
+        double* Cp = (solve_mode == 2) ? s_big + (((size_t)ns * 18 + 1) & ~(size_t)1) : Mx;     // pose system C'
+        int* s_yo = reinterpret_cast<int*>(s_delta + dc);       // row offset tables (okb_chol.cuh) in the idle tail of s_delta
+        int* s_ao = s_yo + ns;
+        const ChainView A{s_band ? s_band : Mx, s_ao, Mx, s_yo, dc};
+        for (int i = tid; i < ns; i += NT) {
+          const int yo = (int)tri_row(dc + i);
+          s_yo[i] = yo;
+          s_ao[i] = s_band ? 18 * i : yo + dc + 9 * (i / 9) - 9;
+        }
+        if (s_band) {
+          for (int e = tid; e < ns * 18; e += NT) {
+            const int i = e / 18, j = 9 * (i / 9) - 9 + e % 18;
+            s_band[e] = (j >= 0 && j <= i) ? Mx[tri_row(dc + i) + dc + j] : 0.0;
+          }
+        }
+#ifdef OKB_CHOL_PROF
+        unsigned long long t_cp = clock64();
+#define CHAIN_MARK(i) do { if (tid == 0) { const unsigned long long n_ = clock64(); st->phase_ns[i] += n_ - t_cp; t_cp = n_; } } while (0)
+#else
+#define CHAIN_MARK(i) do { } while (0)
+#endif
+        if (tid == 0) sh->chol_flag = 0;
         __syncthreads();
-        block_cholesky_backward(Mx, d, s_col, s_tmp);
-        for (int i = tid; i < d; i += NT) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
+        if (!chol_fail) {
+          // warp 0 factors the chain; the other warps follow one block behind with Y over B and z over the rhs
+          // (named barriers 1..nsb; long chains or very wide pose parts run the two steps one after the other)
+          const bool pipelined = nsb <= 15 && dc + 1 <= NT - 32;
+          if (warp == 0) chain_factor(A, nsb, s_col + dc, &sh->chol_flag, pipelined);
+          else if (pipelined) chain_forward(A, nsb, s_col + dc, s_rhs + dc, true);
+          if (!pipelined) {
+            __syncthreads();
+            chain_forward(A, nsb, s_col + dc, s_rhs + dc, false);
+          }
+        }
         __syncthreads();
+        if (sh->chol_flag) chol_fail = 1;
+        CHAIN_MARK(11);
+        if (!chol_fail) {
+          CHAIN_MARK(12);
+          chain_schur(A, Cp, ns, s_rhs, s_rhs + dc);
+          __syncthreads();
+          CHAIN_MARK(13);
+          // appended right-hand side row of the pose system; in place it takes the slot of Y's first row, which
+          // is parked in s_delta until the pose solve is done
+          for (int i = tid; i < dc; i += NT) {
+            if (Cp == Mx) s_delta[i] = Mx[tri_row(dc) + i];
+            Cp[tri_row(dc) + i] = s_rhs[i];
+          }
+          __syncthreads();
+          chol_fail = block_cholesky(Cp, dc, dc + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8, solve_mode != 0);
+        }
+        PHASE_MARK(3);
+        if (!chol_fail) {
+          for (int i = tid; i < dc; i += NT) s_tmp[i] = Cp[tri_row(dc) + i];
+          __syncthreads();
+          CHAIN_MARK(7);      // row swap + dense factorisation (its sub-phases are slots 8..10)
+          block_cholesky_backward(Cp, dc, s_col, s_tmp);
+          CHAIN_MARK(14);
+          if (Cp == Mx) for (int i = tid; i < dc; i += NT) Mx[tri_row(dc) + i] = s_delta[i];
+          __syncthreads();
+          for (int r = tid; r < ns; r += NT) {        // z - Y u_p
+            const double* yr = Mx + s_yo[r];
+            double sacc = s_rhs[dc + r];
+            for (int i = 0; i < dc; ++i) sacc -= yr[i] * s_tmp[i];
+            s_tmp[dc + r] = sacc;
+          }
+          __syncthreads();
+          if (warp == 0) chain_backward(A, nsb, s_col + dc, s_tmp);
+          __syncthreads();
+          CHAIN_MARK(15);
+          for (int i = tid; i < d; i += NT) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
+          __syncthreads();
+        }
+      } else {
+        // ---- dense Cholesky (lower), blocked right-looking (okb_chol.cuh); row d comes out as z = L^-1 rhs
+        if (!chol_fail) chol_fail = block_cholesky(Mx, d, d + 1, s_panel, ld_p, s_col, &sh->chol_flag, st->phase_ns + 8, chol_in_smem != 0);
+        PHASE_MARK(3);
+        if (!chol_fail) {
+          for (int i = tid; i < d; i += NT) s_tmp[i] = Mx[tri_row(d) + i];
+          __syncthreads();
+          block_cholesky_backward(Mx, d, s_col, s_tmp);
+          for (int i = tid; i < d; i += NT) { s_u[i] = s_tmp[i]; W.ud[i] = s_tmp[i]; }
+          __syncthreads();
+        }
       }
     }
     PHASE_MARK(4);
