@@ -56,12 +56,16 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
   okb_ctx* c = new okb_ctx();
   c->device = device_id;
   c->max_windows = max_windows;
-  if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // the landmark / solve chain is the critical path of a round: it runs at the highest stream priority, the IMU terms
+  // (side stream, a long tail of one-warp CTAs) at the lowest, so they fill what the chain leaves idle
+  int prio_least = 0, prio_greatest = 0;
+  if (cudaSetDevice(device_id) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
     g_create_error = "cudaSetDevice / cudaStreamCreate failed";
     delete c;
     return OKB_ERR_CUDA;
   }
-  if (cudaStreamCreateWithFlags(&c->stream_imu, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaStreamCreateWithPriority(&c->stream_imu, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_round, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_imu, cudaEventDisableTiming) != cudaSuccess ||
       create_transfer_stream(&c->stream_xfer) != cudaSuccess ||
@@ -89,6 +93,8 @@ extern "C" int okb_ctx_create(int device_id, int max_windows, okb_ctx** out) {
   }
   cudaMemset(c->d_states, 0, sizeof(SolverState) * max_windows);
   cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
+  cudaFuncSetAttribute(k_imu, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemI_bytes());
+  cudaFuncSetAttribute(k_imu, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_solve<S_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
   cudaFuncSetAttribute(k_solve<S_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_solve<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin);
@@ -1128,10 +1134,14 @@ static int plan_rounds(okb_ctx* c, int first, int count, RoundPlan& P) {
 static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_options& opt, int rounds, const RoundPlan& P) {
   for (int r = 0; r < rounds; ++r) {
     const dim3 gridA(P.max_chunks, count);
-    if (P.max_imu > 0) {   // IMU terms only depend on the previous round's candidate: run beside the landmark kernels
+    static const bool imu_serial = getenv("OKB_IMU_SERIAL") != nullptr;     // diagnostics: k_imu on the main stream, ahead of the landmark kernels
+    if (P.max_imu > 0 && imu_serial) {
+      k_imu<<<dim3((P.max_imu + 32 / IMU_G - 1) / (32 / IMU_G), count), 32, smemI_bytes(), c->stream>>>(c->d_wins, first);
+      c->launches += 1;
+    } else if (P.max_imu > 0) {   // IMU terms only depend on the previous round's candidate: run beside the landmark kernels
       cudaEventRecord(c->ev_round, c->stream);
       cudaStreamWaitEvent(c->stream_imu, c->ev_round, 0);
-      k_imu<<<dim3(P.max_imu, count), 32, 0, c->stream_imu>>>(c->d_wins, first);
+      k_imu<<<dim3((P.max_imu + 32 / IMU_G - 1) / (32 / IMU_G), count), 32, smemI_bytes(), c->stream_imu>>>(c->d_wins, first);
       cudaEventRecord(c->ev_imu, c->stream_imu);
       c->launches += 1;
     }
@@ -1145,7 +1155,7 @@ static int launch_rounds(okb_ctx* c, int first, int count, const okb_solve_optio
     } else if (P.max_chunks > 1) { k_reduce_partials<<<dim3(8, count), 256, 0, c->stream>>>(c->d_wins, first); c->launches += 1; }
     prof_end(c);
     c->launches += 3;
-    if (P.max_imu > 0) cudaStreamWaitEvent(c->stream, c->ev_imu, 0);
+    if (P.max_imu > 0 && !imu_serial) cudaStreamWaitEvent(c->stream, c->ev_imu, 0);
     prof_begin(c, 1);
     if (P.solve_threads == 512) k_solve<512><<<count, 512, P.smS, c->stream>>>(c->d_wins, first, opt, P.chol_smem);
     else k_solve<S_THREADS><<<count, S_THREADS, P.smS, c->stream>>>(c->d_wins, first, opt, P.chol_smem);

@@ -21,6 +21,18 @@ struct WarpCtx {  // one warp
   __device__ __forceinline__ int lanes() const { return 32; }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
+// G lanes of a warp (G = 8, 16, 32): 32 / G independent groups share one warp, each working on its own term.  The
+// small algebra every lane replicates is then issued once for 32 / G terms; the groups may diverge freely (sync()
+// only names the group's own lanes).
+template <int G>
+struct GroupCtx {
+  __device__ __forceinline__ int lane() const { return threadIdx.x & (G - 1); }
+  __device__ __forceinline__ int lanes() const { return G; }
+  __device__ __forceinline__ void sync() const {
+    const unsigned m = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    __syncwarp(m);
+  }
+};
 #endif
 
 // Device-resident cache of one ImuError term (the reference's mutable members, ImuError.hpp:251-276).

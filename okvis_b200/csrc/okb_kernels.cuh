@@ -57,17 +57,21 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Kernel I: one warp per IMU term (255 registers available, no spills): residual, the four minimal
+// Kernel I: IMU_G lanes per IMU term (255 registers available, no spills): residual, the four minimal
 // Jacobians, and the term's contribution  [J0 J1 J2 J3]^T [J0 J1 J2 J3] (30x30), J^T r (30), cost.
 // Re-preintegrates exactly when the reference's Evaluate() would.
 // ------------------------------------------------------------------------------------------------
+constexpr int IMU_G = 16;      // lanes per IMU term: 32 / IMU_G terms per warp
+__host__ __device__ inline size_t smemI_bytes() { return (size_t)(32 / IMU_G) * kImuScratch * sizeof(double); }
 __global__ void __launch_bounds__(32) k_imu(const WinDev* __restrict__ wins, int win_first) {
   const WinDev& W = wins[win_first + blockIdx.y];
   if (W.st->done) return;
-  const int t = blockIdx.x;
+  const int grp = (threadIdx.x & 31) / IMU_G;
+  const int t = blockIdx.x * (32 / IMU_G) + grp;
   if (t >= W.n_imu) return;
-  __shared__ double buf[kImuScratch];
-  WarpCtx cx;
+  extern __shared__ __align__(16) double imu_buf[];
+  double* buf = imu_buf + (size_t)grp * kImuScratch;
+  GroupCtx<IMU_G> cx;
   ImuWork wk{buf, buf + 225, buf + 450, buf + 675 + 450, buf + 675 + 900 + 16};   // P2 aliases the SF buffer (unused while preintegrating)
   double* F01 = buf + 675;
   double* SF = buf + 675 + 450;
@@ -76,19 +80,19 @@ __global__ void __launch_bounds__(32) k_imu(const WinDev* __restrict__ wins, int
   imu_evaluate(cx, W.samples + T.sample_offset, (int)T.sample_count, W.imu_params, T.t0_ns, T.t1_ns, W.pose_c + 7 * T.pose0,
                W.sb_c + 9 * T.sb0, W.pose_c + 7 * T.pose1, W.sb_c + 9 * T.sb1, W.imu_cache + t, wk, F01, (double*)nullptr, r15, SF);
   double* out = W.imu_out + (size_t)t * kImuOut;
-  const int lane = threadIdx.x;
-  for (int e = lane; e < 900; e += 32) {
+  const int lane = cx.lane();
+  for (int e = lane; e < 900; e += IMU_G) {
     const int a = e / 30, b = e % 30;
     double s = 0;
 #pragma unroll
     for (int k = 0; k < 15; ++k) s += SF[k * 30 + a] * SF[k * 30 + b];
     out[e] = s;
   }
-  if (lane < 30) {
+  for (int e = lane; e < 30; e += IMU_G) {
     double s = 0;
 #pragma unroll
-    for (int k = 0; k < 15; ++k) s += SF[k * 30 + lane] * r15[k];
-    out[900 + lane] = s;
+    for (int k = 0; k < 15; ++k) s += SF[k * 30 + e] * r15[k];
+    out[900 + e] = s;
   }
   if (lane == 0) {
     double c = 0;
@@ -276,29 +280,43 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* _
   for (int i = tid; i < d; i += NT) gd[i] = 0.0;
   __syncthreads();
   double cost_dense_local = 0.0;   // accumulated by thread 0
-  // IMU terms were evaluated by k_imu (one warp per term); add their 30x30 blocks term by term
+  // IMU terms were evaluated by k_imu; add their 30x30 blocks.  Terms that form a chain over consecutive frames
+  // (term t ends where term t+1 starts, indices strictly increasing -- what Estimator::addStates builds) are added in
+  // two passes, even terms then odd terms: terms of equal parity touch disjoint blocks.  Anything else goes term by term.
+  bool imu_chain = true;
   for (int t = 0; t < W.n_imu; ++t) {
     const okb_imu_term& T = W.imu_terms[t];
-    const double* out = W.imu_out + (size_t)t * kImuOut;
-    const int offs[4] = {6 * (int)T.pose0, dc + 9 * (int)T.sb0, 6 * (int)T.pose1, dc + 9 * (int)T.sb1};
-    for (int e = tid; e < 930; e += NT) {
+    if (!(T.pose1 > T.pose0 && T.sb1 > T.sb0)) imu_chain = false;
+    if (t + 1 < W.n_imu && (W.imu_terms[t + 1].pose0 < T.pose1 || W.imu_terms[t + 1].sb0 < T.sb1)) imu_chain = false;
+  }
+  const int n_pass = imu_chain ? min(2, W.n_imu) : W.n_imu;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int t_stride = imu_chain ? 2 : 1;
+    const int n_in_pass = imu_chain ? (W.n_imu - pass + 1) / 2 : 1;
+    for (int ee = tid; ee < n_in_pass * 931; ee += NT) {
+      const int t = pass + t_stride * (ee / 931), e = ee % 931;
+      const okb_imu_term& T = W.imu_terms[t];
+      const double* out = W.imu_out + (size_t)t * kImuOut;
       if (e < 900) {
         const int a = e / 30, b = e % 30;
         const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
         const int bb = (b < 6) ? 0 : (b < 15) ? 1 : (b < 21) ? 2 : 3;
         const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
         const int lb = b - ((bb == 0) ? 0 : (bb == 1) ? 6 : (bb == 2) ? 15 : 21);
-        hd_add(Hd, offs[ba] + la, offs[bb] + lb, out[e]);
-      } else {
+        const int oa = (ba == 0) ? 6 * (int)T.pose0 : (ba == 1) ? dc + 9 * (int)T.sb0 : (ba == 2) ? 6 * (int)T.pose1 : dc + 9 * (int)T.sb1;
+        const int ob = (bb == 0) ? 6 * (int)T.pose0 : (bb == 1) ? dc + 9 * (int)T.sb0 : (bb == 2) ? 6 * (int)T.pose1 : dc + 9 * (int)T.sb1;
+        hd_add(Hd, oa + la, ob + lb, out[e]);
+      } else if (e < 930) {
         const int a = e - 900;
         const int ba = (a < 6) ? 0 : (a < 15) ? 1 : (a < 21) ? 2 : 3;
         const int la = a - ((ba == 0) ? 0 : (ba == 1) ? 6 : (ba == 2) ? 15 : 21);
-        gd[offs[ba] + la] += out[e];
+        const int oa = (ba == 0) ? 6 * (int)T.pose0 : (ba == 1) ? dc + 9 * (int)T.sb0 : (ba == 2) ? 6 * (int)T.pose1 : dc + 9 * (int)T.sb1;
+        gd[oa + la] += out[e];
       }
     }
-    if (tid == 0) cost_dense_local += out[930];
     __syncthreads();
   }
+  if (tid == 0) for (int t = 0; t < W.n_imu; ++t) cost_dense_local += W.imu_out[(size_t)t * kImuOut + 930];
   // priors (warp 0)
   if (warp == 0) {
     double c = 0;
@@ -412,11 +430,16 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* _
     __syncthreads();
     if (tid == 0) { st->shard_epoch = epoch; st->shard_wait_ns += globaltimer_ns() - t_w0; st->shard_rounds += 1; }
   }
-  double cost_lm = 0.0, stepn2_lm = 0.0;
   const int n_cx = sharded ? 1 : (L + L1_THREADS - 1) / L1_THREADS;
-  for (int i = 0; i < n_cx * K; ++i) {   // fixed order, replicated in all threads (small)
-    cost_lm += W.partH[(size_t)i * kPartH + 27];
-    stepn2_lm += W.partH[(size_t)i * kPartH + 28];
+  if (warp == 0) {     // cost and step-norm sums of the landmark kernels: lane-strided partials, fixed shuffle tree
+    double c_ = 0.0, s_ = 0.0;
+    for (int i = lane; i < n_cx * K; i += 32) {
+      c_ += W.partH[(size_t)i * kPartH + 27];
+      s_ += W.partH[(size_t)i * kPartH + 28];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c_ += __shfl_xor_sync(0xffffffffu, c_, o); s_ += __shfl_xor_sync(0xffffffffu, s_, o); }
+    if (lane == 0) { sh->cost_lm = c_; sh->stepn2_lm = s_; }
   }
   // H_pp / g_p block contributions
   for (int i = tid; i < 27 * K; i += NT) {
@@ -448,6 +471,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* _
   if (tid == 0) {
     const unsigned long long now = globaltimer_ns();
     sh->adopt = 0; sh->terminate = 0; sh->commit_only = 0; sh->fail = 0;
+    const double cost_lm = sh->cost_lm, stepn2_lm = sh->stepn2_lm;
     const double cand_cost = cost_lm + cost_dense;
     sh->cand_cost = cand_cost;
     if (mode == MODE_INIT) {
@@ -537,28 +561,28 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) k_solve(const WinDev* _
     double VHV_dd = 0.0;
     int chol_fail = sh->fail;
     if (!skip_solve) {
-      // VHV (dense-dense part): v^T H v
-      double vhv_loc = 0.0;
-      for (int i = tid; i < d; i += NT) {     // v^T H v from the lower triangle
-        const double* hrow = Hd + tri_row(i);
-        double s = 0;
-        for (int j = 0; j < i; ++j) s += hrow[j] * s_v[j];
-        vhv_loc += s_v[i] * (2.0 * s + hrow[i] * s_v[i]);
-      }
-      VHV_dd = block_sum(vhv_loc, sh->red);
-      // reduced system M = Hd + mu E - [Sacc], rhs = g - [sum Y z]
+      // One pass over the packed dense Hessian, a warp per row (lanes over the columns: no index arithmetic, coalesced
+      // partials): v^T H v of the dense-dense part, and the reduced system M = Hd + mu E - [Sacc] written in place
+      // when the system lives in shared memory.
       double* Mx = chol_in_smem ? s_big : W.chol;
       const double mu = st->mu;
-      for (int i = tid; i < d * d; i += NT) {
-        const int r0 = i / d, c0 = i % d;
-        if (c0 > r0) continue;                      // the factorisation only references the lower triangle
-        double v = Hd[tri_row(r0) + c0];            // in place when the system lives in shared memory
-        if (r0 == c0) v += mu * s_E[r0];
-        if (r0 < dc && c0 < dc) {
-          v -= W.partA[(size_t)r0 * dcp + c0];     // chunk partials were summed by k_reduce_partials
+      double vhv_loc = 0.0;
+      for (int r0 = warp; r0 < d; r0 += NT / 32) {
+        const double* hrow = Hd + tri_row(r0);
+        double* mrow = Mx + tri_row(r0);
+        const double* arow = W.partA + (size_t)r0 * dcp;      // chunk partials were summed by k_reduce_partials
+        double sacc = 0.0;
+        for (int c0 = lane; c0 <= r0; c0 += 32) {
+          const double h = hrow[c0];
+          double v = h;
+          if (c0 < r0) sacc += h * s_v[c0];
+          else { vhv_loc += s_v[r0] * h * s_v[r0]; v += mu * s_E[r0]; }
+          if (r0 < dc) v -= arow[c0];
+          mrow[c0] = v;
         }
-        Mx[tri_row(r0) + c0] = v;
+        vhv_loc += 2.0 * s_v[r0] * sacc;
       }
+      VHV_dd = block_sum(vhv_loc, sh->red);
       for (int i = tid; i < d; i += NT) {
         double v = s_g[i];
         if (i < dc) {
