@@ -416,7 +416,9 @@ typedef struct okb_pair {          /* DenseMatcher::Pairing */
 
 /* DenseMatcher::match with the plain Hamming MatchingAlgorithm: per-A top-`num_best` lists
  * (out_topk [nA][num_best], may be NULL), greedy mutual assignment in sequential A-ascending order,
- * per-B winners (out_pairs [nB]).  use_ratio / ratio_threshold mirror useDistanceRatioThreshold_. */
+ * per-B winners (out_pairs [nB]).  use_ratio / ratio_threshold mirror useDistanceRatioThreshold_.
+ * nA == 0 or nB == 0 is legal (no matches: every out_pairs entry is {-1, threshold}), like DenseMatcher::match on an
+ * empty MatchingAlgorithm; the same holds for the gated and the candidate-list calls. */
 int okb_hamming_match(okb_ctx* ctx, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes,
                       const uint8_t* skipA, const uint8_t* skipB, float threshold, int num_best,
                       int use_ratio, float ratio_threshold, okb_pair* out_topk, okb_pair* out_pairs);

@@ -380,7 +380,7 @@ class Context:
         A = np.ascontiguousarray(A, dtype=np.uint8)
         B = np.ascontiguousarray(B, dtype=np.uint8)
         nA, nB, nbytes = A.shape[0], B.shape[0], A.shape[1]
-        cap = cap or nA * nB
+        cap = cap or max(nA * nB, 1)
         row_ptr = np.zeros(nA + 1, np.uint32)
         col = np.zeros(cap, np.uint32)
         dist = np.zeros(cap, np.uint16)

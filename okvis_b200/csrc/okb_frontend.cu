@@ -401,15 +401,26 @@ __global__ void __launch_bounds__(UT) k_uniformity(const unsigned long long* __r
 
 // The same algorithm with every hot array in shared memory (the common case: a few thousand NMS candidates, a few
 // thousand cells): one CTA walks dependent chains of loads, so the latency of each load is what the kernel costs.
+// The candidates are re-indexed by their position q in the bucket grid and kept as 16-byte records {key, x, y} in
+// that order: visiting a neighbour is ONE 16-byte load plus the independent state byte (the global-memory kernel
+// chases order -> key -> state -> xy).  The scan starts with the candidate's own cell (where a blocker is most likely),
+// suppression runs one thread per (accepted candidate, neighbouring cell), and the final ranking walks the accepted
+// records with loads that do not depend on each other.
 // Images with more candidates / cells than fit take the global-memory kernel above (both are launched, one returns).
+struct __align__(16) UniRec { unsigned long long key; unsigned short x, y; unsigned int pad; };
 struct UniSmem {
-  unsigned long long keys[UNI_SN];
-  ushort2 xy[UNI_SN];
-  unsigned short order[UNI_SN], blocker[UNI_SN], listA[UNI_SN], listB[UNI_SN], pend[UNI_SN];
-  unsigned short cell_start[UNI_SC + 1], cell_cur[UNI_SC];
+  UniRec rec[UNI_SN];
+  unsigned short blocker[UNI_SN], listA[UNI_SN], listB[UNI_SN], pend[UNI_SN];
+  unsigned short cell_start[UNI_SC + 1];
   unsigned int killed[UNI_SN / 32];     // suppressed this round (atomicOr: several accepted neighbours may hit the same candidate)
   unsigned char state[UNI_SN];          // 0 candidate, 2 accepted, 3 suppressed; only written between the phases
 };
+#ifdef OKB_UNI_PROF
+__device__ unsigned long long g_uni_prof[8];     // cycles of thread 0 per phase (diagnostics build)
+#define UNI_MARK(i) do { if (tid == 0) { const unsigned long long n_ = clock64(); g_uni_prof[i] += n_ - t_up; t_up = n_; } } while (0)
+#else
+#define UNI_MARK(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long* __restrict__ keys, const int* __restrict__ count, int cap,
                                                         int W, int H, double radius, int max_kp, okb_keypoint* kps, int* n_out) {
   extern __shared__ __align__(16) unsigned char uni_raw[];
@@ -422,25 +433,23 @@ __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long
   const int gw = (W + cs - 1) / cs, gh = (H + cs - 1) / cs, n_cells = gw * gh;
   if (!uni_fits_smem(n, n_cells)) return;
   const int r2i = (int)ceil(radius * radius - 1e-9);
-  for (int c = tid; c < n_cells; c += UT) S.cell_cur[c] = 0;
-  for (int i = tid; i < n; i += UT) {
-    const unsigned long long k = keys[i];
-    const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull);
-    S.keys[i] = k;
-    S.xy[i] = make_ushort2((unsigned short)(idx % (uint32_t)W), (unsigned short)(idx / (uint32_t)W));
-    S.state[i] = 0;
-    S.listA[i] = (unsigned short)i;
-  }
-  for (int i = tid; i < UNI_SN / 32; i += UT) S.killed[i] = 0u;
-  __syncthreads();
+#ifdef OKB_UNI_PROF
+  unsigned long long t_up = clock64();
+  if (tid < 8) g_uni_prof[tid] = 0;
+#endif
   // bucket grid: 32-bit counters alias the (still unused) second live list -- UNI_SC cells fit its 2 * UNI_SN bytes
   unsigned int* cnt32 = reinterpret_cast<unsigned int*>(S.listB);
+  for (int c = tid; c < n_cells; c += UT) cnt32[c] = 0u;
+  for (int i = tid; i < UNI_SN / 32; i += UT) S.killed[i] = 0u;
+  for (int i = tid; i < n; i += UT) { S.state[i] = 0; S.listA[i] = (unsigned short)i; }
+  __syncthreads();
+  for (int i = tid; i < n; i += UT) {
+    const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull);
+    atomicAdd(&cnt32[((idx / (uint32_t)W) / cs) * gw + (idx % (uint32_t)W) / cs], 1u);
+  }
+  __syncthreads();
+  UNI_MARK(0);
   {
-
-    for (int c = tid; c < n_cells; c += UT) cnt32[c] = 0u;
-    __syncthreads();
-    for (int i = tid; i < n; i += UT) atomicAdd(&cnt32[(S.xy[i].y / cs) * gw + S.xy[i].x / cs], 1u);
-    __syncthreads();
     int run = 0;
     for (int base = 0; base < n_cells; base += UT) {
       const int c = base + tid;
@@ -455,9 +464,17 @@ __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long
     __syncthreads();
     for (int c = tid; c < n_cells; c += UT) cnt32[c] = S.cell_start[c];
     __syncthreads();
-    for (int i = tid; i < n; i += UT) { const unsigned int pos = atomicAdd(&cnt32[(S.xy[i].y / cs) * gw + S.xy[i].x / cs], 1u); S.order[pos] = (unsigned short)i; }
+    for (int i = tid; i < n; i += UT) {       // the order inside a cell is whatever the atomics give; the result does not depend on it
+      const unsigned long long k = keys[i];
+      const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull);
+      const uint32_t x = idx % (uint32_t)W, y = idx / (uint32_t)W;
+      const unsigned int pos = atomicAdd(&cnt32[(y / cs) * gw + x / cs], 1u);
+      UniRec r; r.key = k; r.x = (unsigned short)x; r.y = (unsigned short)y; r.pad = 0u;
+      S.rec[pos] = r;
+    }
     __syncthreads();
   }
+  UNI_MARK(1);
   int alive = n, rounds = 0;
   bool first_round = true;
   unsigned short* listA = S.listA;
@@ -466,43 +483,49 @@ __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long
     ++rounds;
     if (tid == 0) { s_alive = 0; s_pend = 0; }
     __syncthreads();
+    // accept: a candidate with no undecided neighbour of higher priority (accepted neighbours cannot exist: their
+    // neighbourhood was suppressed in the round that accepted them)
     for (int t = tid; t < alive; t += UT) {
       const int i = listA[t];
-      if (!first_round && S.state[S.blocker[i]] <= 1) continue;
-      const int x = S.xy[i].x, y = S.xy[i].y;
-      const unsigned long long ki = S.keys[i];
-      bool blocked = false;
+      if (!first_round && S.state[S.blocker[i]] == 0) continue;      // the candidate that blocked it is still undecided
+      const UniRec me = S.rec[i];
+      const int x = me.x, y = me.y;
       const int cx = x / cs, cy = y / cs;
-      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1) && !blocked; ++yy)
-        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, gw - 1) && !blocked; ++xx) {
-          const int e = S.cell_start[yy * gw + xx + 1];
-          for (int q = S.cell_start[yy * gw + xx]; q < e; ++q) {
-            const int j = S.order[q];
-            if (S.keys[j] <= ki || S.state[j] > 1) continue;
-            const int dx = (int)S.xy[j].x - x, dy = (int)S.xy[j].y - y;
-            if (dx * dx + dy * dy < r2i) { blocked = true; S.blocker[i] = (unsigned short)j; break; }
-          }
+      bool blocked = false;
+#pragma unroll 1
+      for (int k = 0; k < 9 && !blocked; ++k) {          // own cell first
+        const int kk = (k == 0) ? 4 : (k <= 4 ? k - 1 : k);
+        const int yy = cy + kk / 3 - 1, xx = cx + kk % 3 - 1;
+        if (yy < 0 || yy >= gh || xx < 0 || xx >= gw) continue;
+        const int e = S.cell_start[yy * gw + xx + 1];
+        for (int q = S.cell_start[yy * gw + xx]; q < e; ++q) {
+          const UniRec o = S.rec[q];
+          if (o.key <= me.key || S.state[q] != 0) continue;
+          const int dx = (int)o.x - x, dy = (int)o.y - y;
+          if (dx * dx + dy * dy < r2i) { blocked = true; S.blocker[i] = (unsigned short)q; break; }
         }
+      }
       if (!blocked) S.pend[atomicAdd(&s_pend, 1)] = (unsigned short)i;       // two candidates accepted in one round are never neighbours
     }
     __syncthreads();
+    UNI_MARK(2);
+    // suppress: one thread per (accepted candidate, neighbouring cell)
     const int n_pend = s_pend;
-    for (int t = tid >> 5; t < n_pend; t += UT / 32) {
-      const int i = S.pend[t];
-      const int x = S.xy[i].x, y = S.xy[i].y;
-      const int cx = x / cs, cy = y / cs;
-      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gh - 1); ++yy)
-        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, gw - 1); ++xx) {
-          const int e = S.cell_start[yy * gw + xx + 1];
-          for (int q = S.cell_start[yy * gw + xx] + (tid & 31); q < e; q += 32) {
-            const int j = S.order[q];
-            if (S.state[j] != 0 || j == i) continue;
-            const int dx = (int)S.xy[j].x - x, dy = (int)S.xy[j].y - y;
-            if (dx * dx + dy * dy < r2i) atomicOr(&S.killed[j >> 5], 1u << (j & 31));
-          }
-        }
+    for (int t = tid; t < n_pend * 9; t += UT) {
+      const int i = S.pend[t / 9], kk = t % 9;
+      const UniRec me = S.rec[i];
+      const int yy = (int)me.y / cs + kk / 3 - 1, xx = (int)me.x / cs + kk % 3 - 1;
+      if (yy < 0 || yy >= gh || xx < 0 || xx >= gw) continue;
+      const int e = S.cell_start[yy * gw + xx + 1];
+      for (int q = S.cell_start[yy * gw + xx]; q < e; ++q) {
+        if (S.state[q] != 0 || q == i) continue;
+        const UniRec o = S.rec[q];
+        const int dx = (int)o.x - (int)me.x, dy = (int)o.y - (int)me.y;
+        if (dx * dx + dy * dy < r2i) atomicOr(&S.killed[q >> 5], 1u << (q & 31));
+      }
     }
     __syncthreads();
+    UNI_MARK(3);
     for (int t = tid; t < n_pend; t += UT) S.state[S.pend[t]] = 2;
     __syncthreads();
     for (int t = tid; t < alive; t += UT) {
@@ -516,24 +539,44 @@ __global__ void __launch_bounds__(UT) k_uniformity_smem(const unsigned long long
     unsigned short* tl = listA; listA = listB; listB = tl;
     first_round = false;
     __syncthreads();
+    UNI_MARK(4);
   }
   if (tid == 0) s_n = 0;
   __syncthreads();
   unsigned short* acc = S.pend;
   for (int i = tid; i < n; i += UT) if (S.state[i] == 2) acc[atomicAdd(&s_n, 1)] = (unsigned short)i;
   __syncthreads();
+  UNI_MARK(5);
   const int m = s_n;
+  // ranking by key (descending) = the order the greedy walk would have accepted them in.  The accepted keys are first
+  // packed into the dead live lists (blocker | listA | listB are contiguous: 3 * UNI_SN u16 = room for 3 * UNI_SN / 4
+  // keys) so that the m^2 comparisons read two keys per 16-byte load, nothing dependent; more accepted candidates
+  // than fit there take the indirect loop.
+  unsigned long long* ck = reinterpret_cast<unsigned long long*>(S.blocker);
+  const bool packed = m <= 3 * UNI_SN / 4 - 1;
+  if (packed) {
+    for (int a = tid; a < m; a += UT) ck[a] = S.rec[acc[a]].key;
+    if (tid == 0) ck[m] = 0ull;                         // pad to an even count (key 0 is below every real key)
+  }
+  __syncthreads();
   for (int a = tid; a < m; a += UT) {
-    const unsigned long long ka = S.keys[acc[a]];
+    const UniRec me = S.rec[acc[a]];
     int rank = 0;
-    for (int b = 0; b < m; ++b) rank += S.keys[acc[b]] > ka;
+    if (packed) {
+      const ulonglong2* ck2 = reinterpret_cast<const ulonglong2*>(ck);
+#pragma unroll 4
+      for (int b = 0; b < (m + 1) / 2; ++b) { const ulonglong2 k2 = ck2[b]; rank += (k2.x > me.key) + (k2.y > me.key); }
+    } else {
+      for (int b = 0; b < m; ++b) rank += S.rec[acc[b]].key > me.key;
+    }
     if (rank < max_kp) {
       okb_keypoint kp;
-      kp.x = (float)S.xy[acc[a]].x; kp.y = (float)S.xy[acc[a]].y; kp.size = 12.0f; kp.angle = 0.0f;
-      kp.response = (float)(int32_t)(uint32_t)(ka >> 32); kp.octave = 0;
+      kp.x = (float)me.x; kp.y = (float)me.y; kp.size = 12.0f; kp.angle = 0.0f;
+      kp.response = (float)(int32_t)(uint32_t)(me.key >> 32); kp.octave = 0;
       kps[rank] = kp;
     }
   }
+  UNI_MARK(6);
   if (tid == 0) { *n_out = min(m, max_kp); n_out[1] = rounds; }
 }
 
@@ -742,7 +785,11 @@ extern "C" int okb_detect_describe(okb_ctx* c, int cam_slot, const uint8_t* img,
   FE_CUDA(c, cudaMemcpyAsync(S.h_kp, S.d_kp, sizeof(okb_keypoint) * maxk, cudaMemcpyDeviceToHost, st));
   FE_CUDA(c, cudaMemcpyAsync(S.h_desc, S.d_desc, (size_t)maxk * prm->desc_bytes, cudaMemcpyDeviceToHost, st));
   FE_CUDA(c, cudaStreamSynchronize(st));
-  { static const bool dbg = getenv("OKB_FE_DEBUG") != nullptr; if (dbg) fprintf(stderr, "[okb frontend] candidates %d accepted %d uniformity rounds %d\n", S.h_count[0], S.h_count[1], S.h_count[2]); }
+  { static const bool dbg = getenv("OKB_FE_DEBUG") != nullptr; if (dbg) fprintf(stderr, "[okb frontend] candidates %d accepted %d uniformity rounds %d\n", S.h_count[0], S.h_count[1], S.h_count[2]);
+#ifdef OKB_UNI_PROF
+    if (dbg) { unsigned long long pr[8]; cudaMemcpyFromSymbol(pr, g_uni_prof, sizeof(pr)); fprintf(stderr, "[okb frontend] uniformity cycles: load %llu grid %llu accept %llu kill %llu rebuild %llu compact %llu rank %llu\n", pr[0], pr[1], pr[2], pr[3], pr[4], pr[5], pr[6]); }
+#endif
+  }
   if (S.h_count[0] > kMaxCand) { c->set_error("too many corner candidates"); return OKB_ERR_CAPACITY; }
   const int n = S.h_count[1];
   std::memcpy(out_kp, S.h_kp, sizeof(okb_keypoint) * n);
@@ -1117,7 +1164,13 @@ static int ensure_io(okb_ctx* c, okb_frontend_state* F, size_t bytes) {
 static int hamming_match_impl(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, const uint8_t* skipA,
                               const uint8_t* skipB, float threshold, int num_best, int use_ratio, const okb_match_gate* gate,
                               okb_pair* out_topk, okb_pair* out_pairs) {
-  if (!c || !A || !B || nA < 1 || nB < 1 || num_best < 1 || num_best > MAX_BEST || !out_pairs) return OKB_ERR_INVALID_ARG;
+  if (!c || nA < 0 || nB < 0 || num_best < 1 || num_best > MAX_BEST || (nB > 0 && !out_pairs)) return OKB_ERR_INVALID_ARG;
+  if (nA == 0 || nB == 0) {     // an empty list matches nothing (DenseMatcher::match on an empty MatchingAlgorithm): no device work
+    for (int i = 0; i < nB; ++i) { out_pairs[i].index_a = -1; out_pairs[i].distance = threshold; }
+    if (out_topk) for (size_t i = 0; i < (size_t)nA * num_best; ++i) { out_topk[i].index_a = -1; out_topk[i].distance = threshold; }
+    return OKB_OK;
+  }
+  if (!A || !B) return OKB_ERR_INVALID_ARG;
   if (desc_bytes % 4) { c->set_error("descriptor length must be a multiple of 4"); return OKB_ERR_UNSUPPORTED; }
   const int mode = gate ? gate->mode : OKB_GATE_NONE;
   if (mode != OKB_GATE_NONE && mode != OKB_GATE_3D2D && mode != OKB_GATE_2D2D) return OKB_ERR_INVALID_ARG;
@@ -1220,7 +1273,12 @@ extern "C" int okb_hamming_match_gated(okb_ctx* c, const uint8_t* A, int nA, con
 
 extern "C" int okb_hamming_candidates(okb_ctx* c, const uint8_t* A, int nA, const uint8_t* B, int nB, int desc_bytes, float threshold,
                                       uint32_t* row_ptr, uint32_t* col_idx, uint16_t* dist, int cap) {
-  if (!c || !A || !B || nA < 1 || nB < 1 || !row_ptr || cap < 0) return OKB_ERR_INVALID_ARG;
+  if (!c || nA < 0 || nB < 0 || !row_ptr || cap < 0) return OKB_ERR_INVALID_ARG;
+  if (nA == 0 || nB == 0) {     // empty lists: empty rows, no device work
+    for (int i = 0; i <= nA; ++i) row_ptr[i] = 0;
+    return OKB_OK;
+  }
+  if (!A || !B) return OKB_ERR_INVALID_ARG;
   cudaSetDevice(c->device);
   okb_frontend_state* F = fe(c);
   std::lock_guard<std::mutex> lk(F->match_mtx);
