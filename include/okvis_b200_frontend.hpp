@@ -140,32 +140,23 @@ class DenseMatcher {
   DenseMatcher(okb_ctx* ctx, unsigned char /*numMatcherThreads*/ = 8, unsigned char numBest = 4, bool useDistanceRatioThreshold = false)
       : ctx_(ctx), numBest_(numBest), useDistanceRatioThreshold_(useDistanceRatioThreshold) {}
 
+  // DenseMatcher::match (implementation/DenseMatcher.hpp:48-122) for a matching algorithm whose distance() is the plain
+  // descriptor distance.
   template <typename MATCHING_ALGORITHM_T>
   void match(MATCHING_ALGORITHM_T& matchingAlgorithm) {
     matchingAlgorithm.doSetup();
-    const int nA = (int)matchingAlgorithm.sizeA(), nB = (int)matchingAlgorithm.sizeB();
-    if (nA == 0 || nB == 0) return;
-    std::vector<uint8_t> skipA(nA), skipB(nB);
-    for (int i = 0; i < nA; ++i) skipA[i] = matchingAlgorithm.skipA(i) ? 1 : 0;
-    for (int i = 0; i < nB; ++i) skipB[i] = matchingAlgorithm.skipB(i) ? 1 : 0;
-    std::vector<okb_pair> topk((size_t)nA * numBest_), pairs(nB);
-    const distance_t thr = matchingAlgorithm.distanceThreshold();
-    const int rc = okb_hamming_match(ctx_, matchingAlgorithm.descriptorsA(), nA, matchingAlgorithm.descriptorsB(), nB, matchingAlgorithm.descriptorBytes(),
-                                     skipA.data(), skipB.data(), thr, numBest_, 0, 0.f, topk.data(), pairs.data());
-    if (rc != OKB_OK) throw std::runtime_error(std::string("okvis_b200: ") + okb_last_error(ctx_));
-    // epilogue of matchBody (implementation/DenseMatcher.hpp:92-122), ascending B
-    matchingAlgorithm.reserveMatches((size_t)nB);
-    const distance_t ratio = matchingAlgorithm.distanceRatioThreshold();
-    for (int b = 0; b < nB; ++b) {
-      if (!(pairs[b].distance < thr)) continue;
-      if (useDistanceRatioThreshold_) {
-        const okb_pair* best = &topk[(size_t)pairs[b].index_a * numBest_];
-        if (numBest_ > 1 && best[1].index_a != -1) {
-          if (!(best[0].distance == 0 || best[1].distance / best[0].distance > ratio)) continue;
-        }
-      }
-      matchingAlgorithm.setBestMatch((size_t)pairs[b].index_a, (size_t)b, pairs[b].distance);
-    }
+    matchImpl(matchingAlgorithm, nullptr);
+  }
+
+  // The same for a geometry-gated algorithm (VioKeyframeWindowMatchingAlgorithm: distance() = Hamming AND verifyMatch,
+  // src/VioKeyframeWindowMatchingAlgorithm.cpp:304-339): the algorithm hands over what its doSetup() prepared --
+  // projections + uncertainties (3D-2D) or bearings, ray sigmas and T_AB (2D-2D) -- as an okb_match_gate through
+  // matchGate(); the gate runs on the device inside the top-k kernel (okb_hamming_match_gated).
+  template <typename MATCHING_ALGORITHM_T>
+  void matchGated(MATCHING_ALGORITHM_T& matchingAlgorithm) {
+    matchingAlgorithm.doSetup();
+    const okb_match_gate& gate = matchingAlgorithm.matchGate();
+    matchImpl(matchingAlgorithm, &gate);
   }
 
   // Candidate lists for a geometry-gated matching algorithm: every B with Hamming distance < threshold per A, ascending
@@ -185,6 +176,37 @@ class DenseMatcher {
   }
 
  private:
+  template <typename MATCHING_ALGORITHM_T>
+  void matchImpl(MATCHING_ALGORITHM_T& matchingAlgorithm, const okb_match_gate* gate) {
+    const int nA = (int)matchingAlgorithm.sizeA(), nB = (int)matchingAlgorithm.sizeB();
+    if (nA == 0 || nB == 0) return;
+    std::vector<uint8_t> skipA(nA), skipB(nB);
+    for (int i = 0; i < nA; ++i) skipA[i] = matchingAlgorithm.skipA(i) ? 1 : 0;
+    for (int i = 0; i < nB; ++i) skipB[i] = matchingAlgorithm.skipB(i) ? 1 : 0;
+    std::vector<okb_pair> topk((size_t)nA * numBest_), pairs(nB);
+    const distance_t thr = matchingAlgorithm.distanceThreshold();
+    const int rc = gate ? okb_hamming_match_gated(ctx_, matchingAlgorithm.descriptorsA(), nA, matchingAlgorithm.descriptorsB(), nB,
+                                                  matchingAlgorithm.descriptorBytes(), skipA.data(), skipB.data(), thr, numBest_, 0, 0.f, gate,
+                                                  topk.data(), pairs.data())
+                        : okb_hamming_match(ctx_, matchingAlgorithm.descriptorsA(), nA, matchingAlgorithm.descriptorsB(), nB,
+                                            matchingAlgorithm.descriptorBytes(), skipA.data(), skipB.data(), thr, numBest_, 0, 0.f, topk.data(),
+                                            pairs.data());
+    if (rc != OKB_OK) throw std::runtime_error(std::string("okvis_b200: ") + okb_last_error(ctx_));
+    // epilogue of matchBody (implementation/DenseMatcher.hpp:92-122), ascending B
+    matchingAlgorithm.reserveMatches((size_t)nB);
+    const distance_t ratio = matchingAlgorithm.distanceRatioThreshold();
+    for (int b = 0; b < nB; ++b) {
+      if (!(pairs[b].distance < thr)) continue;
+      if (useDistanceRatioThreshold_) {
+        const okb_pair* best = &topk[(size_t)pairs[b].index_a * numBest_];
+        if (numBest_ > 1 && best[1].index_a != -1) {
+          if (!(best[0].distance == 0 || best[1].distance / best[0].distance > ratio)) continue;
+        }
+      }
+      matchingAlgorithm.setBestMatch((size_t)pairs[b].index_a, (size_t)b, pairs[b].distance);
+    }
+  }
+
   okb_ctx* ctx_;
   int numBest_;
   bool useDistanceRatioThreshold_;

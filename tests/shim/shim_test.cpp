@@ -123,6 +123,37 @@ struct HammingAlgorithm {
   int descriptorBytes() const { return bytes; }
 };
 
+// The geometry-gated variant (what VioKeyframeWindowMatchingAlgorithm<...> is for matchStereo): the 2D-2D gate of a
+// rectified pair.  doSetup() of the reference back-projects the keypoints and derives the ray sigmas
+// (VioKeyframeWindowMatchingAlgorithm.cpp:236-276); here the same quantities for an undistorted pinhole.
+struct GatedStereoAlgorithm : HammingAlgorithm {
+  const std::vector<okb_keypoint>*kA, *kB;
+  okb_camera cam;
+  double baseline_x;
+  std::vector<double> xyA, xyB, szA, szB, rayA, rayB, sgA, sgB;
+  okb_match_gate gate;
+  void doSetup() {
+    HammingAlgorithm::doSetup();
+    auto fill = [&](const std::vector<okb_keypoint>& k, std::vector<double>& xy, std::vector<double>& sz, std::vector<double>& ray, std::vector<double>& sg) {
+      xy.clear(); sz.clear(); ray.clear(); sg.clear();
+      for (const auto& p : k) {
+        xy.push_back(p.x); xy.push_back(p.y); sz.push_back(p.size);
+        ray.push_back((p.x - cam.cu) / cam.fu); ray.push_back((p.y - cam.cv) / cam.fv); ray.push_back(1.0);
+        sg.push_back(std::sqrt(std::sqrt(2.0)) * (0.8 * p.size / 12.0) / cam.fu);
+      }
+    };
+    fill(*kA, xyA, szA, rayA, sgA);
+    fill(*kB, xyB, szB, rayB, sgB);
+    gate = okb_match_gate{};
+    gate.mode = OKB_GATE_2D2D;
+    gate.kp_a = xyA.data(); gate.kp_size_a = szA.data(); gate.bearing_a = rayA.data(); gate.ray_sigma_a = sgA.data();
+    gate.kp_b = xyB.data(); gate.kp_size_b = szB.data(); gate.bearing_b = rayB.data(); gate.ray_sigma_b = sgB.data();
+    gate.cam_a = cam; gate.cam_b = cam;
+    gate.T_AB[0] = baseline_x; gate.T_AB[6] = 1.0;
+  }
+  const okb_match_gate& matchGate() const { return gate; }
+};
+
 static int frontend_demo() {
   const int W = 752, H = 480, shift = 12;
   std::vector<uint8_t> base((size_t)(W + shift) * H), left((size_t)W * H), right((size_t)W * H);
@@ -153,6 +184,16 @@ static int frontend_demo() {
     const float dx = kr[m[1]].x - kl[m[0]].x, dy = kr[m[1]].y - kl[m[0]].y;
     if (std::fabs(dx - shift) < 1.5f && std::fabs(dy) < 1.5f) ++consistent;
   }
+  // gated: B sits 12 px * Z / f to the left of A for a fronto-parallel plane at Z = 5 m
+  GatedStereoAlgorithm galgo;
+  galgo.dA = &dl; galgo.dB = &dr; galgo.bytes = fe.descriptorBytes(); galgo.kA = &kl; galgo.kB = &kr; galgo.cam = cam;
+  galgo.baseline_x = -(double)shift * 5.0 / cam.fu;
+  matcher.matchGated(galgo);
+  int gated_consistent = 0;
+  for (auto& m : galgo.matches) {
+    const float dx = kr[m[1]].x - kl[m[0]].x, dy = kr[m[1]].y - kl[m[0]].y;
+    if (std::fabs(dx - shift) < 1.5f && std::fabs(dy) < 1.5f) ++gated_consistent;
+  }
   std::vector<uint32_t> rp, ci; std::vector<uint16_t> cd;
   matcher.candidates(dl.data(), nl, dr.data(), nr, fe.descriptorBytes(), 60.f, rp, ci, cd);
   double pose[7] = {0, 0, 0, 0, 0, 0, 1}, sb[9] = {0.2, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -162,8 +203,9 @@ static int frontend_demo() {
   std::vector<okb_imu_sample> smp;
   for (int64_t t = 0; t <= 210000000LL; t += 5000000LL) { okb_imu_sample m{}; m.t_ns = t; m.acc[2] = 9.81007; smp.push_back(m); }
   const bool prop = fe.propagation(smp.data(), (int)smp.size(), imu, pose, sb, 5000000LL, 205000000LL, nullptr, nullptr);
-  std::printf("{\"keypoints\": [%d, %d], \"matches\": %zu, \"consistent\": %d, \"candidates\": %zu, \"propagated_x\": %.6f, \"propagation_ok\": %d, "
-              "\"initialized\": %d}\n", nl, nr, algo.matches.size(), consistent, ci.size(), pose[0], prop ? 1 : 0, fe.isInitialized() ? 1 : 0);
+  std::printf("{\"keypoints\": [%d, %d], \"matches\": %zu, \"consistent\": %d, \"gated_matches\": %zu, \"gated_consistent\": %d, \"candidates\": %zu, "
+              "\"propagated_x\": %.6f, \"propagation_ok\": %d, \"initialized\": %d}\n", nl, nr, algo.matches.size(), consistent, galgo.matches.size(),
+              gated_consistent, ci.size(), pose[0], prop ? 1 : 0, fe.isInitialized() ? 1 : 0);
   return 0;
 }
 

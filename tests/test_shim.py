@@ -76,4 +76,7 @@ def test_frontend_and_dense_matcher_shims():
     assert min(r["keypoints"]) > 100 and r["initialized"] == 1
     assert r["matches"] > 60 and r["consistent"] >= 0.7 * r["matches"]     # the blocky texture repeats: some corners are ambiguous
     assert r["candidates"] >= r["matches"]
+    # the 2D-2D gate (matchGated): what survives is geometrically consistent, and the consistent matches survive
+    assert r["gated_matches"] > 60 and r["gated_consistent"] >= 0.95 * r["gated_matches"]
+    assert r["gated_consistent"] >= r["consistent"] - 3
     assert r["propagation_ok"] == 1 and abs(r["propagated_x"] - 0.2 * 0.2) < 1e-6     # 0.2 m/s for 0.2 s
