@@ -1123,6 +1123,18 @@ static int plan_rounds(okb_ctx* c, int first, int count, RoundPlan& P) {
     P.smS = std::max(P.smS, smemS_bytes(W.d, W.dc, W.K, W.marg_n, W.n_imu, chol_smem));
   }
   if (P.smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
+  if (const char* force = getenv("OKB_SOLVE_MODE")) {      // diagnostics / tests: a more modest solve_mode than the windows need (2 or 0)
+    const int m = atoi(force);
+    if ((m == 0 || m == 2) && chol_smem != 0 && !(chol_smem == 2 && m == 2)) {
+      chol_smem = m;
+      P.smS = 0;
+      for (int i = first; i < first + count; ++i) {
+        const WinDev& W = c->host[i];
+        P.smS = std::max(P.smS, smemS_bytes(W.d, W.dc, W.K, W.marg_n, W.n_imu, chol_smem));
+      }
+      if (P.smS > (size_t)c->smem_optin) { c->set_error("window does not fit kernel S shared memory"); return OKB_ERR_CAPACITY; }
+    }
+  }
   P.acc_copies = acc_copies; P.chol_smem = chol_smem;
   P.solve_threads = (2 * count <= c->sm_count) ? 512 : S_THREADS;      // few windows: one wide CTA per SM (all ranks of a sharded window choose alike)
   P.gxQ = std::max(1, std::min((maxL + 127) / 128, (4 * c->sm_count + count - 1) / count));

@@ -106,3 +106,4 @@ def test_window_without_imu_terms(ctx, oracle):
     pp[1]["sqrt_info"] = np.diag([1e2] * 6).reshape(-1)
     wv = dataclasses.replace(w, imu_terms=w.imu_terms[:0].copy(), imu_samples=w.imu_samples[:1].copy(), sb_priors=sp, pose_priors=pp)
     compare(ctx, oracle, wv)
+
