@@ -2,8 +2,9 @@
 // (A ascending; the reference's 4-thread execution is order dependent under ties):
 //   matchBody / doWorkLinearMatching / listBIteration  okvis_matcher/include/okvis/implementation/DenseMatcher.hpp:48-225
 //   assignbest                                         okvis_matcher/src/DenseMatcher.cpp:69-110
-// PINNED by the reference's two known-answer tests (okvis_matcher/test/testMatcher.cpp:69-155),
-// reproduced in tests/test_matcher_oracle.py.
+// PINNED by the reference's two known-answer tests (okvis_matcher/test/testMatcher.cpp:69-155, tests/test_oracle_matcher.py)
+// and by the reference ITSELF: okvis_matcher compiled unmodified from /root/reference (oracle/Makefile.ref ->
+// oracle/_ref/libokvis_matcher_ref.so), bit-exact on random tie-heavy inputs (tests/test_oracle_vs_reference_matcher.py).
 #pragma once
 #include <cstdint>
 #include <functional>
