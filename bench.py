@@ -176,6 +176,30 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def reference_matcher_us(A, B, threads=4, reps=5):
+    """Host time of the REFERENCE's DenseMatcher::match (oracle/_ref/libokvis_matcher_ref.so: okvis_matcher's own sources,
+    oracle/Makefile.ref) on two descriptor lists with the frontend's 4 matcher threads (Frontend.cpp:80); None if the
+    library did not travel.  Test-infrastructure code on the cpu_baseline side of the bench only."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libokvis_matcher_ref.so")
+    if not os.path.exists(so) or len(A) == 0 or len(B) == 0:
+        return None
+    try:
+        lib = C.CDLL(so)
+        A = np.ascontiguousarray(A, np.uint8)
+        B = np.ascontiguousarray(B, np.uint8)
+        oa, od = np.zeros(len(B), np.int32), np.zeros(len(B), np.float32)
+        args = (C.c_void_p(A.ctypes.data), len(A), C.c_void_p(B.ctypes.data), len(B), A.shape[1], C.c_float(60.0), 4, threads,
+                C.c_void_p(oa.ctypes.data), C.c_void_p(od.ctypes.data))
+        lib.okr_match_hamming(*args)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            lib.okr_match_hamming(*args)
+        return (time.perf_counter() - t0) * 1e6 / reps
+    except Exception:
+        return None
+
+
 def frontend_leg(ctx, cam, rank=0, world=1, with_cpu=True):
     """Secondary measurement (north_star rows S-V, BASELINE.json configs[2]): keypoint detect/describe and the all-pairs
     Hamming matcher through the C-ABI with host buffers (host clock, copies included), next to the CPU oracle on a
@@ -220,6 +244,9 @@ def frontend_leg(ctx, cam, rank=0, world=1, with_cpu=True):
             for _ in range(3):
                 op.match_hamming(dl, dr)
             o["cpu_oracle_hamming_match_us"] = (time.perf_counter() - t0) * 1e6 / 3
+            ref_us = reference_matcher_us(dl, dr)
+            if ref_us is not None:       # the reference's own DenseMatcher (oracle/_ref, okvis_matcher compiled unmodified), 4 matcher threads
+                o["cpu_reference_hamming_match_us"] = ref_us
         out[tag] = o
     rng = np.random.Generator(np.random.PCG64(5))
     A = rng.integers(0, 256, (1000, 48), dtype=np.uint8)
